@@ -1,0 +1,296 @@
+// Context, scratch memory, NCCL plumbing (dlopen), operator dispatch and the micro-benchmarks of libcggp_b200.
+#include <dlfcn.h>
+
+#include <cstring>
+
+#include "common.cuh"
+#include "kmath.cuh"
+
+int cggp_matvec_simple(cggp_ctx* ctx, int dtype, int kind, double variance, const void* PX, const void* nX, int64_t n,
+                       const void* PZ, const void* nZ, int64_t m, int D, int64_t ldp, const void* V, int64_t ldv,
+                       int B, void* W, int64_t ldw, const int* active);
+int cggp_matvec_fused(cggp_ctx* ctx, int kind, double variance, const double* PX, const double* nX, int64_t n,
+                      const double* PZ, const double* nZ, int64_t m, int D, int64_t ldp, const double* V, int64_t ldv,
+                      int B, double* W, int64_t ldw, const int* active);
+bool cggp_matvec_fused_supported(cggp_ctx* ctx, int dtype, int64_t m, int D, int B);
+
+static std::string g_err;  // errors raised without a ctx
+
+extern "C" const char* cggp_version(void) { return "cggp_b200 0.1 (sm_100a)"; }
+
+extern "C" int cggp_ctx_create(int device, cggp_ctx** out) {
+  if (!out) return CGGP_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_err = std::string("no CUDA device: ") + cudaGetErrorString(e);
+    return CGGP_ERR_CUDA;  // no CPU fallback by design
+  }
+  if (device < 0 || device >= count) {
+    g_err = "device index out of range";
+    return CGGP_ERR_INVALID;
+  }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) {
+    g_err = cudaGetErrorString(e);
+    return CGGP_ERR_CUDA;
+  }
+  cggp_ctx* ctx = new cggp_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cc_major = prop.major;
+  ctx->cc_minor = prop.minor;
+  if (cudaMalloc(&ctx->cg_state, 16 * sizeof(int)) != cudaSuccess ||
+      cudaMallocHost(&ctx->cg_state_host, 16 * sizeof(int)) != cudaSuccess) {
+    g_err = "ctx allocation failed";
+    delete ctx;
+    return CGGP_ERR_CUDA;
+  }
+  cudaMemset(ctx->cg_state, 0, 16 * sizeof(int));
+  *out = ctx;
+  return CGGP_OK;
+}
+
+struct Ws2 {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+static Ws2& ws2_of(cggp_ctx* ctx) {
+  static Ws2 slots[64];
+  return slots[ctx->device % 64];
+}
+
+extern "C" int cggp_ctx_destroy(cggp_ctx* ctx) {
+  if (!ctx) return CGGP_OK;
+  cudaSetDevice(ctx->device);
+  cggp_ctx_comm_destroy(ctx);
+  if (ctx->ws) cudaFree(ctx->ws);
+  Ws2& w = ws2_of(ctx);
+  if (w.p) { cudaFree(w.p); w.p = nullptr; w.bytes = 0; }
+  if (ctx->cg_state) cudaFree(ctx->cg_state);
+  if (ctx->cg_state_host) cudaFreeHost(ctx->cg_state_host);
+  delete ctx;
+  return CGGP_OK;
+}
+
+extern "C" int cggp_ctx_set_stream(cggp_ctx* ctx, void* stream) {
+  if (!ctx) return CGGP_ERR_INVALID;
+  ctx->stream = (cudaStream_t)stream;
+  return CGGP_OK;
+}
+
+extern "C" const char* cggp_last_error(cggp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+extern "C" int64_t cggp_launch_count(cggp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int cggp_ws_reserve(cggp_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->ws_bytes) return CGGP_OK;
+  CGGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->ws) cudaFree(ctx->ws);
+  ctx->ws = nullptr;
+  ctx->ws_bytes = 0;
+  size_t want = bytes + bytes / 4 + 4096;
+  CGGP_CUDA(ctx, cudaMalloc(&ctx->ws, want));
+  ctx->ws_bytes = want;
+  return CGGP_OK;
+}
+int cggp_ws2_reserve(cggp_ctx* ctx, size_t bytes) {
+  Ws2& w = ws2_of(ctx);
+  if (bytes <= w.bytes) return CGGP_OK;
+  CGGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (w.p) cudaFree(w.p);
+  w.p = nullptr;
+  w.bytes = 0;
+  size_t want = bytes + bytes / 4 + 4096;
+  CGGP_CUDA(ctx, cudaMalloc(&w.p, want));
+  w.bytes = want;
+  return CGGP_OK;
+}
+void* cggp_ws2_ptr(cggp_ctx* ctx) { return ws2_of(ctx).p; }
+
+// ---------------------------------------------------------------------------------------------------------
+// NCCL through dlopen: the process already carries the torch-bundled libnccl.so.2; linking a second copy would
+// clash, so the five entry points are resolved at run time.
+// ---------------------------------------------------------------------------------------------------------
+struct Id128 { char b[128]; };  // layout of ncclUniqueId
+namespace {
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static NcclApi g_nccl;
+
+static int nccl_load(cggp_ctx* ctx) {
+  if (g_nccl.h) return CGGP_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* nm : names) {
+    h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD);
+    if (!h) h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) CGGP_FAIL(ctx, CGGP_ERR_COMM, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+    CGGP_FAIL(ctx, CGGP_ERR_COMM, "libnccl is missing expected symbols");
+  g_nccl.h = h;
+  return CGGP_OK;
+}
+
+extern "C" int cggp_comm_unique_id(void* host_id128) {
+  if (!host_id128) return CGGP_ERR_INVALID;
+  int rc = nccl_load(nullptr);
+  if (rc) return rc;
+  int e = g_nccl.GetUniqueId(host_id128);
+  if (e != 0) {
+    g_err = std::string("ncclGetUniqueId: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error");
+    return CGGP_ERR_COMM;
+  }
+  return CGGP_OK;
+}
+
+extern "C" int cggp_ctx_comm_init(cggp_ctx* ctx, const void* host_id128, int rank, int world) {
+  if (!ctx || !host_id128 || world < 1 || rank < 0 || rank >= world) return CGGP_ERR_INVALID;
+  cggp_ctx_comm_destroy(ctx);
+  ctx->rank = rank;
+  ctx->world = world;
+  if (world == 1) return CGGP_OK;
+  int rc = nccl_load(ctx);
+  if (rc) return rc;
+  CGGP_CUDA(ctx, cudaSetDevice(ctx->device));
+  Id128 id;
+  memcpy(id.b, host_id128, 128);
+  int e = g_nccl.CommInitRank(&ctx->comm, world, id, rank);
+  if (e != 0) CGGP_FAIL(ctx, CGGP_ERR_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error");
+  return CGGP_OK;
+}
+
+extern "C" int cggp_ctx_comm_destroy(cggp_ctx* ctx) {
+  if (!ctx) return CGGP_ERR_INVALID;
+  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  ctx->comm = nullptr;
+  ctx->world = 1;
+  ctx->rank = 0;
+  return CGGP_OK;
+}
+
+extern "C" int cggp_allreduce_sum(cggp_ctx* ctx, int dtype, void* buf, int64_t count) {
+  if (!ctx) return CGGP_ERR_INVALID;
+  if (ctx->world == 1 || count == 0) return CGGP_OK;
+  if (!ctx->comm) CGGP_FAIL(ctx, CGGP_ERR_COMM, "communicator not initialised");
+  const int nccl_dtype = dtype == CGGP_F64 ? 8 : 7;  // ncclFloat64 / ncclFloat32
+  int e = g_nccl.AllReduce(buf, buf, (size_t)count, nccl_dtype, 0 /* ncclSum */, ctx->comm, ctx->stream);
+  if (e != 0) CGGP_FAIL(ctx, CGGP_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error");
+  ctx->launches += 1;
+  return CGGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Matrix-free product dispatch
+// ---------------------------------------------------------------------------------------------------------
+int cggp_matvec_dispatch(cggp_ctx* ctx, int dtype, int kind, double variance, const void* PX, const void* nX,
+                         int64_t n, const void* PZ, const void* nZ, int64_t m, int D, int64_t ldp, const void* V,
+                         int64_t ldv, int B, void* W, int64_t ldw, int variant, const int* active) {
+  if (kind < CGGP_SE || kind > CGGP_MATERN52) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "unknown kernel kind %d", kind);
+  const bool can_fuse = cggp_matvec_fused_supported(ctx, dtype, m, D, B);
+  if (variant == 2 && !can_fuse)
+    CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "fused matvec does not support dtype=%d m=%lld D=%d B=%d", dtype,
+              (long long)m, D, B);
+  if ((variant == 0 && can_fuse) || variant == 2)
+    return cggp_matvec_fused(ctx, kind, variance, (const double*)PX, (const double*)nX, n, (const double*)PZ,
+                             (const double*)nZ, m, D, ldp, (const double*)V, ldv, B, (double*)W, ldw, active);
+  return cggp_matvec_simple(ctx, dtype, kind, variance, PX, nX, n, PZ, nZ, m, D, ldp, V, ldv, B, W, ldw, active);
+}
+
+extern "C" int cggp_kuf_kfu_matvec(cggp_ctx* ctx, int dtype, int kind, double variance, const void* PX,
+                                   const void* nX, int64_t n, const void* PZ, const void* nZ, int64_t m, int D,
+                                   int64_t ldp, const void* V, int64_t ldv, int B, void* W, int64_t ldw, int variant) {
+  if (!ctx) return CGGP_ERR_INVALID;
+  if (B <= 0 || m <= 0) return CGGP_OK;
+  if (variant < 0 || variant > 2) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "variant must be 0, 1 or 2");
+  return cggp_matvec_dispatch(ctx, dtype, kind, variance, PX, nX, n, PZ, nZ, m, D, ldp, V, ldv, B, W, ldw, variant,
+                              nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Micro-benchmarks (roofline denominators)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mb_dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__global__ void mb_kernel(int which, double* out, int iters, double s) {
+  double acc = 0;
+  if (which == 0) {
+    double a[8];
+    for (int i = 0; i < 8; ++i) a[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fma(a[i], s, 1e-9);
+    for (int i = 0; i < 8; ++i) acc += a[i];
+  } else if (which == 1 || which == 4) {
+    double c[16];
+    for (int i = 0; i < 16; ++i) c[i] = 0;
+    const double a = threadIdx.x * 1e-3;
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mb_dmma884(c[2 * i], c[2 * i + 1], a, s);
+    for (int i = 0; i < 16; ++i) acc += c[i];
+  } else if (which == 2) {
+    const FastExpTable tab = fast_exp_table();
+    double a[4];
+    for (int i = 0; i < 4; ++i) a[i] = -(threadIdx.x * 1e-2 + i);
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc += fast_exp(a[i], tab); a[i] += s; }
+  } else {
+    double a[4];
+    for (int i = 0; i < 4; ++i) a[i] = threadIdx.x * 1e-2 + i + 1;
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc += fast_sqrt_pos(a[i]); a[i] += s; }
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+extern "C" int cggp_microbench(cggp_ctx* ctx, int which, int iters, double* host_gops) {
+  if (!ctx || !host_gops || which < 0 || which > 4 || iters < 1) return CGGP_ERR_INVALID;
+  const int nb = ctx->sm_count * 8, nt = 256;
+  int rc = cggp_ws_reserve(ctx, sizeof(double) * nb * nt);
+  if (rc) return rc;
+  cudaEvent_t e0, e1;
+  CGGP_CUDA(ctx, cudaEventCreate(&e0));
+  CGGP_CUDA(ctx, cudaEventCreate(&e1));
+  const double s = (which == 0 || which == 1 || which == 4) ? 0.999 : 1e-6;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, ctx->stream);
+    mb_kernel<<<nb, nt, 0, ctx->stream>>>(which, (double*)ctx->ws, iters, s);
+    cudaEventRecord(e1, ctx->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+    ctx->launches += 1;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  CGGP_CUDA(ctx, cudaGetLastError());
+  const double threads = (double)nb * nt;
+  double ops;
+  if (which == 0) ops = threads * iters * 8 * 2.0;
+  else if (which == 1 || which == 4) ops = (threads / 32) * iters * 8 * (8 * 8 * 4 * 2.0);
+  else ops = threads * iters * 4.0;
+  *host_gops = ops / (best * 1e-3) / 1e9;
+  return CGGP_OK;
+}

@@ -1,0 +1,457 @@
+// Conjugate gradient: fused vector update kernels + device-resident loop (cggp/conjugate_gradient.py:24-122).
+//
+// Per iteration the reference runs ~10 un-fused TF kernels over the [B, n] state plus a host round trip for the
+// while_loop predicate.  Here one kernel (one CTA per right-hand side; all dot products of that row are CTA-local,
+// deterministic) does:  denom = sum p*pA; gamma; v += gamma p; r -= gamma pA; (z, rz') = precond(r);
+// p = z + p rz'/rz; 0.5|r|^2  -- and the last CTA to finish evaluates the stopping condition for the whole batch,
+// appends the residual history row and advances the device-side iteration counter / active flag.  Kernels enqueued
+// after termination see active == 0 and return immediately, so the host never synchronises inside the loop.
+//
+// Rounding follows the reference op by op where it is cheap to do so (separate multiply and add, (p*rz')/rz with a
+// true division, guards `<= 1e-16 -> 0`), so trajectories differ from the TF path only through summation order.
+#include <vector>
+
+#include "common.cuh"
+
+int cggp_symm_matmul_ex(cggp_ctx* ctx, int dtype, const void* A, int64_t lda, int64_t n, const void* V, int64_t ldv,
+                        int B, void* Y, int64_t ldy, const void* addend, int64_t ldadd, double scale,
+                        const int* active);
+int cggp_matvec_dispatch(cggp_ctx* ctx, int dtype, int kind, double variance, const void* PX, const void* nX,
+                         int64_t n, const void* PZ, const void* nZ, int64_t m, int D, int64_t ldp, const void* V,
+                         int64_t ldv, int B, void* W, int64_t ldw, int variant, const int* active);
+int cggp_ws2_reserve(cggp_ctx* ctx, size_t bytes);
+void* cggp_ws2_ptr(cggp_ctx* ctx);
+
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+
+enum { MODE_STEP = 0, MODE_PRE = 1, MODE_POST = 2, MODE_INIT = 3 };
+
+template <typename T>
+struct StepArgs {
+  int mode;
+  int B;
+  int64_t n;
+  const T* q;    // pA (MODE_STEP / MODE_PRE) or vA (MODE_POST / MODE_INIT)
+  const T* rhs;  // b (MODE_POST / MODE_INIT)
+  T* v;
+  T* r;
+  T* p;
+  T* z;          // scratch for the block preconditioner (nullptr for Eye)
+  T* rz;         // [B]
+  T* half_rr;    // [B] 0.5 |r|^2
+  T* half_rz;    // [B] 0.5 rz (stats_error), may be nullptr
+  T* history;    // [cap, B] or nullptr
+  int64_t history_cap;
+  T threshold;
+  int max_iterations;
+  int* state;    // [0] active [1] iteration [2] ticket; nullptr = stand-alone step (no loop control)
+  // block preconditioner
+  int num_blocks, block_size;
+  const int64_t* block_idx;
+  const T* chol;
+};
+
+constexpr int MAX_BS = 64;
+
+// z[blk] = (L L^T)^-1 r[blk] for the blocks of this row; one thread per block (blocks are small and independent)
+template <typename T>
+__device__ void block_precond_apply(const StepArgs<T>& a, const T* __restrict__ r, T* __restrict__ z) {
+  for (int blk = threadIdx.x; blk < a.num_blocks; blk += blockDim.x) {
+    const int bs = a.block_size;
+    const int64_t* idx = a.block_idx + (int64_t)blk * bs;
+    const T* L = a.chol + (int64_t)blk * bs * bs;
+    T y[MAX_BS];
+    for (int i = 0; i < bs; ++i) {
+      T s = r[idx[i]];
+      for (int k = 0; k < i; ++k) s -= L[i * bs + k] * y[k];
+      y[i] = s / L[i * bs + i];
+    }
+    for (int i = bs - 1; i >= 0; --i) {
+      T s = y[i];
+      for (int k = i + 1; k < bs; ++k) s -= L[k * bs + i] * y[k];
+      y[i] = s / L[i * bs + i];
+    }
+    for (int i = 0; i < bs; ++i) z[idx[i]] = y[i];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) cg_step_kernel(const StepArgs<T> a) {
+  if (a.state && a.state[0] == 0) return;
+  __shared__ T red[33];
+  __shared__ int s_last;
+  const int b = blockIdx.x;
+  const int64_t n = a.n;
+  const T* q = a.q + (int64_t)b * n;
+  T* v = a.v + (int64_t)b * n;
+  T* r = a.r + (int64_t)b * n;
+  T* p = a.p + (int64_t)b * n;
+  T* z = a.z ? a.z + (int64_t)b * n : nullptr;
+  const T min_float = T(1e-16);  // conjugate_gradient.py:50 (1e-16 also for float32)
+  T gamma = T(0);
+  const T rz_old = (a.mode == MODE_STEP || a.mode == MODE_PRE) ? a.rz[b] : T(0);
+
+  if (a.mode == MODE_STEP || a.mode == MODE_PRE) {
+    T part = T(0);
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) part = add_rn(part, mul_rn(p[k], q[k]));
+    const T denom = block_sum(part, red);              // :66
+    gamma = denom <= min_float ? T(0) : div_rn(rz_old, denom);  // :67-68
+  }
+  if (a.mode == MODE_PRE) {  // reset iteration, first half: only v is updated (:69); r is recomputed from b - v@A
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) v[k] = add_rn(v[k], mul_rn(gamma, p[k]));
+    return;
+  }
+
+  T rr_part = T(0);
+  if (a.mode == MODE_STEP) {
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) {
+      const T pk = p[k], qk = q[k];
+      v[k] = add_rn(v[k], mul_rn(gamma, pk));          // :69
+      const T rk = add_rn(r[k], -mul_rn(gamma, qk));   // :75
+      r[k] = rk;
+      rr_part = add_rn(rr_part, mul_rn(rk, rk));
+    }
+  } else {  // MODE_POST / MODE_INIT: r = b - v@A (:74, :88)
+    const T* rhs = a.rhs + (int64_t)b * n;
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) {
+      const T rk = add_rn(rhs[k], -q[k]);
+      r[k] = rk;
+      rr_part = add_rn(rr_part, mul_rn(rk, rk));
+    }
+  }
+  const T rr = block_sum(rr_part, red);
+  T rz_new = rr;  // EyePreconditioner (:131-134): z = r, rz = sum r^2
+  const T* zsrc = r;
+  if (a.num_blocks > 0) {  // BlockPreconditioner (intent of :137-157)
+    __syncthreads();       // r of this row is complete in global memory (same CTA wrote it)
+    block_precond_apply(a, r, z);
+    __syncthreads();
+    T zp = T(0);
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) zp = add_rn(zp, mul_rn(z[k], r[k]));
+    rz_new = block_sum(zp, red);  // :157
+    zsrc = z;
+  }
+  if (a.mode == MODE_STEP) {
+    const bool dead = rz_old <= min_float;  // :79
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) {
+      const T upd = dead ? T(0) : div_rn(mul_rn(p[k], rz_new), rz_old);  // :78  (p * new_rz) / rz
+      p[k] = add_rn(zsrc[k], upd);                                       // :83
+    }
+  } else {
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) p[k] = zsrc[k];  // :82 / :90
+  }
+  const T half = T(0.5) * rr;
+  if (threadIdx.x == 0) {
+    a.rz[b] = rz_new;
+    a.half_rr[b] = half;
+    if (a.half_rz) a.half_rz[b] = T(0.5) * rz_new;  // :97
+  }
+  if (!a.state) return;
+  // ---- loop control by the last CTA of this launch (stopping condition :59-62) ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&a.state[2], 1) == a.B - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int it = (a.mode == MODE_INIT) ? 0 : a.state[1] + 1;
+  int over = 0;
+  const volatile T* hr = a.half_rr;
+  for (int k = threadIdx.x; k < a.B; k += blockDim.x) {
+    const T h = hr[k];
+    if (h > a.threshold) over = 1;
+    if (a.history && it < a.history_cap) a.history[(int64_t)it * a.B + k] = h;
+  }
+  over = __syncthreads_or(over);
+  if (threadIdx.x == 0) {
+    a.state[1] = it;
+    a.state[2] = 0;
+    a.state[0] = (over && it < a.max_iterations) ? 1 : 0;
+  }
+}
+
+template <typename T>
+static int launch_step(cggp_ctx* ctx, const StepArgs<T>& a) {
+  cg_step_kernel<T><<<a.B, 512, 0, ctx->stream>>>(a);
+  CGGP_LAUNCH_CHECK(ctx);
+  return CGGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Block-Jacobi factorisation: one CTA per block, in-place right-looking Cholesky in shared memory.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void block_cholesky_kernel(const T* __restrict__ A, int64_t lda, const int64_t* __restrict__ idx, int bs,
+                                      T* __restrict__ chol) {
+  __shared__ T s[MAX_BS][MAX_BS + 1];
+  const int blk = blockIdx.x;
+  const int64_t* id = idx + (int64_t)blk * bs;
+  for (int e = threadIdx.x; e < bs * bs; e += blockDim.x) {
+    const int i = e / bs, j = e % bs;
+    s[i][j] = A[id[i] * lda + id[j]];
+  }
+  __syncthreads();
+  for (int k = 0; k < bs; ++k) {
+    if (threadIdx.x == 0) s[k][k] = sqrt(s[k][k]);
+    __syncthreads();
+    for (int i = k + 1 + threadIdx.x; i < bs; i += blockDim.x) s[i][k] /= s[k][k];
+    __syncthreads();
+    for (int e = threadIdx.x; e < (bs - k - 1) * (bs - k - 1); e += blockDim.x) {
+      const int i = k + 1 + e / (bs - k - 1), j = k + 1 + e % (bs - k - 1);
+      if (j <= i) s[i][j] -= s[i][k] * s[j][k];
+    }
+    __syncthreads();
+  }
+  T* L = chol + (int64_t)blk * bs * bs;
+  for (int e = threadIdx.x; e < bs * bs; e += blockDim.x) {
+    const int i = e / bs, j = e % bs;
+    L[e] = j <= i ? s[i][j] : T(0);
+  }
+}
+
+extern "C" int cggp_block_cholesky(cggp_ctx* ctx, int dtype, const void* A, int64_t lda, int64_t n,
+                                   const int64_t* idx, int num_blocks, int block_size, void* chol) {
+  if (!ctx) return CGGP_ERR_INVALID;
+  if (block_size < 1 || block_size > MAX_BS)
+    CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "block_size %d outside [1, %d]", block_size, MAX_BS);
+  if ((int64_t)num_blocks * block_size != n)
+    CGGP_FAIL(ctx, CGGP_ERR_INVALID, "blocks (%d x %d) must partition n=%lld", num_blocks, block_size, (long long)n);
+  if (dtype == CGGP_F64)
+    block_cholesky_kernel<double><<<num_blocks, 256, 0, ctx->stream>>>((const double*)A, lda, idx, block_size,
+                                                                      (double*)chol);
+  else
+    block_cholesky_kernel<float><<<num_blocks, 256, 0, ctx->stream>>>((const float*)A, lda, idx, block_size,
+                                                                     (float*)chol);
+  CGGP_LAUNCH_CHECK(ctx);
+  return CGGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+static void fill_precond(StepArgs<T>& a, const cggp_precond* pc) {
+  a.num_blocks = 0;
+  a.block_size = 0;
+  a.block_idx = nullptr;
+  a.chol = nullptr;
+  if (pc && pc->type == CGGP_PRECOND_BLOCK) {
+    a.num_blocks = pc->num_blocks;
+    a.block_size = pc->block_size;
+    a.block_idx = pc->dev_block_indices;
+    a.chol = (const T*)pc->dev_chol;
+  }
+}
+
+static int check_precond(cggp_ctx* ctx, const cggp_precond* pc, int64_t n) {
+  if (!pc || pc->type == CGGP_PRECOND_EYE) return CGGP_OK;
+  if (pc->type != CGGP_PRECOND_BLOCK) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "unknown preconditioner type %d", pc->type);
+  if (pc->block_size < 1 || pc->block_size > MAX_BS)
+    CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "block_size %d outside [1, %d]", pc->block_size, MAX_BS);
+  if ((int64_t)pc->num_blocks * pc->block_size != n)
+    CGGP_FAIL(ctx, CGGP_ERR_INVALID, "block preconditioner must partition n");
+  if (!pc->dev_block_indices || !pc->dev_chol) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "block preconditioner buffers missing");
+  return CGGP_OK;
+}
+
+template <typename T>
+static int fused_step_impl(cggp_ctx* ctx, int B, int64_t n, const void* pA, void* v, void* r, void* p, void* rz,
+                           void* half_rr, const cggp_precond* pc) {
+  StepArgs<T> a{};
+  a.mode = MODE_STEP;
+  a.B = B;
+  a.n = n;
+  a.q = (const T*)pA;
+  a.v = (T*)v;
+  a.r = (T*)r;
+  a.p = (T*)p;
+  a.rz = (T*)rz;
+  a.half_rr = (T*)half_rr;
+  fill_precond(a, pc);
+  if (a.num_blocks > 0) {
+    int rc = cggp_ws2_reserve(ctx, sizeof(T) * (size_t)B * n);
+    if (rc) return rc;
+    a.z = (T*)cggp_ws2_ptr(ctx);
+  }
+  return launch_step(ctx, a);
+}
+
+extern "C" int cggp_cg_fused_step(cggp_ctx* ctx, int dtype, int B, int64_t n, const void* pA, void* v, void* r,
+                                  void* p, void* rz, void* half_rr, const cggp_precond* pc) {
+  if (!ctx) return CGGP_ERR_INVALID;
+  if (B <= 0 || n <= 0) return CGGP_OK;
+  int rc = check_precond(ctx, pc, n);
+  if (rc) return rc;
+  if (dtype == CGGP_F64) return fused_step_impl<double>(ctx, B, n, pA, v, r, p, rz, half_rr, pc);
+  return fused_step_impl<float>(ctx, B, n, pA, v, r, p, rz, half_rr, pc);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Operator application  Y = V @ A  for the two operator forms
+// ---------------------------------------------------------------------------------------------------------
+static int apply_operator(cggp_ctx* ctx, const cggp_operator* op, const void* V, int B, void* Y, void* wbuf,
+                          const int* active) {
+  const int64_t n = op->n;
+  if (op->type == CGGP_OP_DENSE)
+    return cggp_symm_matmul_ex(ctx, op->dtype, op->dev_A, op->lda, n, V, n, B, Y, n, nullptr, 0, 0.0, active);
+  // W = V @ (Kuf_r Kfu_r) on this rank's shard
+  int rc = cggp_matvec_dispatch(ctx, op->dtype, op->kind, op->variance, op->dev_PX, op->dev_normsX, op->n_local,
+                                op->dev_PZ, op->dev_normsZ, n, op->D, op->ldp, V, n, B, wbuf, n, op->variant, active);
+  if (rc) return rc;
+  // the one collective of the path: sum the partial [B, M] products over ranks
+  rc = cggp_allreduce_sum(ctx, op->dtype, wbuf, (int64_t)B * n);
+  if (rc) return rc;
+  // Y = V @ Kuu + scale * W
+  return cggp_symm_matmul_ex(ctx, op->dtype, op->dev_A, op->lda, n, V, n, B, Y, n, wbuf, n, op->scale, active);
+}
+
+template <typename T>
+static int cg_solve_impl(cggp_ctx* ctx, const cggp_operator* op, const void* rhs, const void* x0, int B,
+                         double error_threshold, int max_iterations, int max_steps_cycle, const cggp_precond* pc,
+                         int check_every, void* solution, int32_t* host_steps, void* half_rz, void* history,
+                         int64_t history_cap) {
+  const int64_t n = op->n;
+  const size_t vec = sizeof(T) * (size_t)B * n;
+  const bool block = pc && pc->type == CGGP_PRECOND_BLOCK;
+  const bool sgpr = op->type == CGGP_OP_SGPR;
+  // r, p, q (+ z) (+ w) and the per-row scalars
+  size_t need = vec * (3 + (block ? 1 : 0) + (sgpr ? 1 : 0)) + sizeof(T) * 3 * (size_t)B + 256;
+  int rc = cggp_ws2_reserve(ctx, need);
+  if (rc) return rc;
+  char* base = (char*)cggp_ws2_ptr(ctx);
+  T* r = (T*)base; base += vec;
+  T* p = (T*)base; base += vec;
+  T* q = (T*)base; base += vec;
+  T* z = nullptr;
+  if (block) { z = (T*)base; base += vec; }
+  T* w = nullptr;
+  if (sgpr) { w = (T*)base; base += vec; }
+  T* rz = (T*)base; base += sizeof(T) * B;
+  T* half_rr = (T*)base; base += sizeof(T) * B;
+  T* half_rz_int = (T*)base; base += sizeof(T) * B;
+  T* v = (T*)solution;
+  T* hrz = half_rz ? (T*)half_rz : half_rz_int;
+
+  int* st = ctx->cg_state;
+  ctx->cg_state_host[0] = 1;
+  ctx->cg_state_host[1] = 0;
+  ctx->cg_state_host[2] = 0;
+  CGGP_CUDA(ctx, cudaMemcpyAsync(st, ctx->cg_state_host, 3 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CGGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the pinned staging buffer is reused below
+
+  StepArgs<T> a{};
+  a.B = B;
+  a.n = n;
+  a.rhs = (const T*)rhs;
+  a.v = v;
+  a.r = r;
+  a.p = p;
+  a.z = z;
+  a.rz = rz;
+  a.half_rr = half_rr;
+  a.half_rz = hrz;
+  a.history = (T*)history;
+  a.history_cap = history ? history_cap : 0;
+  a.threshold = (T)error_threshold;
+  a.max_iterations = max_iterations;
+  a.state = st;
+  fill_precond(a, pc);
+
+  // init (:87-92): r = b - v@A, (z, rz) = precond(r), p = z, i = 0
+  if (x0) {
+    CGGP_CUDA(ctx, cudaMemcpyAsync(v, x0, vec, cudaMemcpyDeviceToDevice, ctx->stream));
+    rc = apply_operator(ctx, op, v, B, q, w, nullptr);
+    if (rc) return rc;
+  } else {
+    // v = 0: v@A is exactly 0 for finite A, so the product is skipped (b - 0 == b bit for bit)
+    CGGP_CUDA(ctx, cudaMemsetAsync(v, 0, vec, ctx->stream));
+    CGGP_CUDA(ctx, cudaMemsetAsync(q, 0, vec, ctx->stream));
+  }
+  a.mode = MODE_INIT;
+  a.q = q;
+  rc = launch_step(ctx, a);
+  if (rc) return rc;
+
+  if (check_every < 1) check_every = 16;
+  cudaEvent_t ev[2];
+  CGGP_CUDA(ctx, cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+  CGGP_CUDA(ctx, cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  int* hstage = ctx->cg_state_host;  // [0..2] chunk A, [4..6] chunk B
+  int enq = 0;                       // iterations enqueued so far
+  int chunk = 0;
+  bool done = false;
+  int pending[2] = {0, 0};
+  while (!done) {
+    const int slot = chunk & 1;
+    // enqueue one chunk of iterations (skipped on the device once inactive)
+    for (int c = 0; c < check_every && enq < max_iterations; ++c, ++enq) {
+      const bool reset = (enq % max_steps_cycle) == (max_steps_cycle - 1);  // :71, pre-increment i
+      rc = apply_operator(ctx, op, p, B, q, w, st);
+      if (rc) goto fail;
+      a.q = q;
+      if (!reset) {
+        a.mode = MODE_STEP;
+        rc = launch_step(ctx, a);
+        if (rc) goto fail;
+      } else {
+        a.mode = MODE_PRE;
+        rc = launch_step(ctx, a);
+        if (rc) goto fail;
+        rc = apply_operator(ctx, op, v, B, q, w, st);
+        if (rc) goto fail;
+        a.mode = MODE_POST;
+        rc = launch_step(ctx, a);
+        if (rc) goto fail;
+      }
+    }
+    {
+      cudaError_t e = cudaMemcpyAsync(hstage + 4 * slot, st, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaEventRecord(ev[slot], ctx->stream);
+      if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = CGGP_ERR_CUDA; goto fail; }
+      pending[slot] = 1;
+    }
+    // look at the PREVIOUS chunk's flag while this one runs (keeps the GPU fed)
+    const int prev = slot ^ 1;
+    if (pending[prev]) {
+      cudaError_t e = cudaEventSynchronize(ev[prev]);
+      if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = CGGP_ERR_CUDA; goto fail; }
+      pending[prev] = 0;
+      if (hstage[4 * prev] == 0) done = true;
+    }
+    if (enq >= max_iterations) done = true;
+    ++chunk;
+  }
+  {
+    cudaError_t e = cudaMemcpyAsync(hstage, st, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = CGGP_ERR_CUDA; goto fail; }
+    if (host_steps) *host_steps = hstage[1];
+  }
+  rc = CGGP_OK;
+fail:
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
+  return rc;
+}
+
+extern "C" int cggp_cg_solve(cggp_ctx* ctx, const cggp_operator* op, const void* rhs, const void* x0, int B,
+                             double error_threshold, int max_iterations, int max_steps_cycle, const cggp_precond* pc,
+                             int check_every, void* solution, int32_t* host_steps, void* half_rz, void* history,
+                             int64_t history_cap) {
+  if (!ctx) return CGGP_ERR_INVALID;
+  if (!op || !rhs || !solution) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "null operator / rhs / solution");
+  if (B <= 0 || op->n <= 0) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "empty system (B=%d, n=%lld)", B, (long long)op->n);
+  if (max_steps_cycle < 1) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "max_steps_cycle must be >= 1");
+  if (max_iterations < 0) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "max_iterations must be >= 0");
+  if (op->type != CGGP_OP_DENSE && op->type != CGGP_OP_SGPR) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "bad operator type");
+  int rc = check_precond(ctx, pc, op->n);
+  if (rc) return rc;
+  if (op->dtype == CGGP_F64)
+    return cg_solve_impl<double>(ctx, op, rhs, x0, B, error_threshold, max_iterations, max_steps_cycle, pc,
+                                 check_every, solution, host_steps, half_rz, history, history_cap);
+  return cg_solve_impl<float>(ctx, op, rhs, x0, B, error_threshold, max_iterations, max_steps_cycle, pc, check_every,
+                              solution, host_steps, half_rz, history, history_cap);
+}

@@ -1,0 +1,83 @@
+// Shared definitions of libcggp_b200: context, error handling, dtype dispatch, reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <string>
+
+#include "../../include/cggp_b200.h"
+
+struct cggp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  int sm_count = 148;
+  int cc_major = 0, cc_minor = 0;
+  // scratch owned by the ctx (grown on demand, freed at destroy)
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  // device-side CG loop state: [0]=active, [1]=iteration, [2]=ticket
+  int* cg_state = nullptr;
+  int* cg_state_host = nullptr;  // pinned
+  // NCCL (dlopen'ed)
+  void* comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+#define CGGP_FAIL(ctx, code, ...)                       \
+  do {                                                  \
+    char _buf[512];                                     \
+    snprintf(_buf, sizeof(_buf), __VA_ARGS__);          \
+    if (ctx) (ctx)->err = _buf;                         \
+    return (code);                                      \
+  } while (0)
+
+#define CGGP_CUDA(ctx, expr)                                                                          \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      CGGP_FAIL(ctx, CGGP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                __LINE__);                                                                            \
+  } while (0)
+
+#define CGGP_LAUNCH_CHECK(ctx)                \
+  do {                                        \
+    (ctx)->launches += 1;                     \
+    CGGP_CUDA(ctx, cudaPeekAtLastError());    \
+  } while (0)
+
+int cggp_ws_reserve(cggp_ctx* ctx, size_t bytes);
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Deterministic block-wide sum (fixed order); every thread gets the result.  `red` has >= 33 elements.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect `red` from a previous use
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    T s = lane < nw ? red[lane] : T(0);
+    s = warp_sum(s);
+    if (lane == 0) red[32] = s;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+// Kernels inside the CG loop skip their work once the device-side loop has terminated.
+__device__ __forceinline__ bool cg_inactive(const int* active) { return active != nullptr && *active == 0; }
+
+struct LsParam {
+  double v[128];
+  int count;
+};

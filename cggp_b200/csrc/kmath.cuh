@@ -1,0 +1,137 @@
+// Stationary-kernel arithmetic (GPflow K_r2 / K_r; see include/cggp_b200.h for the reference call sites).
+//   SE        : v * exp(-0.5 r2)                          (no clamp: GPflow SquaredExponential.K_r2)
+//   Matern-1/2: r = sqrt(max(r2, 1e-36)); v * exp(-r)
+//   Matern-3/2: v * (1 + sqrt3 r) * exp(-sqrt3 r)
+//   Matern-5/2: v * (1 + sqrt5 r + 5/3 r^2) * exp(-sqrt5 r)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/cggp_b200.h"
+
+template <typename T>
+struct KConst;
+template <>
+struct KConst<double> {
+  static __device__ __forceinline__ double sqrt3() { return 1.7320508075688772; }
+  static __device__ __forceinline__ double sqrt5() { return 2.23606797749979; }
+  static __device__ __forceinline__ double c53() { return 5.0 / 3.0; }
+  static __device__ __forceinline__ double clamp() { return 1e-36; }
+};
+template <>
+struct KConst<float> {
+  // float32 casts of the float64 constants, as GPflow builds them in the default float
+  static __device__ __forceinline__ float sqrt3() { return 1.7320508075688772f; }
+  static __device__ __forceinline__ float sqrt5() { return 2.23606797749979f; }
+  static __device__ __forceinline__ float c53() { return (float)(5.0 / 3.0); }
+  static __device__ __forceinline__ float clamp() { return 1e-36f; }
+};
+
+__device__ __forceinline__ double xexp(double x) { return exp(x); }
+__device__ __forceinline__ float xexp(float x) { return expf(x); }
+__device__ __forceinline__ double xsqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float xsqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ double xmax(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float xmax(float a, float b) { return fmaxf(a, b); }
+
+// Library-math kernel value (1-ulp exp / correctly rounded sqrt): the accuracy baseline of the library.
+template <typename T, int KIND>
+__device__ __forceinline__ T kernel_value(T r2, T variance) {
+  if (KIND == CGGP_SE) {
+    return variance * xexp(T(-0.5) * r2);
+  }
+  T r = xsqrt(xmax(r2, KConst<T>::clamp()));
+  if (KIND == CGGP_MATERN12) {
+    return variance * xexp(-r);
+  } else if (KIND == CGGP_MATERN32) {
+    T s = KConst<T>::sqrt3() * r;
+    return variance * (T(1) + s) * xexp(-s);
+  } else {
+    T s = KConst<T>::sqrt5() * r;
+    return variance * (T(1) + s + KConst<T>::c53() * (r * r)) * xexp(-s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// FP64 fast path for the fused matvec kernel.  On B200 the FP64 pipe (64 DFMA/clk/SM) is the binding unit, so the
+// transcendental parts are written to minimise FP64-pipe instructions and push everything else to the ALU / SFU /
+// shuffle pipes, which issue in the gaps.
+// ---------------------------------------------------------------------------------------------------------
+
+// sqrt(u) for normal u > 0: MUFU.RSQ64H seed (2^-22.9) + two residual-corrected Newton steps: 1 DMUL + 4 DFMA.
+__device__ __forceinline__ double fast_sqrt_pos(double u) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(u));
+  // h = y / 2 by an exponent decrement on the ALU pipe (y is a normal number far from the subnormal range here)
+  double h = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));
+  double g = u * y;
+  double e = fma(-g, g, u);
+  g = fma(e, h, g);
+  e = fma(-g, g, u);
+  g = fma(e, h, g);
+  return g;
+}
+
+// exp(x) for x <= ~0 (any x in [-745, 700] works).  x*32/ln2 = n + f, n = 32 k + j:
+//   exp(x) = 2^k * 2^(j/32) * exp(d),  d = x - n ln2/32,  |d| <= ln2/64
+// 2^(j/32) comes from a 32-entry table held one entry per lane (two SHFLs, no shared memory), exp(d) from a
+// degree-5 near-minimax polynomial (|rel err| < 1e-16 on the interval).  FP64-pipe cost: 3 (reduction) + 5 (poly)
+// + 1 (table multiply) = 9 instructions; the exponent add and table indexing run on the ALU pipe.
+struct FastExpTable {
+  int hi, lo;  // this lane's entry 2^(lane/32)
+};
+__device__ __forceinline__ FastExpTable fast_exp_table() {
+  double t = exp2((double)(threadIdx.x & 31) * (1.0 / 32.0));
+  FastExpTable r;
+  r.hi = __double2hiint(t);
+  r.lo = __double2loint(t);
+  return r;
+}
+__device__ __forceinline__ double fast_exp(double x, const FastExpTable& tab) {
+  const double L2E32 = 46.16624130844682903551758979206054839765;  // 32 / ln 2
+  const double MAGIC = 6755399441055744.0;                           // 1.5 * 2^52
+  const double LN2_32 = 0.02166084939249829091928849858592451515688;
+  // clamp on the ALU pipe: for x < 0 the high word grows with |x| as an unsigned integer
+  {
+    unsigned hx = (unsigned)__double2hiint(x);
+    if (hx > 0xC0874000u) x = -744.0;  // x < -744 (0xC0874000 = high word of -744.0)
+  }
+  double t = fma(x, L2E32, MAGIC);
+  int n = __double2loint(t);
+  double nf = t - MAGIC;
+  double d = fma(nf, -LN2_32, x);
+  // minimax (Remez) coefficients of exp(d) on |d| <= ln2/64, max rel err 1.41e-16 (tools/fit_exp_poly.py)
+  double q = fma(d, 8.33337406147829918e-03, 4.16668703096581480e-02);
+  q = fma(q, d, 1.66666666664448626e-01);
+  q = fma(q, d, 4.99999999994028277e-01);
+  q = fma(q, d, 1.0);
+  q = fma(q, d, 1.0);
+  int j = n & 31;
+  int hi = __shfl_sync(0xffffffffu, tab.hi, j);
+  int lo = __shfl_sync(0xffffffffu, tab.lo, j);
+  hi += (n >> 5) << 20;  // * 2^k; stays normal for x >= -708, below that the result is < 1e-307 and flushed
+  // below x = -708 the scaled table value would leave the normal range; the true result is < 1e-307: flush to 0
+  // (integer compare on the high word: x < -708.0 <=> hi(x) > hi(-708.0) as unsigned, ALU pipe)
+  if ((unsigned)__double2hiint(x) > 0xC0862000u) { hi = 0; lo = 0; }
+  return __hiloint2double(hi, lo) * q;
+}
+
+// Fast kernel value on r2 (variance is applied by the caller once per row, not per entry).
+template <int KIND>
+__device__ __forceinline__ double kernel_value_fast_unit(double r2, const FastExpTable& tab) {
+  if (KIND == CGGP_SE) {
+    return fast_exp(-0.5 * r2, tab);
+  }
+  // max(r2, 1e-36) as a signed compare of the high words (ALU pipe; negative r2 has a negative high word)
+  double rc = (__double2hiint(r2) < 0x38754484) ? 1e-36 : r2;
+  double r = fast_sqrt_pos(rc);
+  if (KIND == CGGP_MATERN12) {
+    return fast_exp(-r, tab);
+  } else if (KIND == CGGP_MATERN32) {
+    double s = 1.7320508075688772 * r;
+    return (1.0 + s) * fast_exp(-s, tab);
+  } else {
+    double s = 2.23606797749979 * r;
+    double poly = fma(5.0 / 3.0, rc, 1.0 + s);  // r*r == rc up to one rounding
+    return poly * fast_exp(-s, tab);
+  }
+}

@@ -1,0 +1,247 @@
+// Prepared points, kernel / distance matrices, nearest-centre assignment and cluster statistics.
+// Reference behaviour: GPflow Stationary.scale + square_distance + K_r2 (call sites cggp/models.py:300,333-335),
+// cggp/distance.py:9-34, cggp/selection.py:14-32, cggp/optimize.py:50-67,88-96.
+#include "common.cuh"
+#include "kmath.cuh"
+#include "tile.cuh"
+
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void prepare_points_kernel(const T* __restrict__ X, int64_t n, int D, int64_t ldx, LsParam ls,
+                                      T* __restrict__ P, int64_t ldp, T* __restrict__ norms) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T s = T(0);
+  for (int d = 0; d < D; ++d) {
+    const T l = (T)ls.v[ls.count == 1 ? 0 : d];
+    const T v = X[i * ldx + d] / l;  // true division, as GPflow's X / lengthscales
+    P[i * ldp + d] = v;
+    s += v * v;                      // reduce_sum(square(.)) in feature order
+  }
+  for (int d = D; d < ldp; ++d) P[i * ldp + d] = T(0);
+  norms[i] = s;
+}
+
+template <typename T, int KIND>
+__device__ __forceinline__ T pair_value(int output, int distance, T acc, T na, T nb, T variance) {
+  if (output == CGGP_OUT_DISTANCE && distance == CGGP_DIST_EUCLIDEAN) return xsqrt(acc);  // acc = sum (a-b)^2
+  const T r2 = (T(-2) * acc) + (na + nb);  // GPflow: dist = -2 a.b; dist += |a|^2 + |b|^2
+  if (output == CGGP_OUT_DISTANCE && distance == CGGP_DIST_SQEUCLIDEAN) return r2;
+  const T k = kernel_value<T, KIND>(r2, variance);
+  if (output == CGGP_OUT_KERNEL) return k;
+  if (distance == CGGP_DIST_COVARIANCE) return (variance + variance) - T(2) * k;  // distance.py:21
+  return T(1) - k / xsqrt(variance * variance);                                      // distance.py:30
+}
+
+template <typename T, int KIND, int MODE>
+__global__ void __launch_bounds__(TILE_THREADS)
+kernel_matrix_kernel(const T* __restrict__ PA, const T* __restrict__ nA, int64_t n, const T* __restrict__ PB,
+                     const T* __restrict__ nB, int64_t m, int D, int64_t ldp, T variance, int output, int distance,
+                     T jitter, T* __restrict__ out, int64_t ldo) {
+  __shared__ TileSmem<T> s;
+  const int64_t row0 = (int64_t)blockIdx.y * TILE, col0 = (int64_t)blockIdx.x * TILE;
+  T acc[4][4];
+  tile_compute<T, MODE>(acc, s, PA, ldp, row0, n, PB, ldp, col0, m, D);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = row0 + ty * 4 + i;
+    if (r >= n) continue;
+    const T na = nA[r];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t c = col0 + tx * 4 + j;
+      if (c >= m) continue;
+      T v = pair_value<T, KIND>(output, distance, acc[i][j], na, nB[c], variance);
+      if (r == c) v += jitter;
+      out[r * ldo + c] = v;
+    }
+  }
+}
+
+// One CTA per 64 data rows, sweeping all centres; running (min, argmin) per row, first minimum wins (tf.argmin).
+template <typename T, int KIND, int MODE>
+__global__ void __launch_bounds__(TILE_THREADS)
+nearest_center_kernel(const T* __restrict__ PX, const T* __restrict__ nX, int64_t n, const T* __restrict__ PZ,
+                      const T* __restrict__ nZ, int64_t m, int D, int64_t ldp, T variance, int distance,
+                      int64_t* __restrict__ idx, T* __restrict__ dist) {
+  __shared__ TileSmem<T> s;
+  const int64_t row0 = (int64_t)blockIdx.x * TILE;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  T best[4];
+  int64_t bidx[4];
+  T na[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    best[i] = T(INFINITY);
+    bidx[i] = 0;
+    const int64_t r = row0 + ty * 4 + i;
+    na[i] = r < n ? nX[r] : T(0);
+  }
+  for (int64_t col0 = 0; col0 < m; col0 += TILE) {
+    T acc[4][4];
+    tile_compute<T, MODE>(acc, s, PX, ldp, row0, n, PZ, ldp, col0, m, D);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t c = col0 + tx * 4 + j;
+      if (c >= m) continue;
+      const T nb = nZ[c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const T v = pair_value<T, KIND>(CGGP_OUT_DISTANCE, distance, acc[i][j], na[i], nb, variance);
+        if (v < best[i]) {  // columns are visited in increasing order per thread: strict < keeps the first minimum
+          best[i] = v;
+          bidx[i] = c;
+        }
+      }
+    }
+  }
+  // merge the 16 tx-threads of a row (they sit in one half-warp): smaller value wins, ties -> smaller index
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const T ov = __shfl_xor_sync(0xffffffffu, best[i], o);
+      const int64_t oi = __shfl_xor_sync(0xffffffffu, bidx[i], o);
+      if (ov < best[i] || (ov == best[i] && oi < bidx[i])) {
+        best[i] = ov;
+        bidx[i] = oi;
+      }
+    }
+    const int64_t r = row0 + ty * 4 + i;
+    if (tx == 0 && r < n) {
+      idx[r] = bidx[i];
+      dist[r] = best[i];
+    }
+  }
+}
+
+template <typename T>
+__global__ void cluster_stats_kernel(const int64_t* __restrict__ idx, const T* __restrict__ y, int64_t n, int64_t m,
+                                     T* __restrict__ counts, T* __restrict__ sums) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t j = idx[i];
+  if (j < 0 || j >= m) return;
+  atomicAdd(&counts[j], T(1));
+  atomicAdd(&sums[j], y[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+#define DISPATCH_KIND(T, MODE, CALL)                                          \
+  switch (kind) {                                                             \
+    case CGGP_SE: { constexpr int K = CGGP_SE; CALL; } break;                 \
+    case CGGP_MATERN12: { constexpr int K = CGGP_MATERN12; CALL; } break;     \
+    case CGGP_MATERN32: { constexpr int K = CGGP_MATERN32; CALL; } break;     \
+    case CGGP_MATERN52: { constexpr int K = CGGP_MATERN52; CALL; } break;     \
+    default: CGGP_FAIL(ctx, CGGP_ERR_INVALID, "unknown kernel kind %d", kind); \
+  }
+
+extern "C" int64_t cggp_prepared_ld(int D) { return ((int64_t)D + 1 + 3) / 4 * 4; }
+
+extern "C" int cggp_prepare_points(cggp_ctx* ctx, int dtype, const void* X, int64_t n, int D, int64_t ldx,
+                                   const double* ls, int ls_count, void* P, int64_t ldp, void* norms) {
+  if (!ctx) return CGGP_ERR_INVALID;
+  if (D < 1 || D > 128) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "D=%d outside [1,128]", D);
+  if (ls_count != 1 && ls_count != D) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "lengthscales count %d != 1 or D", ls_count);
+  if (ldp < cggp_prepared_ld(D)) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "ldp=%lld < %lld", (long long)ldp,
+                                           (long long)cggp_prepared_ld(D));
+  if (n == 0) return CGGP_OK;
+  LsParam lp;
+  lp.count = ls_count;
+  for (int d = 0; d < ls_count; ++d) lp.v[d] = ls[d];
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  if (dtype == CGGP_F64)
+    prepare_points_kernel<double><<<blocks, threads, 0, ctx->stream>>>((const double*)X, n, D, ldx, lp, (double*)P,
+                                                                        ldp, (double*)norms);
+  else
+    prepare_points_kernel<float><<<blocks, threads, 0, ctx->stream>>>((const float*)X, n, D, ldx, lp, (float*)P, ldp,
+                                                                       (float*)norms);
+  CGGP_LAUNCH_CHECK(ctx);
+  return CGGP_OK;
+}
+
+template <typename T>
+static int kernel_matrix_impl(cggp_ctx* ctx, int kind, double variance, int output, int distance, const void* PA,
+                              const void* nA, int64_t n, const void* PB, const void* nB, int64_t m, int D,
+                              int64_t ldp, double jitter, void* out, int64_t ldo) {
+  dim3 grid((unsigned)((m + TILE - 1) / TILE), (unsigned)((n + TILE - 1) / TILE));
+  const bool diff = (output == CGGP_OUT_DISTANCE && distance == CGGP_DIST_EUCLIDEAN);
+#define KM_CALL(MODE)                                                                                             \
+  kernel_matrix_kernel<T, K, MODE><<<grid, TILE_THREADS, 0, ctx->stream>>>(                                       \
+      (const T*)PA, (const T*)nA, n, (const T*)PB, (const T*)nB, m, D, ldp, (T)variance, output, distance,        \
+      (T)jitter, (T*)out, ldo)
+  if (diff) {
+    DISPATCH_KIND(T, 1, KM_CALL(1));
+  } else {
+    DISPATCH_KIND(T, 0, KM_CALL(0));
+  }
+#undef KM_CALL
+  CGGP_LAUNCH_CHECK(ctx);
+  return CGGP_OK;
+}
+
+extern "C" int cggp_kernel_matrix(cggp_ctx* ctx, int dtype, int kind, double variance, int output, int distance,
+                                  const void* PA, const void* nA, int64_t n, const void* PB, const void* nB, int64_t m,
+                                  int D, int64_t ldp, double jitter, void* out, int64_t ldo) {
+  if (!ctx) return CGGP_ERR_INVALID;
+  if (n == 0 || m == 0) return CGGP_OK;
+  if (n > 65535LL * TILE) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "n too large for one kernel_matrix call; batch it");
+  if (ldo < m) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "ldo < m");
+  if (dtype == CGGP_F64)
+    return kernel_matrix_impl<double>(ctx, kind, variance, output, distance, PA, nA, n, PB, nB, m, D, ldp, jitter, out,
+                                      ldo);
+  return kernel_matrix_impl<float>(ctx, kind, variance, output, distance, PA, nA, n, PB, nB, m, D, ldp, jitter, out,
+                                   ldo);
+}
+
+template <typename T>
+static int nearest_center_impl(cggp_ctx* ctx, int kind, double variance, int distance, const void* PX, const void* nX,
+                               int64_t n, const void* PZ, const void* nZ, int64_t m, int D, int64_t ldp, int64_t* idx,
+                               void* dist) {
+  const unsigned grid = (unsigned)((n + TILE - 1) / TILE);
+  const bool diff = distance == CGGP_DIST_EUCLIDEAN;
+#define NC_CALL(MODE)                                                                                       \
+  nearest_center_kernel<T, K, MODE><<<grid, TILE_THREADS, 0, ctx->stream>>>(                                \
+      (const T*)PX, (const T*)nX, n, (const T*)PZ, (const T*)nZ, m, D, ldp, (T)variance, distance, idx,     \
+      (T*)dist)
+  if (diff) {
+    DISPATCH_KIND(T, 1, NC_CALL(1));
+  } else {
+    DISPATCH_KIND(T, 0, NC_CALL(0));
+  }
+#undef NC_CALL
+  CGGP_LAUNCH_CHECK(ctx);
+  return CGGP_OK;
+}
+
+extern "C" int cggp_nearest_center(cggp_ctx* ctx, int dtype, int kind, double variance, int distance, const void* PX,
+                                   const void* nX, int64_t n, const void* PZ, const void* nZ, int64_t m, int D,
+                                   int64_t ldp, int64_t* idx, void* dist) {
+  if (!ctx) return CGGP_ERR_INVALID;
+  if (n == 0) return CGGP_OK;
+  if (m == 0) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "nearest_center needs at least one centre");
+  if (dtype == CGGP_F64)
+    return nearest_center_impl<double>(ctx, kind, variance, distance, PX, nX, n, PZ, nZ, m, D, ldp, idx, dist);
+  return nearest_center_impl<float>(ctx, kind, variance, distance, PX, nX, n, PZ, nZ, m, D, ldp, idx, dist);
+}
+
+extern "C" int cggp_cluster_stats(cggp_ctx* ctx, int dtype, const int64_t* idx, const void* y, int64_t n, int64_t m,
+                                  void* counts, void* sums) {
+  if (!ctx) return CGGP_ERR_INVALID;
+  const size_t es = dtype == CGGP_F64 ? 8 : 4;
+  CGGP_CUDA(ctx, cudaMemsetAsync(counts, 0, es * m, ctx->stream));
+  CGGP_CUDA(ctx, cudaMemsetAsync(sums, 0, es * m, ctx->stream));
+  if (n == 0) return CGGP_OK;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  if (dtype == CGGP_F64)
+    cluster_stats_kernel<double><<<blocks, threads, 0, ctx->stream>>>(idx, (const double*)y, n, m, (double*)counts,
+                                                                       (double*)sums);
+  else
+    cluster_stats_kernel<float><<<blocks, threads, 0, ctx->stream>>>(idx, (const float*)y, n, m, (float*)counts,
+                                                                      (float*)sums);
+  CGGP_LAUNCH_CHECK(ctx);
+  return CGGP_OK;
+}

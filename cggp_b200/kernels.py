@@ -1,0 +1,179 @@
+"""Stationary kernels with the GPflow surface the reference uses (``kernel(X)``, ``kernel(X, X2)``,
+``kernel(X, full_cov=False)``, ``.K``, ``.K_diag``, ``.variance``, ``.lengthscales``), evaluated on the GPU
+through the C ABI (``cggp_prepare_points`` + ``cggp_kernel_matrix``).
+
+Replaces the GPflow calls at ``cggp/models.py:300,333-335``, ``cggp/distance.py:17-20,26-29`` and the kernel
+factory of ``cggp/cli_utils.py:363-368`` (default ``Matern32(variance=1, lengthscales=[1]*D)``).  Arithmetic follows
+GPflow: inputs divided by the lengthscales, expanded squared distance without clamp, ``max(r2, 1e-36)`` before the
+square root for the Matern family.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+
+@dataclass
+class PreparedPoints:
+    """Scaled rows ``X / lengthscales`` zero-padded to ``ldp`` columns, and their squared norms."""
+
+    P: torch.Tensor      # [n, ldp]
+    norms: torch.Tensor  # [n]
+    D: int
+
+    @property
+    def n(self) -> int:
+        return self.P.shape[0]
+
+    @property
+    def ldp(self) -> int:
+        return self.P.shape[1]
+
+    def rows(self, start: int, stop: int) -> "PreparedPoints":
+        return PreparedPoints(self.P[start:stop], self.norms[start:stop], self.D)
+
+
+def prepare_points(X, lengthscales, dtype=None) -> PreparedPoints:
+    X = _lib.row_major(_lib.as_device_tensor(X, dtype))
+    ctx = _lib.context(X.device)
+    ctx.use_current_stream()
+    n, D = X.shape
+    ldp = int(ctx.lib.cggp_prepared_ld(D))
+    P = torch.empty((n, ldp), dtype=X.dtype, device=X.device)
+    norms = torch.empty((n,), dtype=X.dtype, device=X.device)
+    ls = torch.as_tensor(lengthscales, dtype=torch.float64).reshape(-1).cpu()
+    if ls.numel() not in (1, D):
+        raise ValueError(f"lengthscales must have 1 or {D} entries, got {ls.numel()}")
+    arr = (C.c_double * ls.numel())(*ls.tolist())
+    ctx.check(ctx.lib.cggp_prepare_points(ctx.handle, _lib.dtype_code(X.dtype), _lib.ptr(X), n, D, X.stride(0),
+                                          arr, ls.numel(), _lib.ptr(P), ldp, _lib.ptr(norms)))
+    return PreparedPoints(P, norms, D)
+
+
+def kernel_matrix(kind, variance, A: PreparedPoints, B: PreparedPoints, *, output=_lib.OUT_KERNEL,
+                  distance=_lib.DIST_EUCLIDEAN, jitter=0.0, out=None) -> torch.Tensor:
+    if A.D != B.D or A.ldp != B.ldp or A.P.dtype != B.P.dtype:
+        raise ValueError("point sets disagree in dimension / dtype")
+    ctx = _lib.context(A.P.device)
+    ctx.use_current_stream()
+    if out is None:
+        out = torch.empty((A.n, B.n), dtype=A.P.dtype, device=A.P.device)
+    step = 65535 * 64  # rows per call (grid.y limit)
+    for s in range(0, max(A.n, 1), step):
+        e = min(A.n, s + step)
+        if e <= s:
+            break
+        ctx.check(ctx.lib.cggp_kernel_matrix(
+            ctx.handle, _lib.dtype_code(A.P.dtype), int(kind), float(variance), int(output), int(distance),
+            _lib.ptr(A.P[s:e]), _lib.ptr(A.norms[s:e]), e - s, _lib.ptr(B.P), _lib.ptr(B.norms), B.n, A.D, A.ldp,
+            float(jitter), _lib.ptr(out[s:e]), out.stride(0)))
+    return out
+
+
+class Stationary:
+    kind = None
+    name = "stationary"
+
+    def __init__(self, variance=1.0, lengthscales=1.0):
+        self.variance = float(variance)
+        self.lengthscales = torch.as_tensor(lengthscales, dtype=torch.float64).reshape(-1).cpu()
+
+    @property
+    def ard(self) -> bool:
+        return self.lengthscales.numel() > 1
+
+    def prepare(self, X, dtype=None) -> PreparedPoints:
+        return X if isinstance(X, PreparedPoints) else prepare_points(X, self.lengthscales, dtype)
+
+    def K(self, X, X2=None, *, jitter=0.0):
+        A = self.prepare(X)
+        B = A if X2 is None else self.prepare(X2, A.P.dtype)
+        return kernel_matrix(self.kind, self.variance, A, B, jitter=jitter)
+
+    def K_diag(self, X):
+        if isinstance(X, PreparedPoints):
+            n, dtype, device = X.n, X.P.dtype, X.P.device
+        else:
+            X = _lib.as_device_tensor(X)
+            n, dtype, device = X.shape[0], X.dtype, X.device
+        return torch.full((n,), self.variance, dtype=dtype, device=device)
+
+    def __call__(self, X, X2=None, *, full_cov=True):
+        if not full_cov:
+            if X2 is not None:
+                raise ValueError("Ambiguous inputs: `not full_cov` and `X2` are not compatible.")
+            return self.K_diag(X)
+        return self.K(X, X2)
+
+
+class SquaredExponential(Stationary):
+    kind = _lib.SE
+    name = "se"
+
+
+class Matern12(Stationary):
+    kind = _lib.MATERN12
+    name = "matern12"
+
+
+class Matern32(Stationary):
+    kind = _lib.MATERN32
+    name = "matern32"
+
+
+class Matern52(Stationary):
+    kind = _lib.MATERN52
+    name = "matern52"
+
+
+KERNELS = {k.name: k for k in (SquaredExponential, Matern12, Matern32, Matern52)}
+
+
+class InducingPoints:
+    """GPflow ``InducingPoints`` surface: ``.Z`` and ``.num_inducing``."""
+
+    def __init__(self, Z):
+        self.Z = _lib.as_device_tensor(Z)
+
+    @property
+    def num_inducing(self) -> int:
+        return self.Z.shape[0]
+
+
+def inducingpoint_wrapper(iv) -> InducingPoints:
+    return iv if isinstance(iv, InducingPoints) else InducingPoints(iv)
+
+
+def Kuu(inducing_variable, kernel: Stationary, *, jitter=0.0):
+    """GPflow ``covariances.Kuu``: ``K(Z, Z) + jitter I`` (cggp/models.py:300,333)."""
+    return kernel.K(inducingpoint_wrapper(inducing_variable).Z, jitter=float(jitter))
+
+
+def Kuf(inducing_variable, kernel: Stationary, Xnew):
+    """GPflow ``covariances.Kuf``: ``K(Z, Xnew)`` [M, N] (cggp/models.py:334)."""
+    return kernel.K(inducingpoint_wrapper(inducing_variable).Z, Xnew)
+
+
+class Gaussian:
+    """GPflow ``likelihoods.Gaussian`` (variance only), the likelihood of cggp/cli_utils.py:153,164."""
+
+    def __init__(self, variance=1.0):
+        self.variance = float(variance)
+
+    def variational_expectations(self, X, Fmu, Fvar, Y):
+        import math
+
+        v = self.variance
+        ve = -0.5 * math.log(2.0 * math.pi) - 0.5 * math.log(v) - 0.5 * ((Y - Fmu) ** 2 + Fvar) / v
+        return ve.sum(-1)
+
+    def predict_log_density(self, X, Fmu, Fvar, Y):
+        import math
+
+        s2 = Fvar + self.variance
+        ld = -0.5 * (math.log(2.0 * math.pi) + torch.log(s2) + (Y - Fmu) ** 2 / s2)
+        return ld.sum(-1)

@@ -1,0 +1,134 @@
+"""Operator descriptors accepted at the ``matrix`` position of ``conjugate_gradient``:
+a dense ``[n, n]`` tensor (the reference's only form, ``Kuu + Lambda``, cggp/models.py:301,337) or the matrix-free
+north-star operator ``Sigma = Kuu + jitter I + s^-2 Kuf Kfu`` (the system GPflow's SGPR factorises, cggp/cli_utils.py:444-446)
+whose data term is computed on the fly over this rank's shard of X and summed over ranks by one all-reduce per
+iteration."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .kernels import PreparedPoints, Stationary, kernel_matrix
+
+
+class LinearOperator:
+    n: int
+    dtype: torch.dtype
+    device: torch.device
+
+    def c_struct(self) -> _lib.Operator:  # pragma: no cover - interface
+        raise NotImplementedError
+
+    def matmul(self, V: torch.Tensor) -> torch.Tensor:  # pragma: no cover - interface
+        raise NotImplementedError
+
+
+class DenseOperator(LinearOperator):
+    """``V @ A`` for a symmetric dense ``A`` (CG requires symmetry; the product reads rows of A, not columns)."""
+
+    def __init__(self, A):
+        A = _lib.row_major(_lib.as_device_tensor(A))
+        if A.shape[0] != A.shape[1]:
+            raise ValueError(f"matrix must be square, got {tuple(A.shape)}")
+        self.A = A
+        self.n = A.shape[0]
+        self.dtype = A.dtype
+        self.device = A.device
+
+    def c_struct(self):
+        op = _lib.Operator()
+        op.type = _lib.OP_DENSE
+        op.dtype = _lib.dtype_code(self.dtype)
+        op.n = self.n
+        op.dev_A = self.A.data_ptr()
+        op.lda = self.A.stride(0)
+        return op
+
+    def matmul(self, V):
+        V = _lib.row_major(V)
+        ctx = _lib.context(self.device)
+        ctx.use_current_stream()
+        Y = torch.empty_like(V)
+        ctx.check(ctx.lib.cggp_symm_matmul(ctx.handle, _lib.dtype_code(self.dtype), _lib.ptr(self.A),
+                                           self.A.stride(0), self.n, _lib.ptr(V), V.stride(0), V.shape[0],
+                                           _lib.ptr(Y), Y.stride(0)))
+        return Y
+
+
+class SGPROperator(LinearOperator):
+    """``Sigma = Kuu + jitter I + Kuf Kfu / noise_variance`` applied matrix-free.
+
+    ``X`` is THIS RANK's shard of the training inputs (rows); ``Z`` and ``Kuu`` are replicated.  With a communicator
+    initialised on the context (``_lib.context().init_comm()``) every application all-reduces the partial product."""
+
+    def __init__(self, kernel: Stationary, X, Z, noise_variance: float, jitter: float = 1e-6, variant: int = 0):
+        self.kernel = kernel
+        self.PZ = kernel.prepare(Z)
+        self.PX = kernel.prepare(X, self.PZ.P.dtype)
+        self.noise_variance = float(noise_variance)
+        self.jitter = float(jitter)
+        self.variant = int(variant)
+        self.n = self.PZ.n
+        self.dtype = self.PZ.P.dtype
+        self.device = self.PZ.P.device
+        self.Kuu = kernel_matrix(kernel.kind, kernel.variance, self.PZ, self.PZ, jitter=self.jitter)
+
+    def c_struct(self):
+        op = _lib.Operator()
+        op.type = _lib.OP_SGPR
+        op.dtype = _lib.dtype_code(self.dtype)
+        op.n = self.n
+        op.dev_A = self.Kuu.data_ptr()
+        op.lda = self.Kuu.stride(0)
+        op.kind = self.kernel.kind
+        op.D = self.PZ.D
+        op.variance = self.kernel.variance
+        op.scale = 1.0 / self.noise_variance
+        op.dev_PX = self.PX.P.data_ptr()
+        op.dev_normsX = self.PX.norms.data_ptr()
+        op.n_local = self.PX.n
+        op.dev_PZ = self.PZ.P.data_ptr()
+        op.dev_normsZ = self.PZ.norms.data_ptr()
+        op.ldp = self.PZ.ldp
+        op.variant = self.variant
+        return op
+
+    def kuf_kfu_matmul(self, V, variant=None, allreduce=True):
+        """``V @ (Kuf Kfu)`` over the local shard (+ all-reduce)."""
+        V = _lib.row_major(V)
+        ctx = _lib.context(self.device)
+        ctx.use_current_stream()
+        W = torch.empty_like(V)
+        ctx.check(ctx.lib.cggp_kuf_kfu_matvec(
+            ctx.handle, _lib.dtype_code(self.dtype), self.kernel.kind, self.kernel.variance,
+            _lib.ptr(self.PX.P), _lib.ptr(self.PX.norms), self.PX.n, _lib.ptr(self.PZ.P), _lib.ptr(self.PZ.norms),
+            self.n, self.PZ.D, self.PZ.ldp, _lib.ptr(V), V.stride(0), V.shape[0], _lib.ptr(W), W.stride(0),
+            self.variant if variant is None else int(variant)))
+        if allreduce and ctx.world > 1:
+            ctx.allreduce_sum_(W)
+        return W
+
+    def matmul(self, V):
+        W = self.kuf_kfu_matmul(V)
+        return DenseOperator(self.Kuu).matmul(V) + W / self.noise_variance
+
+    def kuf_times(self, Y):
+        """``Kuf @ Y`` for the local shard ``Y [n_local, P]`` (+ all-reduce): the right-hand side ``Kuf y``.
+        Computed in row batches so that nothing of size N x M is ever resident."""
+        Y = _lib.as_device_tensor(Y, self.dtype)
+        out = torch.zeros((self.n, Y.shape[1]), dtype=self.dtype, device=self.device)
+        step = max(1, (1 << 27) // max(self.n, 1))
+        for s in range(0, self.PX.n, step):
+            e = min(self.PX.n, s + step)
+            Kzx = kernel_matrix(self.kernel.kind, self.kernel.variance, self.PZ, self.PX.rows(s, e))
+            out += Kzx @ Y[s:e]
+        ctx = _lib.context(self.device)
+        if ctx.world > 1:
+            ctx.allreduce_sum_(out)
+        return out
+
+
+def as_operator(matrix) -> LinearOperator:
+    return matrix if isinstance(matrix, LinearOperator) else DenseOperator(matrix)

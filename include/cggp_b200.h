@@ -1,0 +1,191 @@
+/* cggp_b200.h - C ABI of the B200-native conjugate-gradient hot path (libcggp_b200.so).
+ *
+ * The reference (awav/conjugate-gradient-sparse-gp) is pure Python: it has no FFI, plugin or operator registry.
+ * Its boundary for this path is three Python surfaces, each of which one group of entry points
+ * below replaces; the Python mirror in cggp_b200/ keeps the reference names/argument order and calls these
+ * through ctypes (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer marked `dev` is a DEVICE pointer borrowed from the caller (e.g. a DLPack capsule); the
+ *     library never frees or retains it beyond the call unless stated.  `host` pointers are host memory.
+ *   - matrices are row-major with explicit leading dimensions (in elements).
+ *   - dtype is CGGP_F64 or CGGP_F32 and applies to every floating-point buffer of the call.
+ *   - every call is asynchronous on the ctx stream unless stated, returns 0 on success and <0 on error;
+ *     cggp_last_error(ctx) gives the message.  A ctx is bound to one device and one stream and is not re-entrant.
+ *   - there is no CPU fallback: without a CUDA device cggp_ctx_create fails.
+ */
+#ifndef CGGP_B200_H
+#define CGGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cggp_ctx cggp_ctx;
+
+enum cggp_dtype { CGGP_F32 = 0, CGGP_F64 = 1 };
+
+/* GPflow stationary kernels the reference instantiates (cggp/cli_utils.py:103-135,363-368,462-473). */
+enum cggp_kernel_kind { CGGP_SE = 0, CGGP_MATERN12 = 1, CGGP_MATERN32 = 2, CGGP_MATERN52 = 3 };
+
+/* cggp/distance.py:9-34 distance types (+ GPflow square_distance as used by cggp/optimize.py:50). */
+enum cggp_distance { CGGP_DIST_EUCLIDEAN = 0, CGGP_DIST_COVARIANCE = 1, CGGP_DIST_CORRELATION = 2,
+                     CGGP_DIST_SQEUCLIDEAN = 3 };
+
+/* Output selector of cggp_kernel_matrix. */
+enum cggp_tile_output { CGGP_OUT_KERNEL = 0, CGGP_OUT_DISTANCE = 1 };
+
+enum cggp_status {
+  CGGP_OK = 0, CGGP_ERR_INVALID = -1, CGGP_ERR_CUDA = -2, CGGP_ERR_UNSUPPORTED = -3, CGGP_ERR_COMM = -4
+};
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Context
+ * ------------------------------------------------------------------------------------------------------- */
+int cggp_ctx_create(int device, cggp_ctx** out);
+int cggp_ctx_destroy(cggp_ctx* ctx);
+/* Bind the CUDA stream (cudaStream_t as void*) that all later calls launch on; default is the NULL stream. */
+int cggp_ctx_set_stream(cggp_ctx* ctx, void* cuda_stream);
+const char* cggp_last_error(cggp_ctx* ctx);
+/* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
+int64_t cggp_launch_count(cggp_ctx* ctx);
+const char* cggp_version(void);
+
+/* Multi-GPU: one rank per GPU; the only collective on the path is the per-iteration all-reduce of the
+ * partial [B, M] product.  The id is an ncclUniqueId (128 bytes) made on rank 0 and sent to the others by the
+ * host (torch.distributed).  NCCL is dlopen'ed from the process (the torch-bundled libnccl.so.2). */
+int cggp_comm_unique_id(void* host_id128);
+int cggp_ctx_comm_init(cggp_ctx* ctx, const void* host_id128, int rank, int world);
+int cggp_ctx_comm_destroy(cggp_ctx* ctx);
+/* In-place sum all-reduce of `count` elements on the ctx stream (no-op when world == 1). */
+int cggp_allreduce_sum(cggp_ctx* ctx, int dtype, void* dev_buf, int64_t count);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Kernel evaluation  (replaces the GPflow calls at cggp/models.py:112,141-143,236,255-257,300,333-335 and
+ * cggp/distance.py:17-20,26-29: Stationary.scale, square_distance, K_r2 / K_r, Kuu, Kuf)
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* "Prepared points": P[i, 0:D] = X[i, :] / lengthscales, zero padding up to ldp (ldp = D rounded up to a multiple
+ * of 4 after adding one spare column, see cggp_prepared_ld), norms[i] = sum_d P[i, d]^2.
+ * lengthscales: host double[D] (ARD) or host double[1] with ls_count = 1 (isotropic). */
+int64_t cggp_prepared_ld(int D);
+int cggp_prepare_points(cggp_ctx* ctx, int dtype, const void* dev_X, int64_t n, int D, int64_t ldx,
+                        const double* host_lengthscales, int ls_count, void* dev_P, int64_t ldp,
+                        void* dev_norms);
+
+/* out[i, j] for prepared row sets A (n rows) and B (m rows):
+ *   output = CGGP_OUT_KERNEL   : k(a_i, b_j) = variance * K_r2(|a_i|^2 + |b_j|^2 - 2 a_i.b_j)   (GPflow expanded form,
+ *                                 no clamp for SE, max(r2, 1e-36) before sqrt for Matern)  [+ jitter on i == j]
+ *   output = CGGP_OUT_DISTANCE : cggp/distance.py value for `distance` (euclidean uses the difference form of
+ *                                 distance.py:9-11 on the prepared rows; sq-euclidean the expanded GPflow form). */
+int cggp_kernel_matrix(cggp_ctx* ctx, int dtype, int kind, double variance, int output, int distance,
+                       const void* dev_PA, const void* dev_normsA, int64_t n,
+                       const void* dev_PB, const void* dev_normsB, int64_t m,
+                       int D, int64_t ldp, double jitter, void* dev_out, int64_t ldo);
+
+/* Nearest-centre assignment (cggp/selection.py:14-32, cggp/optimize.py:50-51): for every prepared data row the
+ * argmin over the m centres of `distance` (first minimum wins, as tf.argmin) and that minimal distance. */
+int cggp_nearest_center(cggp_ctx* ctx, int dtype, int kind, double variance, int distance,
+                        const void* dev_PX, const void* dev_normsX, int64_t n,
+                        const void* dev_PZ, const void* dev_normsZ, int64_t m, int D, int64_t ldp,
+                        int64_t* dev_idx, void* dev_dist);
+/* Cluster statistics (cggp/optimize.py:53-67,88-96): counts[j] = #{i: idx[i] == j}, sums[j] = sum_{idx[i]==j} y[i]. */
+int cggp_cluster_stats(cggp_ctx* ctx, int dtype, const int64_t* dev_idx, const void* dev_y, int64_t n, int64_t m,
+                       void* dev_counts, void* dev_sums);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Matrix-free product with Kuf Kfu  (the north-star operator's data term)
+ *   W[b, :] = V[b, :] @ (Kuf Kfu),  Kfu[i, j] = k(x_i, z_j) never materialised; X is this rank's shard.
+ *   variant: 0 = auto, 1 = simple two-sweep kernels, 2 = fused cluster kernel (one evaluation per entry).
+ *   The result is NOT all-reduced; call cggp_allreduce_sum (cggp_cg_solve does it per iteration).
+ * ------------------------------------------------------------------------------------------------------- */
+int cggp_kuf_kfu_matvec(cggp_ctx* ctx, int dtype, int kind, double variance,
+                        const void* dev_PX, const void* dev_normsX, int64_t n,
+                        const void* dev_PZ, const void* dev_normsZ, int64_t m, int D, int64_t ldp,
+                        const void* dev_V, int64_t ldv, int B, void* dev_W, int64_t ldw, int variant);
+
+/* Y[B, n] = V[B, n] @ A[n, n] for SYMMETRIC A (CG's `state.p @ A`, cggp/conjugate_gradient.py:65,74,87). */
+int cggp_symm_matmul(cggp_ctx* ctx, int dtype, const void* dev_A, int64_t lda, int64_t n,
+                     const void* dev_V, int64_t ldv, int B, void* dev_Y, int64_t ldy);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Conjugate gradient  (replaces cggp/conjugate_gradient.py:24-122, forward pass)
+ * ------------------------------------------------------------------------------------------------------- */
+enum cggp_operator_type {
+  CGGP_OP_DENSE = 0,  /* A given as [n, n] (the reference's only form: Kuu + Lambda, cggp/models.py:301,337) */
+  CGGP_OP_SGPR = 1    /* A = Kuu_dense + scale * Kuf Kfu, matrix-free over this rank's X shard, all-reduced */
+};
+
+typedef struct cggp_operator {
+  int32_t type;
+  int32_t dtype;
+  int64_t n;            /* system size (= M) */
+  /* dense part: A (CGGP_OP_DENSE) or Kuu incl. jitter (CGGP_OP_SGPR); symmetric, row-major */
+  const void* dev_A;
+  int64_t lda;
+  /* CGGP_OP_SGPR only */
+  int32_t kind;
+  int32_t D;
+  double variance;
+  double scale;         /* 1 / noise_variance */
+  const void* dev_PX;   /* prepared X shard [n_local, ldp] */
+  const void* dev_normsX;
+  int64_t n_local;
+  const void* dev_PZ;   /* prepared Z [n, ldp] */
+  const void* dev_normsZ;
+  int64_t ldp;
+  int32_t variant;      /* as cggp_kuf_kfu_matvec */
+  int32_t _pad;
+} cggp_operator;
+
+enum cggp_precond_type {
+  CGGP_PRECOND_EYE = 0,   /* EyePreconditioner, cggp/conjugate_gradient.py:131-134 */
+  CGGP_PRECOND_BLOCK = 1  /* BlockPreconditioner (intent of :137-157): z[blk] = A[blk,blk]^-1 r[blk] */
+};
+
+typedef struct cggp_precond {
+  int32_t type;
+  int32_t num_blocks;
+  int32_t block_size;
+  int32_t _pad;
+  const int64_t* dev_block_indices; /* [num_blocks, block_size], a partition of 0..n-1 */
+  const void* dev_chol;             /* [num_blocks, block_size, block_size] lower Cholesky factors
+                                       (cggp_block_cholesky), or NULL for EYE */
+} cggp_precond;
+
+/* Gather the diagonal blocks A[blk, blk] of a dense symmetric matrix and factorise them (lower Cholesky). */
+int cggp_block_cholesky(cggp_ctx* ctx, int dtype, const void* dev_A, int64_t lda, int64_t n,
+                        const int64_t* dev_block_indices, int num_blocks, int block_size, void* dev_chol);
+
+/* One fused CG update on [B, n] row-major state given pA = p @ A  (cggp/conjugate_gradient.py:66-84, non-reset branch;
+ * with `reset` != 0 the caller passes fresh_r = b - v_new @ A ... see cggp_cg_solve).  Exported for unit tests / ncu.
+ *   denom = sum p*pA; gamma = rz/denom (0 where denom <= 1e-16); v += gamma p; r -= gamma pA;
+ *   (z, rz') = precond(r); p = z + p*rz'/rz (0 where rz <= 1e-16); rz = rz'; half_rr[b] = 0.5 * sum r^2.  */
+int cggp_cg_fused_step(cggp_ctx* ctx, int dtype, int B, int64_t n, const void* dev_pA, void* dev_v, void* dev_r,
+                       void* dev_p, void* dev_rz, void* dev_half_rr, const cggp_precond* precond);
+
+/* Full solve, reference semantics (row layout: rhs/x0/solution are [B, n], rows = right-hand sides):
+ *   continue while any_b(0.5 |r_b|^2 > error_threshold) and i < max_iterations            (:59-62)
+ *   residual refresh r = b - v@A, p = z when i % max_steps_cycle == max_steps_cycle - 1    (:71-84)
+ *   returns steps (int32) and half_rz[b] = 0.5 * rz_b                                       (:96-98)
+ * The loop runs on the device without a host round trip per iteration: iterations are enqueued in chunks of
+ * `check_every`; once the device-side convergence flag is set the remaining enqueued kernels are no-ops.
+ * dev_x0 may be NULL (zeros).  dev_history (may be NULL): [history_cap, B] receives 0.5|r_b|^2 at every evaluation of
+ * the stopping condition (steps + 1 rows).  host_steps receives the step count; this call synchronises the stream. */
+int cggp_cg_solve(cggp_ctx* ctx, const cggp_operator* op, const void* dev_rhs, const void* dev_x0, int B,
+                  double error_threshold, int max_iterations, int max_steps_cycle, const cggp_precond* precond,
+                  int check_every, void* dev_solution, int32_t* host_steps, void* dev_half_rz,
+                  void* dev_history, int64_t history_cap);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Micro-benchmarks for the roofline denominators that MEASURED_PEAKS.json lacks:
+ * which: 0 = FP64 DFMA, 1 = FP64 DMMA m8n8k4, 2 = the library's FP64 exp, 3 = FP64 sqrt (rsqrt seed + Newton),
+ *        4 = DMMA m16n8k4.  Returns giga-ops/s in *host_gops (FMA counted as 2 flop; exp/sqrt as 1 evaluation). */
+int cggp_microbench(cggp_ctx* ctx, int which, int iters, double* host_gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGGP_B200_H */

@@ -1,0 +1,88 @@
+"""CPU checks of the boundary: the C-ABI library loads, exports every symbol include/cggp_b200.h declares, and the
+product path refuses to run without a GPU (no CPU fallback, no oracle import)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "cggp_b200.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cggp_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    sys.path.insert(0, ROOT)
+    from cggp_b200 import build
+
+    return ctypes.CDLL(build.build())
+
+
+def test_header_declares_expected_surface():
+    fns = header_functions()
+    for must in ["cggp_cg_solve", "cggp_cg_fused_step", "cggp_kuf_kfu_matvec", "cggp_kernel_matrix",
+                 "cggp_nearest_center", "cggp_allreduce_sum", "cggp_block_cholesky", "cggp_symm_matmul"]:
+        assert must in fns
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in header_functions():
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+
+
+def test_ctypes_signatures_cover_header():
+    from cggp_b200 import _lib
+
+    assert sorted(_lib.SIGNATURES) == header_functions()
+
+
+def test_struct_layout_matches_header():
+    from cggp_b200 import _lib
+
+    assert ctypes.sizeof(_lib.Operator) == 112
+    assert ctypes.sizeof(_lib.Precond) == 32
+    assert _lib.Operator.dev_PZ.offset == 80 and _lib.Operator.variant.offset == 104
+
+
+def test_prepared_ld_and_version(lib):
+    lib.cggp_prepared_ld.restype = ctypes.c_int64
+    assert [lib.cggp_prepared_ld(d) for d in (1, 2, 3, 4, 11, 90)] == [4, 4, 4, 8, 12, 92]
+    lib.cggp_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.cggp_version()
+
+
+def test_no_cpu_fallback_and_no_oracle_in_product():
+    import torch
+
+    import cggp_b200
+
+    if not torch.cuda.is_available():
+        with pytest.raises(cggp_b200._lib.CggpError):
+            cggp_b200._lib.context()
+        with pytest.raises(cggp_b200._lib.CggpError):
+            cggp_b200.conjugate_gradient(torch.eye(3, dtype=torch.float64), torch.ones(1, 3, dtype=torch.float64),
+                                         None, 1e-6)
+    # nothing under cggp_b200/ may import the oracle
+    pkg = os.path.join(ROOT, "cggp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_sass_has_dmma_and_no_cpu_path():
+    out = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "cggp_b200", "libcggp_b200.so")],
+                         capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "DMMA" in out.stdout
+    assert "sm_100a" in out.stdout

@@ -1,0 +1,399 @@
+"""GPU parity tests: the CUDA path (through the C ABI) vs the CPU oracle and the golden vectors produced by the
+reference's own code (tests/golden).  Tolerances follow BASELINE.json's north_star: per-iteration CG residual
+norms 1e-9 relative (while the oracle's own summation-order noise floor is below that), ELBO / mean / variance
+1e-8 relative in float64, 1e-4 in float32, iteration counts +-1."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import cg as ocg  # noqa: E402
+from oracle import gpflow_restated as g  # noqa: E402
+from oracle import models as om  # noqa: E402
+
+KERNELS = ["se", "matern12", "matern32", "matern52"]
+
+
+def dev(x, dtype=None):
+    return torch.as_tensor(np.asarray(x), dtype=dtype).cuda()
+
+
+def cpu(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import cggp_b200
+
+    assert torch.cuda.is_available()
+    return cggp_b200
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("name", KERNELS)
+@pytest.mark.parametrize("D", [1, 2, 3, 11, 17, 90])
+def test_kernel_matrix_vs_oracle(cb, name, D):
+    rng = np.random.default_rng(D)
+    X = rng.standard_normal((301, D)) * (1.0 if D < 50 else 0.3)
+    Z = rng.standard_normal((130, D)) * (1.0 if D < 50 else 0.3)
+    ls = 0.6 + rng.random(D)
+    ok = g.KERNELS[name](variance=1.7, lengthscales=ls)
+    k = cb.kernels.KERNELS[name](variance=1.7, lengthscales=ls)
+    np.testing.assert_allclose(cpu(k.K(dev(X), dev(Z))), ok.K(X, Z), rtol=1e-12, atol=1e-14)
+    Kxx = cpu(k(dev(X)))
+    np.testing.assert_allclose(Kxx, ok.K(X), rtol=1e-8 if name in ("matern12", "matern32") else 1e-12, atol=1e-7 if name in ("matern12", "matern32") else 1e-14)
+    np.testing.assert_array_equal(cpu(k(dev(X), full_cov=False)), ok.K_diag(X))
+    np.testing.assert_allclose(cpu(cb.Kuu(dev(Z), k, jitter=1e-6)), g.Kuu(Z, ok, 1e-6), rtol=1e-8, atol=1e-7)
+
+
+def test_kernel_matrix_float32_and_isotropic(cb):
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((200, 5)).astype(np.float32)
+    Z = rng.standard_normal((70, 5)).astype(np.float32)
+    for name in KERNELS:
+        ok = g.KERNELS[name](variance=0.9, lengthscales=1.3, dtype=np.float32)
+        k = cb.kernels.KERNELS[name](variance=0.9, lengthscales=1.3)
+        out = k.K(dev(X), dev(Z))
+        assert out.dtype == torch.float32
+        np.testing.assert_allclose(cpu(out), ok.K(X, Z), rtol=2e-5, atol=2e-6)
+
+
+def test_empty_and_ragged_shapes(cb):
+    k = cb.Matern32(lengthscales=[1.0, 2.0])
+    X = torch.zeros((0, 2), dtype=torch.float64, device="cuda")
+    Z = torch.randn((5, 2), dtype=torch.float64, device="cuda")
+    assert tuple(k.K(X, Z).shape) == (0, 5)
+    assert tuple(k.K(Z, X).shape) == (5, 0)
+    Xs = torch.randn((65, 2), dtype=torch.float64, device="cuda")[::2]  # non-contiguous rows
+    ok = g.Matern32(lengthscales=[1.0, 2.0])
+    np.testing.assert_allclose(cpu(k.K(Xs, Z)), ok.K(cpu(Xs), cpu(Z)), rtol=1e-12, atol=1e-14)
+
+
+# ------------------------------------------------------------------------------------------------ distances
+@pytest.mark.parametrize("dtype_name", ["euclidean", "covariance", "correlation"])
+def test_distance_fn_vs_oracle(cb, dtype_name):
+    rng = np.random.default_rng(1)
+    cent = rng.standard_normal((33, 3))
+    pts = rng.standard_normal((50, 3))
+    ok = g.Matern32(variance=1.5, lengthscales=[1.0, 2.0, 0.5])
+    k = cb.Matern32(variance=1.5, lengthscales=[1.0, 2.0, 0.5])
+    fn = cb.create_distance_fn(k, dtype_name)
+    ofn = om.create_distance_fn(ok, dtype_name)
+    # reference call convention: (centroids [M, D], point [D]) -> [M]
+    np.testing.assert_allclose(cpu(fn((dev(cent), dev(pts[7])))), ofn((cent, pts[7])), rtol=1e-12, atol=1e-13)
+    full = cpu(fn((dev(cent), dev(pts))))
+    np.testing.assert_allclose(full, om.pairwise_distance(ok, dtype_name, pts, cent).T, rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("dtype_name", ["euclidean", "covariance", "correlation"])
+def test_nearest_center_and_cluster_stats(cb, dtype_name):
+    from cggp_b200 import selection
+
+    rng = np.random.default_rng(2)
+    X = rng.standard_normal((5003, 2))
+    y = rng.standard_normal((5003, 1))
+    Z = X[rng.choice(5003, 97, replace=False)].copy()
+    ok = g.SquaredExponential(variance=1.3, lengthscales=[0.8, 1.4])
+    k = cb.SquaredExponential(variance=1.3, lengthscales=[0.8, 1.4])
+    fn = cb.create_distance_fn(k, dtype_name)
+    idx, dist = selection.kmeans_indices_and_distances(dev(Z), dev(X), fn)
+    oidx, odist = om.kmeans_indices_and_distances(Z, X, ok, dtype_name)
+    np.testing.assert_array_equal(cpu(idx), oidx)  # index work: bit exact
+    np.testing.assert_allclose(cpu(dist), odist, rtol=1e-10, atol=1e-12)
+    _, u, counts = selection.kmeans_update_inducing_parameters(None, (dev(X), dev(y)), fn, lambda: dev(Z))
+    _, ou, ocounts = om.kmeans_update_inducing_parameters(Z, X, y, ok, dtype_name)
+    np.testing.assert_array_equal(cpu(counts), ocounts)
+    np.testing.assert_allclose(cpu(u), ou, rtol=1e-11, atol=1e-13)
+    _, means, cnt = selection.nearest_center_update(dev(Z), (dev(X), dev(y)))
+    _, omeans, ocnt = om.oips_style_assignment(Z, X, y)
+    np.testing.assert_array_equal(cpu(cnt).astype(np.int64), ocnt)
+    np.testing.assert_allclose(cpu(means), omeans, rtol=1e-11, atol=1e-13)
+
+
+def test_nearest_center_ties_pick_first(cb):
+    from cggp_b200 import selection
+
+    Z = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 0.0], [1.0, 0.0]])
+    X = np.array([[0.1, 0.0], [0.9, 0.0], [0.5, 0.0]])
+    idx, _ = selection.kmeans_indices_and_distances(dev(Z), dev(X))
+    np.testing.assert_array_equal(cpu(idx), [0, 1, 0])
+
+
+# ------------------------------------------------------------------------------------------------ dense products
+@pytest.mark.parametrize("B,n", [(1, 500), (5, 500), (8, 257), (9, 64), (37, 200), (130, 333), (64, 128)])
+def test_symm_matmul(cb, B, n):
+    rng = np.random.default_rng(B * 1000 + n)
+    A = rng.standard_normal((n, n))
+    A = A + A.T
+    V = rng.standard_normal((B, n))
+    Y = cb.DenseOperator(dev(A)).matmul(dev(V))
+    np.testing.assert_allclose(cpu(Y), V @ A, rtol=1e-12, atol=1e-11)
+    Yf = cb.DenseOperator(dev(A, torch.float32)).matmul(dev(V, torch.float32))
+    np.testing.assert_allclose(cpu(Yf), V @ A, rtol=2e-4, atol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------------ CG vs golden
+CASES = ["cgtest_se", "matern32_thr1e-6", "reset_cycle7", "maxit_cap", "zero_rhs_row", "float32"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_cg_vs_reference_golden(cb, cg_golden, name):
+    c = cg_golden[name]
+    max_it = None if int(c["max_it"]) < 0 else int(c["max_it"])
+    x0 = dev(c["x0"]) if np.any(c["x0"]) else torch.zeros_like(dev(c["rhs"]))
+    sol, (steps, err, hist) = cb.conjugate_gradient(dev(c["A"]), dev(c["rhs"]), x0, float(c["thr"]), None, max_it,
+                                                    int(c["cycle"]), return_history=True)
+    f32 = c["A"].dtype == np.float32
+    assert sol.dtype == (torch.float32 if f32 else torch.float64)
+    assert abs(int(steps) - int(c["steps"])) <= 1
+    ref_hist = c["history"]
+    k = min(hist.shape[0], ref_hist.shape[0])
+    h = cpu(hist)[:k]
+    # residual trajectory: 0.5|r|^2 relative 2e-9 (=1e-9 on |r|) while above the rounding noise floor of the oracle
+    if f32:
+        np.testing.assert_allclose(h[:10], ref_hist[:10], rtol=2e-3, atol=1e-6)
+    else:
+        floor = 1e-13 * ref_hist[0].max()
+        early = min(k, 25)
+        np.testing.assert_allclose(h[:early], ref_hist[:early], rtol=2e-9, atol=floor)
+        np.testing.assert_allclose(h, ref_hist[:k], rtol=1e-4, atol=1e4 * floor)
+    tol = 5e-3 if f32 else 1e-7
+    np.testing.assert_allclose(cpu(sol), c["solution"], rtol=tol, atol=tol)
+    if int(steps) == int(c["steps"]):
+        np.testing.assert_allclose(cpu(err), c["error"], rtol=1e-2 if f32 else 1e-4, atol=1e-30 if not f32 else 1e-9)
+
+
+def test_cg_adapter_and_callable_operator(cb, cg_golden):
+    c = cg_golden["adapter"]
+    cg = cb.ConjugateGradient(float(c["thr"]), record_history=True)
+    sol = cg(dev(c["A"]), dev(c["rhs"]))
+    assert tuple(sol.shape) == c["rhs"].shape
+    np.testing.assert_allclose(cpu(sol), c["solution"], rtol=1e-8, atol=1e-9)
+    assert abs(cg.last_history.shape[0] - c["history"].shape[0]) <= 1
+    sol2 = cb.ConjugateGradient(float(c["thr"]))(cb.DenseOperator(dev(c["A"])), dev(c["rhs"]))
+    np.testing.assert_array_equal(cpu(sol2), cpu(sol))
+
+
+def test_cg_reference_test_contract_value_and_gradient(cb):
+    """cggp/cg_test.py:12-46 on the new path: CG(1e-12) vs direct solve, values and gradients w.r.t. the matrix."""
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((100, 2))
+    ls = rng.random(2) ** 2 + 0.5
+    A0 = g.SquaredExponential(variance=1.3, lengthscales=ls).K(X) + 0.1 ** 2 * np.eye(100)
+    rhs = rng.standard_normal((100, 5))
+    A = dev(A0).requires_grad_(True)
+    A2 = dev(A0).requires_grad_(True)
+    inv_solution = torch.linalg.solve(A2, dev(rhs))
+    cg = cb.ConjugateGradient(1e-12)
+    cg_solution = cg(A, dev(rhs))  # column layout [n, m], as ConjugateGradient.__call__ expects
+    np.testing.assert_allclose(cpu(cg_solution), cpu(inv_solution), rtol=1e-3, atol=1e-4)
+    inv_solution.sum().backward()
+    cg_solution.sum().backward()
+    np.testing.assert_allclose(cpu(A.grad), cpu(A2.grad), rtol=1e-3, atol=1e-3)
+
+
+def test_cg_backward_vs_reference_closure(cb, cg_golden):
+    c = cg_golden["matern32_thr1e-6"]
+    A = dev(c["A"]).requires_grad_(True)
+    b = dev(c["rhs"]).requires_grad_(True)
+    sol, _ = cb.conjugate_gradient(A, b, None, float(c["thr"]), None, None, int(c["cycle"]))
+    sol.backward(dev(c["dx"]))
+    np.testing.assert_allclose(cpu(b.grad), c["db"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(cpu(A.grad), c["dA"], rtol=1e-6, atol=1e-6)
+
+
+def test_cg_fused_step_matches_oracle_step(cb):
+    """One application of the fused vector kernel == one cg_step of conjugate_gradient.py:64-85."""
+    import ctypes as C
+
+    from cggp_b200 import _lib
+
+    rng = np.random.default_rng(5)
+    B, n = 7, 1000
+    M = rng.standard_normal((n, n))
+    A = M @ M.T / n + np.eye(n)
+    p, v, r = (rng.standard_normal((B, n)) for _ in range(3))
+    rz = np.sum(r * r, -1, keepdims=True)
+    pA = p @ A
+    denom = np.sum(p * pA, -1, keepdims=True)
+    gamma = rz / denom
+    v1 = v + gamma * p
+    r1 = r - gamma * pA
+    rz1 = np.sum(r1 * r1, -1, keepdims=True)
+    p1 = r1 + p * rz1 / rz
+    tv, tr, tp, tq = dev(v), dev(r), dev(p), dev(pA)
+    trz = dev(rz[:, 0].copy())
+    half = torch.empty(B, dtype=torch.float64, device="cuda")
+    ctx = _lib.context()
+    ctx.use_current_stream()
+    ctx.check(ctx.lib.cggp_cg_fused_step(ctx.handle, _lib.F64, B, n, _lib.ptr(tq), _lib.ptr(tv), _lib.ptr(tr),
+                                         _lib.ptr(tp), _lib.ptr(trz), _lib.ptr(half), None))
+    np.testing.assert_allclose(cpu(tv), v1, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(cpu(tr), r1, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(cpu(tp), p1, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(cpu(trz), rz1[:, 0], rtol=1e-13)
+    np.testing.assert_allclose(cpu(half), 0.5 * rz1[:, 0], rtol=1e-13)
+
+
+def test_block_preconditioner(cb):
+    rng = np.random.default_rng(0)
+    n, bs = 96, 12
+    X = np.sort(rng.uniform(0, 10, size=(n, 1)), axis=0)
+    A = np.exp(-0.5 * (X - X.T) ** 2) + 1e-2 * np.eye(n)
+    rhs = rng.standard_normal((2, n))
+    blocks = rng.permutation(n).reshape(n // bs, bs)
+    hist = []
+    osol, (osteps, oerr) = ocg.conjugate_gradient(A, rhs, np.zeros_like(rhs), 1e-10, ocg.BlockPreconditioner(blocks),
+                                                  500, 1000, history=hist)
+    sol, (steps, err, h) = cb.conjugate_gradient(dev(A), dev(rhs), None, 1e-10, cb.BlockPreconditioner(blocks), 500,
+                                                 1000, return_history=True)
+    assert abs(int(steps) - int(osteps)) <= 1
+    np.testing.assert_allclose(cpu(h)[:8], np.array(hist)[:8], rtol=1e-7)
+    np.testing.assert_allclose(cpu(sol) @ A, rhs, atol=1e-4)
+    with pytest.raises(ValueError):
+        cb.conjugate_gradient(dev(A), dev(rhs), None, 1e-10, cb.BlockPreconditioner(blocks[:-1]), 10, 100)
+
+
+# ------------------------------------------------------------------------------------------------ matrix-free
+@pytest.mark.parametrize("name", KERNELS)
+@pytest.mark.parametrize("N,M,D,B", [(1000, 64, 2, 1), (2500, 200, 3, 5), (777, 129, 11, 2), (64, 500, 2, 1)])
+def test_kuf_kfu_matvec_simple_vs_oracle(cb, name, N, M, D, B):
+    rng = np.random.default_rng(N + M)
+    X = rng.standard_normal((N, D))
+    Z = rng.standard_normal((M, D))
+    V = rng.standard_normal((B, M))
+    ls = 0.8 + rng.random(D)
+    ok = g.KERNELS[name](variance=1.1, lengthscales=ls)
+    k = cb.kernels.KERNELS[name](variance=1.1, lengthscales=ls)
+    op = cb.SGPROperator(k, dev(X), dev(Z), 0.1, variant=1)
+    W = op.kuf_kfu_matmul(dev(V))
+    ref = om.kuf_kfu_matmul(ok, X, Z, V, chunk=512)
+    np.testing.assert_allclose(cpu(W), ref, rtol=1e-11, atol=1e-11 * np.abs(ref).max())
+    full = op.matmul(dev(V))
+    oref = om.sgpr_operator(ok, X, Z, 0.1)(V)
+    np.testing.assert_allclose(cpu(full), oref, rtol=1e-11, atol=1e-11 * np.abs(oref).max())
+
+
+def test_matrix_free_cg_matches_oracle(cb):
+    rng = np.random.default_rng(3)
+    N, M, D = 3000, 96, 2
+    X = rng.uniform(-3, 3, (N, D))
+    Y = np.sin(X.sum(-1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
+    Z = rng.uniform(-3, 3, (M, D))
+    ok = g.Matern52(variance=1.0, lengthscales=[1.0, 1.0])
+    k = cb.Matern52(variance=1.0, lengthscales=[1.0, 1.0])
+    noise = 0.1
+    rhs = (ok.K(Z, X) @ Y / noise).T  # [1, M]
+    hist = []
+    osol, (osteps, _) = ocg.conjugate_gradient(om.sgpr_operator(ok, X, Z, noise), rhs, np.zeros_like(rhs), 1e-6, None,
+                                               60, 1000, history=hist)
+    op = cb.SGPROperator(k, dev(X), dev(Z), noise, variant=1)
+    sol, (steps, err, h) = cb.conjugate_gradient(op, dev(rhs), None, 1e-6, None, 60, 1000, return_history=True)
+    assert abs(int(steps) - int(osteps)) <= 1
+    hh, oh = cpu(h), np.array(hist)
+    np.testing.assert_allclose(hh[:12], oh[:12], rtol=2e-9)
+    kk = min(len(hh), len(oh))
+    np.testing.assert_allclose(hh[:kk], oh[:kk], rtol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------ models
+def build_models(cb, c):
+    name = str(c["kernel"])
+    k = cb.kernels.KERNELS[name](variance=float(c["variance"]), lengthscales=c["lengthscales"])
+    lik = cb.Gaussian(float(c["noise"]))
+    probes = c["probes"]
+    num_probes = None if probes.shape[1] == 0 else probes.shape[1]
+    cg = cb.ConjugateGradient(float(c["thr"]))
+    m = cb.CGGP(k, lik, dev(c["Z"]), cg, num_probes=num_probes, cluster_counts=dev(c["counts"]),
+                pseudo_u=dev(c["u"]), num_data=int(c["num_data"]))
+    if num_probes is not None:
+        m.probes = dev(probes)
+    cl = cb.ClusterGP(k, lik, dev(c["Z"]), cluster_counts=dev(c["counts"]), pseudo_u=dev(c["u"]),
+                      num_data=int(c["num_data"]))
+    return m, cl
+
+
+@pytest.mark.parametrize("name", ["se_exacttrace", "matern32_probes", "matern52_exacttrace"])
+def test_cggp_vs_reference_golden(cb, models_golden, name):
+    c = models_golden[name]
+    m, cl = build_models(cb, c)
+    np.testing.assert_allclose(float(m.prior_kl()), c["cggp_kl"], rtol=1e-8)
+    mu, var = m.predict_f(dev(c["Xnew"]))
+    assert tuple(mu.shape) == (37, 1) and tuple(var.shape) == (37, 1)
+    np.testing.assert_allclose(cpu(mu), c["cggp_mu"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(cpu(var), c["cggp_var"], rtol=1e-8, atol=1e-9)
+    _, var_fc = m.predict_f(dev(c["Xnew"]), full_cov=True)
+    assert tuple(var_fc.shape) == (1, 37, 37)
+    np.testing.assert_allclose(cpu(var_fc), c["cggp_var_fullcov"], rtol=1e-8, atol=1e-9)
+    elbo = m.elbo((dev(c["X"][:200]), dev(c["y"][:200])))
+    np.testing.assert_allclose(float(elbo), c["cggp_elbo"], rtol=1e-8)
+    # Cholesky comparator
+    np.testing.assert_allclose(float(cl.prior_kl()), c["cluster_kl"], rtol=1e-8)
+    cmu, cvar = cl.predict_f(dev(c["Xnew"]))
+    np.testing.assert_allclose(cpu(cmu), c["cluster_mu"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(cpu(cvar), c["cluster_var"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(float(cl.elbo((dev(c["X"][:200]), dev(c["y"][:200])))), c["cluster_elbo"], rtol=1e-8)
+
+
+def test_eval_logdet_value_and_gradient(cb, models_golden):
+    c = models_golden["se_exacttrace"]
+    m, cl = build_models(cb, c)
+    Kmm = cb.Kuu(dev(c["Z"]), m.kernel)
+    KmmLambda = cb.add_diagonal(Kmm, m.diag_variance[:, 0]).requires_grad_(True)
+    val = cb.eval_logdet(KmmLambda, m.conjugate_gradient)
+    assert float(val) == 0.0
+    val.backward()
+    np.testing.assert_allclose(cpu(KmmLambda.grad), c["logdet_grad"], rtol=1e-7, atol=1e-8)
+
+
+def test_model_shape_validation(cb):
+    k = cb.SquaredExponential()
+    Z = torch.zeros((4, 2), dtype=torch.float64, device="cuda")
+    with pytest.raises(ValueError):
+        cb.ClusterGP(k, cb.Gaussian(0.1), Z, pseudo_u=torch.zeros((3, 1), dtype=torch.float64))
+    with pytest.raises(ValueError):
+        cb.ClusterGP(k, cb.Gaussian(0.1), Z, cluster_counts=torch.zeros((4,), dtype=torch.float64))
+    with pytest.raises(AssertionError):
+        cb.CGGP(k, cb.Gaussian(0.1), Z, cb.ConjugateGradient(1e-6)).predict_f(Z, full_output_cov=True)
+
+
+def test_sgpr_predict_matrix_free_vs_gpflow_restatement(cb):
+    rng = np.random.default_rng(4)
+    N, M, D = 1500, 40, 2
+    X = rng.uniform(-2, 2, (N, D))
+    Y = np.sin(2 * X[:, :1]) + 0.1 * rng.standard_normal((N, 1))
+    Z = rng.uniform(-2, 2, (M, D))
+    Xs = rng.uniform(-2, 2, (25, D))
+    ok = g.Matern52(variance=1.2, lengthscales=[0.9, 1.4])
+    k = cb.Matern52(variance=1.2, lengthscales=[0.9, 1.4])
+    ref_mean, ref_var = g.SGPR((X, Y), ok, Z, noise_variance=0.2).predict_f(Xs)
+    cg = cb.ConjugateGradient(1e-22, max_iterations=4000)
+    model = cb.sgpr_class((dev(X), dev(Y)), k, cb.Gaussian(0.2), dev(Z), conjugate_gradient=cg, variant=1)
+    mean, var = model.predict_f(dev(Xs))
+    np.testing.assert_allclose(cpu(mean), ref_mean, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(cpu(var), ref_var, rtol=1e-5, atol=1e-6)
+
+
+def test_dlpack_zero_copy_import(cb):
+    """Foreign device tensors come in through __dlpack__ without a copy (TF: tf.experimental.dlpack)."""
+
+    class Foreign:  # stands in for a TensorFlow / CuPy / JAX device tensor
+        def __init__(self, t):
+            self.t = t
+
+        def __dlpack__(self, stream=None):
+            return self.t.__dlpack__()
+
+        def __dlpack_device__(self):
+            return self.t.__dlpack_device__()
+
+    from cggp_b200 import _lib
+
+    t = torch.arange(12, dtype=torch.float64, device="cuda").reshape(3, 4)
+    w = _lib.as_device_tensor(Foreign(t))
+    assert w.data_ptr() == t.data_ptr()
+    A = torch.eye(4, dtype=torch.float64, device="cuda") * 2
+    sol, _ = cb.conjugate_gradient(Foreign(A), Foreign(t), None, 1e-20)
+    np.testing.assert_allclose(cpu(sol), cpu(t) / 2, rtol=1e-14)
