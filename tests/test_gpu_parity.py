@@ -23,6 +23,19 @@ def cpu(t):
     return t.detach().cpu().numpy()
 
 
+def assert_history_parity(h, oracle_hist, oracle_hist_alt, rtol=2e-9, slack=50.0):
+    """0.5|r|^2 per iteration within rtol of the oracle, or within `slack` x the oracle's OWN summation-order noise
+    (two chunkings of the same NumPy restatement) where CG has amplified rounding beyond rtol."""
+    k = min(len(h), len(oracle_hist), len(oracle_hist_alt))
+    h, a, b = np.asarray(h)[:k], np.asarray(oracle_hist)[:k], np.asarray(oracle_hist_alt)[:k]
+    floor = np.abs(a - b) / np.abs(a)
+    floor = np.maximum.accumulate(floor, axis=0)  # once noise has been amplified it stays
+    dev_ = np.abs(h - a) / np.abs(a)
+    bad = dev_ > np.maximum(rtol, slack * floor)
+    assert not bad.any(), f"residual trajectory off at iterations {np.argwhere(bad)[:5].tolist()}: {dev_[bad][:5]}"
+    assert (dev_[:3] <= rtol).all()
+
+
 @pytest.fixture(scope="module")
 def cb():
     import cggp_b200
@@ -42,10 +55,15 @@ def test_kernel_matrix_vs_oracle(cb, name, D):
     ok = g.KERNELS[name](variance=1.7, lengthscales=ls)
     k = cb.kernels.KERNELS[name](variance=1.7, lengthscales=ls)
     np.testing.assert_allclose(cpu(k.K(dev(X), dev(Z))), ok.K(X, Z), rtol=1e-12, atol=1e-14)
-    Kxx = cpu(k(dev(X)))
-    np.testing.assert_allclose(Kxx, ok.K(X), rtol=1e-8 if name in ("matern12", "matern32") else 1e-12, atol=1e-7 if name in ("matern12", "matern32") else 1e-14)
+    Kxx, oKxx = cpu(k(dev(X))), ok.K(X)
+    off = ~np.eye(301, dtype=bool)
+    np.testing.assert_allclose(Kxx[off], oKxx[off], rtol=1e-12, atol=1e-14)
+    # x == z exactly: the expanded r2 is pure rounding noise (+-1e-15), and Matern-1/2, 3/2 are not smooth at 0:
+    # sqrt(max(noise, 1e-36)) ~ 3e-8 in the reference as well, so the diagonal is only defined to ~1e-7
+    rough = name in ("matern12", "matern32")
+    np.testing.assert_allclose(np.diag(Kxx), np.diag(oKxx), rtol=1e-6 if rough else 1e-12)
     np.testing.assert_array_equal(cpu(k(dev(X), full_cov=False)), ok.K_diag(X))
-    np.testing.assert_allclose(cpu(cb.Kuu(dev(Z), k, jitter=1e-6)), g.Kuu(Z, ok, 1e-6), rtol=1e-8, atol=1e-7)
+    np.testing.assert_allclose(cpu(cb.Kuu(dev(Z), k, jitter=1e-6)), g.Kuu(Z, ok, 1e-6), rtol=1e-6 if rough else 1e-12)
 
 
 def test_kernel_matrix_float32_and_isotropic(cb):
@@ -142,27 +160,26 @@ CASES = ["cgtest_se", "matern32_thr1e-6", "reset_cycle7", "maxit_cap", "zero_rhs
 def test_cg_vs_reference_golden(cb, cg_golden, name):
     c = cg_golden[name]
     max_it = None if int(c["max_it"]) < 0 else int(c["max_it"])
-    x0 = dev(c["x0"]) if np.any(c["x0"]) else torch.zeros_like(dev(c["rhs"]))
+    x0 = dev(c["x0"]) if np.any(c["x0"]) else None
     sol, (steps, err, hist) = cb.conjugate_gradient(dev(c["A"]), dev(c["rhs"]), x0, float(c["thr"]), None, max_it,
                                                     int(c["cycle"]), return_history=True)
     f32 = c["A"].dtype == np.float32
     assert sol.dtype == (torch.float32 if f32 else torch.float64)
     assert abs(int(steps) - int(c["steps"])) <= 1
-    ref_hist = c["history"]
-    k = min(hist.shape[0], ref_hist.shape[0])
-    h = cpu(hist)[:k]
-    # residual trajectory: 0.5|r|^2 relative 2e-9 (=1e-9 on |r|) while above the rounding noise floor of the oracle
-    if f32:
-        np.testing.assert_allclose(h[:10], ref_hist[:10], rtol=2e-3, atol=1e-6)
-    else:
-        floor = 1e-13 * ref_hist[0].max()
-        early = min(k, 25)
-        np.testing.assert_allclose(h[:early], ref_hist[:early], rtol=2e-9, atol=floor)
-        np.testing.assert_allclose(h, ref_hist[:k], rtol=1e-4, atol=1e4 * floor)
-    tol = 5e-3 if f32 else 1e-7
-    np.testing.assert_allclose(cpu(sol), c["solution"], rtol=tol, atol=tol)
+    # the oracle's own rounding-noise floor: same algorithm, the products summed in a permuted order
+    A = c["A"]
+    perm = np.random.default_rng(0).permutation(A.shape[0])
+    alt_hist = []
+    alt_sol, _ = ocg.conjugate_gradient(lambda V: V[:, perm] @ A[perm, :], c["rhs"], c["x0"], float(c["thr"]), None,
+                                        max_it, int(c["cycle"]), history=alt_hist)
+    assert_history_parity(cpu(hist), c["history"], np.array(alt_hist), rtol=2e-4 if f32 else 2e-9)
+    noise = np.abs(alt_sol - c["solution"]).max()
+    tol = 20 * noise + (1e-4 if f32 else 1e-9)
+    np.testing.assert_allclose(cpu(sol), c["solution"], rtol=0, atol=tol)
     if int(steps) == int(c["steps"]):
-        np.testing.assert_allclose(cpu(err), c["error"], rtol=1e-2 if f32 else 1e-4, atol=1e-30 if not f32 else 1e-9)
+        k = int(steps)
+        floor = abs(alt_hist[k] - c["history"][k]) / c["history"][k]
+        np.testing.assert_allclose(cpu(err)[:, 0], c["error"][:, 0], rtol=max(1e-3 if f32 else 1e-8, 50 * floor.max()))
 
 
 def test_cg_adapter_and_callable_operator(cb, cg_golden):
@@ -258,8 +275,10 @@ def test_block_preconditioner(cb):
 
 # ------------------------------------------------------------------------------------------------ matrix-free
 @pytest.mark.parametrize("name", KERNELS)
-@pytest.mark.parametrize("N,M,D,B", [(1000, 64, 2, 1), (2500, 200, 3, 5), (777, 129, 11, 2), (64, 500, 2, 1)])
-def test_kuf_kfu_matvec_simple_vs_oracle(cb, name, N, M, D, B):
+@pytest.mark.parametrize("N,M,D,B", [(1000, 64, 2, 1), (2500, 200, 3, 5), (777, 129, 11, 2), (64, 500, 2, 1),
+                                     (4099, 700, 7, 3), (300, 40, 15, 1)])
+@pytest.mark.parametrize("variant", [1, 2])
+def test_kuf_kfu_matvec_vs_oracle(cb, name, N, M, D, B, variant):
     rng = np.random.default_rng(N + M)
     X = rng.standard_normal((N, D))
     Z = rng.standard_normal((M, D))
@@ -267,16 +286,34 @@ def test_kuf_kfu_matvec_simple_vs_oracle(cb, name, N, M, D, B):
     ls = 0.8 + rng.random(D)
     ok = g.KERNELS[name](variance=1.1, lengthscales=ls)
     k = cb.kernels.KERNELS[name](variance=1.1, lengthscales=ls)
-    op = cb.SGPROperator(k, dev(X), dev(Z), 0.1, variant=1)
+    op = cb.SGPROperator(k, dev(X), dev(Z), 0.1, variant=variant)
     W = op.kuf_kfu_matmul(dev(V))
     ref = om.kuf_kfu_matmul(ok, X, Z, V, chunk=512)
-    np.testing.assert_allclose(cpu(W), ref, rtol=1e-11, atol=1e-11 * np.abs(ref).max())
+    np.testing.assert_allclose(cpu(W), ref, rtol=1e-11, atol=1e-12 * np.abs(ref).max())
     full = op.matmul(dev(V))
     oref = om.sgpr_operator(ok, X, Z, 0.1)(V)
-    np.testing.assert_allclose(cpu(full), oref, rtol=1e-11, atol=1e-11 * np.abs(oref).max())
+    np.testing.assert_allclose(cpu(full), oref, rtol=1e-11, atol=1e-12 * np.abs(oref).max())
 
 
-def test_matrix_free_cg_matches_oracle(cb):
+def test_fused_matvec_is_deterministic_and_linear(cb):
+    rng = np.random.default_rng(9)
+    N, M, D = 20000, 1024, 11
+    X, Z = rng.standard_normal((N, D)), rng.standard_normal((M, D))
+    k = cb.Matern52(variance=0.9, lengthscales=np.full(D, 2.0))
+    op = cb.SGPROperator(k, dev(X), dev(Z), 0.1, variant=2)
+    V = dev(rng.standard_normal((2, M)))
+    W1, W2 = op.kuf_kfu_matmul(V), op.kuf_kfu_matmul(V)
+    assert torch.equal(W1, W2)  # bitwise reproducible: fixed-order reductions, no atomics on data
+    Ws = op.kuf_kfu_matmul(V[:1] * 2.0 + V[1:])
+    np.testing.assert_allclose(cpu(Ws), cpu(2.0 * W1[:1] + W1[1:]), rtol=1e-12)
+    # symmetric PSD quadratic form: v (Kuf Kfu) v^T = |Kfu v|^2 >= 0 and equals the simple path
+    Wsimple = op.kuf_kfu_matmul(V, variant=1)
+    np.testing.assert_allclose(cpu(W1), cpu(Wsimple), rtol=1e-12, atol=1e-12 * float(Wsimple.abs().max()))
+    assert float((W1[0] * V[0]).sum()) > 0
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_matrix_free_cg_matches_oracle(cb, variant):
     rng = np.random.default_rng(3)
     N, M, D = 3000, 96, 2
     X = rng.uniform(-3, 3, (N, D))
@@ -286,16 +323,15 @@ def test_matrix_free_cg_matches_oracle(cb):
     k = cb.Matern52(variance=1.0, lengthscales=[1.0, 1.0])
     noise = 0.1
     rhs = (ok.K(Z, X) @ Y / noise).T  # [1, M]
-    hist = []
+    hist, hist_alt = [], []
     osol, (osteps, _) = ocg.conjugate_gradient(om.sgpr_operator(ok, X, Z, noise), rhs, np.zeros_like(rhs), 1e-6, None,
                                                60, 1000, history=hist)
-    op = cb.SGPROperator(k, dev(X), dev(Z), noise, variant=1)
+    ocg.conjugate_gradient(om.sgpr_operator(ok, X, Z, noise, chunk=377), rhs, np.zeros_like(rhs), 1e-6, None, 60, 1000,
+                           history=hist_alt)
+    op = cb.SGPROperator(k, dev(X), dev(Z), noise, variant=variant)
     sol, (steps, err, h) = cb.conjugate_gradient(op, dev(rhs), None, 1e-6, None, 60, 1000, return_history=True)
     assert abs(int(steps) - int(osteps)) <= 1
-    hh, oh = cpu(h), np.array(hist)
-    np.testing.assert_allclose(hh[:12], oh[:12], rtol=2e-9)
-    kk = min(len(hh), len(oh))
-    np.testing.assert_allclose(hh[:kk], oh[:kk], rtol=1e-3)
+    assert_history_parity(cpu(h), hist, hist_alt)
 
 
 # ------------------------------------------------------------------------------------------------ models

@@ -103,3 +103,25 @@ def test_distances_and_assignment():
     _, means, cnt = om.oips_style_assignment(Z, X, y)
     np.testing.assert_array_equal(cnt, counts[:, 0].astype(np.int64))
     np.testing.assert_allclose(means, u[:, 0])
+
+
+def test_torch_cpu_port_matches_numpy_oracle():
+    """The multi-threaded CPU baseline of bench.py is the same algorithm as the NumPy oracle."""
+    import torch
+
+    from oracle import torch_cpu as tc
+
+    rng = np.random.default_rng(5)
+    X, Z = rng.standard_normal((700, 4)), rng.standard_normal((60, 4))
+    ls = np.array([0.9, 1.1, 1.3, 0.7])
+    for name in g.KERNELS:
+        ok = g.KERNELS[name](variance=1.3, lengthscales=ls)
+        Kt = tc.kernel_matrix(name, 1.3, torch.as_tensor(ls), torch.as_tensor(X), torch.as_tensor(Z)).numpy()
+        np.testing.assert_allclose(Kt, ok.K(X, Z), rtol=1e-12, atol=1e-14)
+    ok = g.Matern52(variance=1.3, lengthscales=ls)
+    rhs = rng.standard_normal((2, 60))
+    hist = []
+    ocg.conjugate_gradient(om.sgpr_operator(ok, X, Z, 0.1), rhs, np.zeros_like(rhs), 0.0, None, 6, 100, history=hist)
+    mm = tc.sgpr_operator("matern52", 1.3, torch.as_tensor(ls), torch.as_tensor(X), torch.as_tensor(Z), 0.1, chunk=256)
+    _, h = tc.cg_iterations(mm, torch.as_tensor(rhs), 6)
+    np.testing.assert_allclose(h.numpy(), np.array(hist), rtol=1e-7)

@@ -1,0 +1,44 @@
+"""Quick device timing of the matrix-free product and one CG iteration (development aid; bench.py is the contract)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import cggp_b200 as cb
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts), sum(ts) / len(ts)
+
+def main():
+    cfgs = [("c3", 2_000_000, 4096, 11, "matern52"), ("c2", 434_874, 2048, 3, "se"), ("c1", 10_000, 500, 2, "se")]
+    if len(sys.argv) > 1:
+        cfgs = [c for c in cfgs if c[0] in sys.argv[1:]]
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for name, N, M, D, kern in cfgs:
+        X = torch.randn(N, D, dtype=torch.float64, device="cuda", generator=g)
+        Z = torch.randn(M, D, dtype=torch.float64, device="cuda", generator=g)
+        V = torch.randn(1, M, dtype=torch.float64, device="cuda", generator=g)
+        k = cb.kernels.KERNELS[kern](variance=1.0, lengthscales=[1.0] * D)
+        op = cb.SGPROperator(k, X, Z, 0.1)
+        best, avg = timeit(lambda: op.kuf_kfu_matmul(V, variant=2))
+        falg = 2.0 * N * M * (D + 2)
+        print(f"{name}: fused matvec N={N} M={M} D={D} {kern}: best {best:.3f} ms avg {avg:.3f} ms  "
+              f"-> {falg / best / 1e9:.2f} TFLOP/s F_alg, {N * M / best / 1e6:.1f} Gentry/s")
+        if N <= 500_000:
+            best1, _ = timeit(lambda: op.kuf_kfu_matmul(V, variant=1), reps=3, warm=1)
+            print(f"{name}: simple matvec best {best1:.3f} ms ({best1 / best:.1f}x fused)")
+        # full CG iterations (fixed count, threshold 0)
+        rhs = torch.randn(1, M, dtype=torch.float64, device="cuda", generator=g)
+        its = 20
+        def solve():
+            cb.conjugate_gradient(op, rhs, None, 0.0, None, its, its + 1)
+        best, avg = timeit(solve, reps=3, warm=1)
+        print(f"{name}: CG {its} its: {best:.2f} ms -> {its / best * 1e3:.1f} it/s")
+
+if __name__ == "__main__":
+    main()
