@@ -60,6 +60,8 @@ SIGNATURES = {
     "cggp_last_error": (C.c_char_p, [_vp]),
     "cggp_launch_count": (_i64, [_vp]),
     "cggp_version": (C.c_char_p, []),
+    "cggp_profile_enable": (_i, [_vp, _i]),
+    "cggp_profile_read": (_i, [_vp, _i, C.POINTER(_d), C.POINTER(_i64)]),
     "cggp_comm_unique_id": (_i, [_vp]),
     "cggp_ctx_comm_init": (_i, [_vp, _vp, _i, _i]),
     "cggp_ctx_comm_destroy": (_i, [_vp]),
@@ -137,6 +139,21 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self.lib.cggp_launch_count(self.handle))
+
+    PROFILE_SECTIONS = ("kuf_kfu_matvec", "dense_symm_matmul", "cg_fused_step", "allreduce")
+
+    def profile(self, on: bool = True):
+        """Start (and clear) / stop per-section CUDA-event timing of the launches made through this context."""
+        self.check(self.lib.cggp_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_read(self):
+        """{section: (total_ms, launch_groups)}; synchronises the context stream."""
+        out = {}
+        for i, name in enumerate(self.PROFILE_SECTIONS):
+            ms, cnt = C.c_double(0.0), C.c_int64(0)
+            self.check(self.lib.cggp_profile_read(self.handle, i, C.byref(ms), C.byref(cnt)))
+            out[name] = (ms.value, cnt.value)
+        return out
 
     def init_comm(self, group=None):
         """Create the NCCL communicator of this rank from the torch.distributed process group (host plumbing):

@@ -13,6 +13,10 @@ int cggp_matvec_fused(cggp_ctx* ctx, int kind, double variance, const double* PX
                       const double* PZ, const double* nZ, int64_t m, int D, int64_t ldp, const double* V, int64_t ldv,
                       int B, double* W, int64_t ldw, const int* active);
 bool cggp_matvec_fused_supported(cggp_ctx* ctx, int dtype, int64_t m, int D, int B);
+int cggp_matvec_pipe(cggp_ctx* ctx, int kind, double variance, const double* PX, const double* nX, int64_t n,
+                     const double* PZ, const double* nZ, int64_t m, int D, int64_t ldp, const double* V, int64_t ldv,
+                     int B, double* W, int64_t ldw, const int* active);
+bool cggp_matvec_pipe_supported(cggp_ctx* ctx, int dtype, int64_t m, int D, int B);
 
 static std::string g_err;  // errors raised without a ctx
 
@@ -71,6 +75,8 @@ extern "C" int cggp_ctx_destroy(cggp_ctx* ctx) {
   if (w.p) { cudaFree(w.p); w.p = nullptr; w.bytes = 0; }
   if (ctx->cg_state) cudaFree(ctx->cg_state);
   if (ctx->cg_state_host) cudaFreeHost(ctx->cg_state_host);
+  for (int s = 0; s < CGGP_PROF_SECTIONS; ++s)
+    for (cudaEvent_t e : ctx->prof_ev[s]) cudaEventDestroy(e);
   delete ctx;
   return CGGP_OK;
 }
@@ -83,6 +89,50 @@ extern "C" int cggp_ctx_set_stream(cggp_ctx* ctx, void* stream) {
 
 extern "C" const char* cggp_last_error(cggp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
 extern "C" int64_t cggp_launch_count(cggp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------------
+// Section timing
+// ---------------------------------------------------------------------------------------------------------
+static const size_t PROF_CAP = 1 << 16;  // event pairs per section; later launches are not recorded
+
+ProfScope::ProfScope(cggp_ctx* c, int s) : ctx(c), sec(s), live(false) {
+  if (!c || !c->prof_on || c->prof_used[s] >= PROF_CAP) return;
+  std::vector<cudaEvent_t>& ev = c->prof_ev[s];
+  const size_t i = c->prof_used[s];
+  while (ev.size() < 2 * (i + 1)) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    ev.push_back(e);
+  }
+  live = cudaEventRecord(ev[2 * i], c->stream) == cudaSuccess;
+}
+ProfScope::~ProfScope() {
+  if (!live) return;
+  const size_t i = ctx->prof_used[sec];
+  cudaEventRecord(ctx->prof_ev[sec][2 * i + 1], ctx->stream);
+  ctx->prof_used[sec] = i + 1;
+}
+
+extern "C" int cggp_profile_enable(cggp_ctx* ctx, int on) {
+  if (!ctx) return CGGP_ERR_INVALID;
+  ctx->prof_on = on != 0;
+  for (int s = 0; s < CGGP_PROF_SECTIONS; ++s) ctx->prof_used[s] = 0;
+  return CGGP_OK;
+}
+
+extern "C" int cggp_profile_read(cggp_ctx* ctx, int section, double* host_ms_total, int64_t* host_count) {
+  if (!ctx || section < 0 || section >= CGGP_PROF_SECTIONS || !host_ms_total || !host_count) return CGGP_ERR_INVALID;
+  CGGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  double total = 0.0;
+  for (size_t i = 0; i < ctx->prof_used[section]; ++i) {
+    float ms = 0.f;
+    CGGP_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->prof_ev[section][2 * i], ctx->prof_ev[section][2 * i + 1]));
+    total += ms;
+  }
+  *host_ms_total = total;
+  *host_count = (int64_t)ctx->prof_used[section];
+  return CGGP_OK;
+}
 
 int cggp_ws_reserve(cggp_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->ws_bytes) return CGGP_OK;
@@ -189,6 +239,7 @@ extern "C" int cggp_allreduce_sum(cggp_ctx* ctx, int dtype, void* buf, int64_t c
   if (ctx->world == 1 || count == 0) return CGGP_OK;
   if (!ctx->comm) CGGP_FAIL(ctx, CGGP_ERR_COMM, "communicator not initialised");
   const int nccl_dtype = dtype == CGGP_F64 ? 8 : 7;  // ncclFloat64 / ncclFloat32
+  ProfScope prof(ctx, 3);
   int e = g_nccl.AllReduce(buf, buf, (size_t)count, nccl_dtype, 0 /* ncclSum */, ctx->comm, ctx->stream);
   if (e != 0) CGGP_FAIL(ctx, CGGP_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error");
   ctx->launches += 1;
@@ -203,6 +254,14 @@ int cggp_matvec_dispatch(cggp_ctx* ctx, int dtype, int kind, double variance, co
                          int64_t ldv, int B, void* W, int64_t ldw, int variant, const int* active) {
   if (kind < CGGP_SE || kind > CGGP_MATERN52) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "unknown kernel kind %d", kind);
   const bool can_fuse = cggp_matvec_fused_supported(ctx, dtype, m, D, B);
+  const bool can_pipe = cggp_matvec_pipe_supported(ctx, dtype, m, D, B);
+  ProfScope prof(ctx, 0);
+  if (variant == 3 && !can_pipe)
+    CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "pipelined matvec does not support dtype=%d m=%lld D=%d B=%d", dtype,
+              (long long)m, D, B);
+  if ((variant == 0 && can_pipe) || variant == 3)
+    return cggp_matvec_pipe(ctx, kind, variance, (const double*)PX, (const double*)nX, n, (const double*)PZ,
+                            (const double*)nZ, m, D, ldp, (const double*)V, ldv, B, (double*)W, ldw, active);
   if (variant == 2 && !can_fuse)
     CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "fused matvec does not support dtype=%d m=%lld D=%d B=%d", dtype,
               (long long)m, D, B);
@@ -217,7 +276,7 @@ extern "C" int cggp_kuf_kfu_matvec(cggp_ctx* ctx, int dtype, int kind, double va
                                    int64_t ldp, const void* V, int64_t ldv, int B, void* W, int64_t ldw, int variant) {
   if (!ctx) return CGGP_ERR_INVALID;
   if (B <= 0 || m <= 0) return CGGP_OK;
-  if (variant < 0 || variant > 2) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "variant must be 0, 1 or 2");
+  if (variant < 0 || variant > 3) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "variant must be 0, 1, 2 or 3");
   return cggp_matvec_dispatch(ctx, dtype, kind, variance, PX, nX, n, PZ, nZ, m, D, ldp, V, ldv, B, W, ldw, variant,
                               nullptr);
 }

@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(512) cg_step_kernel(const StepArgs<T> a) {
 
 template <typename T>
 static int launch_step(cggp_ctx* ctx, const StepArgs<T>& a) {
+  ProfScope prof(ctx, 2);
   cg_step_kernel<T><<<a.B, 512, 0, ctx->stream>>>(a);
   CGGP_LAUNCH_CHECK(ctx);
   return CGGP_OK;

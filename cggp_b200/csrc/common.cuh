@@ -5,6 +5,7 @@
 
 #include <cstdio>
 #include <string>
+#include <vector>
 
 #include "../../include/cggp_b200.h"
 
@@ -24,6 +25,19 @@ struct cggp_ctx {
   // NCCL (dlopen'ed)
   void* comm = nullptr;
   int rank = 0, world = 1;
+  // optional per-section device timing (cggp_profile_*): event pairs recorded on the ctx stream
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev[CGGP_PROF_SECTIONS];  // start, stop, start, stop, ...
+  size_t prof_used[CGGP_PROF_SECTIONS] = {0, 0, 0, 0};
+};
+
+// RAII section timer: no-op unless profiling is enabled on the ctx
+struct ProfScope {
+  cggp_ctx* ctx;
+  int sec;
+  bool live;
+  ProfScope(cggp_ctx* c, int s);
+  ~ProfScope();
 };
 
 #define CGGP_FAIL(ctx, code, ...)                       \

@@ -100,6 +100,7 @@ static int symm_matmul_impl(cggp_ctx* ctx, const T* A, int64_t lda, int64_t n, c
 int cggp_symm_matmul_ex(cggp_ctx* ctx, int dtype, const void* A, int64_t lda, int64_t n, const void* V, int64_t ldv,
                         int B, void* Y, int64_t ldy, const void* addend, int64_t ldadd, double scale,
                         const int* active) {
+  ProfScope prof(ctx, 1);
   if (dtype == CGGP_F64)
     return symm_matmul_impl<double>(ctx, (const double*)A, lda, n, (const double*)V, ldv, B, (double*)Y, ldy,
                                     (const double*)addend, ldadd, scale, active);

@@ -115,6 +115,69 @@ __device__ __forceinline__ double fast_exp(double x, const FastExpTable& tab) {
   return __hiloint2double(hi, lo) * q;
 }
 
+// exp(-a) for a >= 0 (the Matern argument): same scheme as fast_exp with the negation folded into the FMA operand
+// modifiers, so no FP64-pipe instruction is spent on forming -a.
+__device__ __forceinline__ double fast_exp_neg(double a, const FastExpTable& tab) {
+  const double L2E32 = 46.16624130844682903551758979206054839765;
+  const double MAGIC = 6755399441055744.0;
+  const double LN2_32 = 0.02166084939249829091928849858592451515688;
+  if ((unsigned)__double2hiint(a) > 0x40874000u) a = 744.0;  // a > 744 (also catches NaN): result flushed below
+  double t = fma(a, -L2E32, MAGIC);
+  int n = __double2loint(t);
+  double nf = t - MAGIC;
+  double d = fma(nf, -LN2_32, -a);
+  double q = fma(d, 8.33337406147829918e-03, 4.16668703096581480e-02);
+  q = fma(q, d, 1.66666666664448626e-01);
+  q = fma(q, d, 4.99999999994028277e-01);
+  q = fma(q, d, 1.0);
+  q = fma(q, d, 1.0);
+  int j = n & 31;
+  int hi = __shfl_sync(0xffffffffu, tab.hi, j);
+  int lo = __shfl_sync(0xffffffffu, tab.lo, j);
+  hi += (n >> 5) << 20;
+  if ((unsigned)__double2hiint(a) > 0x40862000u) { hi = 0; lo = 0; }  // a > 708: true result < 1e-307, flush to 0
+  return __hiloint2double(hi, lo) * q;
+}
+
+// Clamp-free cores used by the pipelined matvec, whose caller bounds the argument with two integer min / max on the
+// high word (ALU pipe) instead: x in [-708.4, 709] resp. a in [0, 708.4], results are normal numbers.
+__device__ __forceinline__ double fast_exp_core(double x, const FastExpTable& tab) {
+  const double L2E32 = 46.16624130844682903551758979206054839765;
+  const double MAGIC = 6755399441055744.0;
+  const double LN2_32 = 0.02166084939249829091928849858592451515688;
+  double t = fma(x, L2E32, MAGIC);
+  int n = __double2loint(t);
+  double nf = t - MAGIC;
+  double d = fma(nf, -LN2_32, x);
+  double q = fma(d, 8.33337406147829918e-03, 4.16668703096581480e-02);
+  q = fma(q, d, 1.66666666664448626e-01);
+  q = fma(q, d, 4.99999999994028277e-01);
+  q = fma(q, d, 1.0);
+  q = fma(q, d, 1.0);
+  int hi = __shfl_sync(0xffffffffu, tab.hi, n);  // SHFL uses the lane index modulo 32
+  int lo = __shfl_sync(0xffffffffu, tab.lo, n);
+  hi += (n >> 5) << 20;
+  return __hiloint2double(hi, lo) * q;
+}
+__device__ __forceinline__ double fast_exp_neg_core(double a, const FastExpTable& tab) {
+  const double L2E32 = 46.16624130844682903551758979206054839765;
+  const double MAGIC = 6755399441055744.0;
+  const double LN2_32 = 0.02166084939249829091928849858592451515688;
+  double t = fma(a, -L2E32, MAGIC);
+  int n = __double2loint(t);
+  double nf = t - MAGIC;
+  double d = fma(nf, -LN2_32, -a);
+  double q = fma(d, 8.33337406147829918e-03, 4.16668703096581480e-02);
+  q = fma(q, d, 1.66666666664448626e-01);
+  q = fma(q, d, 4.99999999994028277e-01);
+  q = fma(q, d, 1.0);
+  q = fma(q, d, 1.0);
+  int hi = __shfl_sync(0xffffffffu, tab.hi, n);
+  int lo = __shfl_sync(0xffffffffu, tab.lo, n);
+  hi += (n >> 5) << 20;
+  return __hiloint2double(hi, lo) * q;
+}
+
 // Fast kernel value on r2 (variance is applied by the caller once per row, not per entry).
 template <int KIND>
 __device__ __forceinline__ double kernel_value_fast_unit(double r2, const FastExpTable& tab) {

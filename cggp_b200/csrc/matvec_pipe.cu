@@ -1,0 +1,578 @@
+// Software-pipelined fused matrix-free product  W = V @ (Kuf Kfu)  in float64 (variant 3, the default).
+//
+//   t_i = sum_j K_ij v_j   (phase 1: needs all M columns of row i)      w_j = sum_i K_ij t_i   (phase 2)
+//
+// Every Gram entry k(x_i, z_j) is evaluated ONCE per application and is never written to global memory.
+//
+// What binds on B200 (profiles/r01_fused_v2_summary.md): the FP64 pipe (64 FMA/clk/SM, shared by DFMA and DMMA).
+// The first fused kernel (matvec_fused.cu, K tile in registers, 2 x 4 warps per SM) kept that pipe only 45 % busy:
+// 8 warps/SM cannot cover the DFMA dependency chains of sqrt / exp, and every row block ends in an exposed L2
+// round trip for the exchange of the partial t.  This kernel fixes both:
+//   * 1 CTA of 16 warps per SM (4 warps per scheduler, 4 independent epilogue chains each); the K values a thread
+//     produced in phase 1 are parked in a thread-private slice of shared memory (conflict-free 16-byte slots,
+//     196 KB per SM) instead of 128 registers, and read back by the same thread in phase 2;
+//   * the M inducing points are split over a GROUP of C CTAs (256 columns each; the warp's Z fragments, its v
+//     entries and its w accumulators stay in registers for the whole kernel, Z is never re-read);
+//   * phases are software pipelined: P1(block i+1) runs between publishing the partial t of block i and consuming
+//     the group's sum, so the L2 exchange (release/acquire counter per group) is hidden behind ~3 us of math;
+//   * X row tiles (48 rows x ldp doubles + norms) are staged by TMA bulk copies (cp.async.bulk + mbarrier) two
+//     blocks ahead; the scaled squared distance  a2 = alpha |x|^2 + alpha |z|^2 + beta x.z  comes straight out of
+//     DMMA m8n8k4 (alpha |z|^2 rides in the spare feature column, alpha |x|^2 initialises the accumulator), with
+//     alpha / beta chosen per kernel family so that no per-entry scaling multiply is left (kmath.cuh).
+// Determinism: all reductions run in a fixed order (no atomics on data); every CTA of a group sums the C partials
+// in the same order, so all ranks hold bit-identical t.
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+#include "kmath.cuh"
+
+namespace kpipe {
+constexpr int XS = 2;     // X-tile ring stages
+constexpr int SLOTS = 4;  // exchange slot ring: a CTA publishes block j+1 only after it gathered block j, and block j+2
+                          // only after every CTA published j+1 (= finished reading j), so 2 slots would already do
+
+struct Args {
+  const double* PX;
+  const double* nX;
+  int64_t n;
+  const double* PZ;
+  const double* nZ;
+  int64_t m;
+  int D;
+  int64_t ldp;
+  const double* V;
+  int64_t ldv;
+  double variance2;
+  double* Wp;     // [G][NB][m] per-group partial results
+  double* part;   // [G][SLOTS][C][BM*NB] exchanged partial t
+  int* counters;  // [G][SLOTS] one arrival counter per slot of the ring (monotonic over the launch)
+  int C, G;
+  int64_t nblocks;
+  int tma_ok;     // PX / nX are 16-byte aligned and ldp == KS * 4: full tiles go through cp.async.bulk
+  const int* active;
+};
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// a2 = alpha (|x|^2 + |z|^2) + beta x.z : the argument the kernel family wants, produced directly by the DMMA
+template <int KIND>
+struct Fam;
+template <>
+struct Fam<CGGP_SE> {  // K = exp(-r2 / 2): the DMMA delivers the exponent itself
+  static constexpr double alpha = -0.5, beta = 1.0;
+};
+template <>
+struct Fam<CGGP_MATERN12> {  // a = r
+  static constexpr double alpha = 1.0, beta = -2.0;
+  static constexpr double clampv = 1e-36;
+  static constexpr int clamp_hi = 0x38754484;
+};
+template <>
+struct Fam<CGGP_MATERN32> {  // a = sqrt(3) r
+  static constexpr double alpha = 3.0, beta = -6.0;
+  static constexpr double clampv = 3e-36;
+  static constexpr int clamp_hi = 0x388fe6c6;
+};
+template <>
+struct Fam<CGGP_MATERN52> {  // a = sqrt(5) r
+  static constexpr double alpha = 5.0, beta = -10.0;
+  static constexpr double clampv = 5e-36;
+  static constexpr int clamp_hi = 0x389a95a5;
+};
+
+// Unit-variance kernel value from the scaled argument q.  FP64-pipe instructions: SE 9, Matern-1/2 14, 3/2 16,
+// 5/2 17.  Range handling costs two integer min / max on the high word (ALU pipe), no FP64 compare / select:
+//   Matern: hi(q) -> clamp to [hi(alpha 1e-36), hi(708^2)] as SIGNED ints: negative q (rounding noise at x == z) and
+//           q below GPflow's max(r2, 1e-36) land on the lower clamp, q beyond (708 lengthscales)^2 on the upper one
+//           (exp(-708) = 3e-308 instead of an underflowed 0: absolute error 3e-308);
+//   SE:     hi(q) -> min with hi(-708) as UNSIGNED ints (more negative = larger).
+template <int KIND>
+__device__ __forceinline__ double kval(double q, const FastExpTable& tab) {
+  if constexpr (KIND == CGGP_SE) {
+    const unsigned h = min((unsigned)__double2hiint(q), 0xC0862000u);
+    return fast_exp_core(__hiloint2double((int)h, __double2loint(q)), tab);
+  } else {
+    const int h = min(max(__double2hiint(q), Fam<KIND>::clamp_hi), 0x411e9840);
+    const double qc = __hiloint2double(h, __double2loint(q));
+    const double a = fast_sqrt_pos(qc);
+    const double e = fast_exp_neg_core(a, tab);
+    if constexpr (KIND == CGGP_MATERN12) {
+      return e;
+    } else if constexpr (KIND == CGGP_MATERN32) {
+      return (1.0 + a) * e;
+    } else {
+      return fma(qc, 1.0 / 3.0, 1.0 + a) * e;  // 1 + sqrt5 r + 5/3 r^2, with a^2 = 5 r2 (= qc up to one rounding)
+    }
+  }
+}
+
+template <int WARPS, int RB, int CBW, int NB, int KS>
+struct Layout {
+  static constexpr int THREADS = WARPS * 32;
+  static constexpr int BM = RB * 8;
+  static constexpr int WN = CBW * 8;
+  static constexpr int BN = WARPS * WN;
+  static constexpr int LDX = KS * 4;
+  static constexpr size_t kbuf_bytes = (size_t)2 * RB * CBW * THREADS * sizeof(double2);
+  static constexpr size_t xt_bytes = (size_t)XS * BM * LDX * sizeof(double);
+  static constexpr size_t xn_bytes = (size_t)XS * BM * sizeof(double);
+  static constexpr size_t tred_bytes = (size_t)2 * WARPS * BM * NB * sizeof(double);
+  static constexpr size_t tfull_bytes = (size_t)2 * BM * NB * sizeof(double);
+  static constexpr size_t total = kbuf_bytes + xt_bytes + xn_bytes + tred_bytes + tfull_bytes + (XS + 2) * sizeof(uint64_t);
+};
+
+// Hand-offs inside a CTA.  T (named barrier 1 + parity): "the partial t of block j is in tred[j & 1] and X stage
+// j % XS is free" - the compute warps arrive without waiting, the exchange warp waits.  F (mbarrier per parity):
+// "t of block j is in tfull[j & 1]" - the 32 exchange lanes arrive, every compute warp waits on its own, so the
+// compute warps are never synchronised with each other and drift apart by up to a phase.
+__device__ __forceinline__ void bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+constexpr int BAR_T = 1;  // + parity of the block
+
+template <int KIND, int KS, int WARPS, int RB, int CBW, int NB, int HB>
+__global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args a) {
+  if (cg_inactive(a.active)) return;
+  using L = Layout<WARPS, RB, CBW, NB, KS>;
+  constexpr int THREADS = L::THREADS, BM = L::BM, WN = L::WN, BN = L::BN, LDX = L::LDX;
+  constexpr int ALL = THREADS + 32;  // compute warps + the exchange warp
+  const int g = blockIdx.x / a.C, rank = blockIdx.x % a.C;
+  if (g >= a.G) return;  // CTAs beyond the last full group stay idle
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* kbuf = reinterpret_cast<double2*>(smem_raw);
+  double* xt = reinterpret_cast<double*>(smem_raw + L::kbuf_bytes);
+  double* xn = reinterpret_cast<double*>(smem_raw + L::kbuf_bytes + L::xt_bytes);
+  double* tred = reinterpret_cast<double*>(smem_raw + L::kbuf_bytes + L::xt_bytes + L::xn_bytes);  // [2][WARPS][BM*NB]
+  double* tfull = tred + 2 * WARPS * BM * NB;                                                       // [2][BM*NB]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(tfull + 2 * BM * NB);
+
+  const int64_t nit = a.nblocks > g ? (a.nblocks - g + a.G - 1) / a.G : 0;  // row blocks of this group
+  auto row0_of = [&](int64_t it) { return (g + it * (int64_t)a.G) * BM; };
+  auto is_manual = [&](int64_t it) { return !a.tma_ok || row0_of(it) + BM > a.n; };
+
+  uint64_t* mbarF = mbar + XS;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < XS; ++s) mbar_init(&mbar[s], 1);
+    mbar_init(&mbarF[0], 32);
+    mbar_init(&mbarF[1], 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == WARPS) {
+    // =============================== exchange warp ===============================
+    // Stages X tiles (TMA bulk copies, two blocks ahead), reduces the 16 per-warp partial t, publishes them to the
+    // group through L2, waits for the other CTAs, sums the C partials in rank order and hands t to the compute
+    // warps - all while those are already busy with phase 1 of the next block.
+    auto stage_tile = [&](int64_t it) {
+      if (it >= nit) return;
+      const int s = (int)(it % XS);
+      const int64_t r0 = row0_of(it);
+      if (!is_manual(it)) {
+        if (lane == 0) {
+          constexpr unsigned xb = BM * LDX * sizeof(double), nb = BM * sizeof(double);
+          mbar_expect_tx(&mbar[s], xb + nb);
+          tma_bulk_g2s(xt + s * BM * LDX, a.PX + r0 * a.ldp, xb, &mbar[s]);
+          tma_bulk_g2s(xn + s * BM, a.nX + r0, nb, &mbar[s]);
+        }
+      } else {  // ragged last block / unaligned caller: guarded loads, visible to the compute warps via barrier F
+        for (int e = lane; e < BM * LDX; e += 32) {
+          const int r = e / LDX, k = e % LDX;
+          double x = 0.0;
+          if (r0 + r < a.n) x = (k < a.D) ? a.PX[(r0 + r) * a.ldp + k] : (k == a.D ? 1.0 : 0.0);
+          xt[s * BM * LDX + e] = x;
+        }
+        for (int e = lane; e < BM; e += 32) xn[s * BM + e] = (r0 + e < a.n) ? a.nX[r0 + e] : 0.0;
+      }
+    };
+#pragma unroll
+    for (int s = 0; s < XS; ++s) stage_tile(s);
+    __threadfence_block();
+    __syncthreads();  // (S) first tiles staged (manual ones visible)
+    double* slots_g = a.part + (int64_t)g * SLOTS * a.C * (BM * NB);
+    for (int64_t it = 0; it < nit; ++it) {
+      const int par = (int)(it & 1);
+      bar_sync(BAR_T + par, ALL);  // every compute warp finished phase 1 of block it
+      stage_tile(it + XS);         // X stage it % XS is free again
+      const double* tr = tred + par * WARPS * BM * NB;
+      double* tf = tfull + par * BM * NB;
+      const int64_t r0 = row0_of(it);
+      double sum[(BM * NB + 31) / 32];
+#pragma unroll
+      for (int q = 0; q < (BM * NB + 31) / 32; ++q) {
+        const int e = q * 32 + lane;
+        double v = 0.0;
+        if (e < BM * NB) {
+          v = tr[e];
+#pragma unroll
+          for (int w = 1; w < WARPS; ++w) v += tr[w * BM * NB + e];
+        }
+        sum[q] = v;
+      }
+      if (a.C > 1) {
+        double* mine = slots_g + ((int64_t)(it % SLOTS) * a.C + rank) * (BM * NB);
+#pragma unroll
+        for (int q = 0; q < (BM * NB + 31) / 32; ++q)
+          if (q * 32 + lane < BM * NB) __stcg(&mine[q * 32 + lane], sum[q]);
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          int* cnt = &a.counters[g * SLOTS + (int)(it % SLOTS)];
+          atomicAdd(cnt, 1);
+          // block `it` is the (it / SLOTS + 1)-th user of its slot
+          const int target = a.C * (int)(it / SLOTS + 1);
+          while (ld_acquire(cnt) < target) {
+          }
+        }
+        __syncwarp();
+        const double* sl = slots_g + (int64_t)(it % SLOTS) * a.C * (BM * NB);
+#pragma unroll
+        for (int q = 0; q < (BM * NB + 31) / 32; ++q) {
+          const int e = q * 32 + lane;
+          if (e < BM * NB) {
+            double v = 0.0;
+            for (int c = 0; c < a.C; ++c) v += __ldcg(&sl[(int64_t)c * BM * NB + e]);  // same order on every rank
+            sum[q] = v;
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < (BM * NB + 31) / 32; ++q) {
+        const int e = q * 32 + lane;
+        // rows past the end contribute nothing
+        if (e < BM * NB) tf[e] = (r0 + e / NB < a.n) ? sum[q] * a.variance2 : 0.0;
+      }
+      mbar_arrive(&mbarF[par]);  // release: this lane's tfull entries (and a manually staged X tile) are visible
+    }
+    return;
+  }
+
+  // =============================== compute warps ===============================
+  const int lr = lane >> 2, lk = lane & 3;
+  const int64_t col0 = (int64_t)rank * BN + warp * WN;  // first column of this warp
+  // per-warp constants held in registers for the whole kernel: Z fragments, v entries, w accumulators
+  double bf[CBW][KS];
+  double2 vv[CBW][NB];
+#pragma unroll
+  for (int cb = 0; cb < CBW; ++cb) {
+    const int64_t zc = col0 + cb * 8 + lr;  // B fragment: column lr of the 8-block, features ks*4 + lk
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int k = ks * 4 + lk;
+      double val = 0.0;
+      if (zc < a.m) {
+        if (k < a.D) val = Fam<KIND>::beta * a.PZ[zc * a.ldp + k];
+        else if (k == a.D) val = Fam<KIND>::alpha * a.nZ[zc];
+      }
+      bf[cb][ks] = val;
+    }
+    const int64_t vc = col0 + cb * 8 + 2 * lk;  // C fragment: columns 2 lk, 2 lk + 1
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      vv[cb][b].x = vc < a.m ? a.V[(int64_t)b * a.ldv + vc] : 0.0;
+      vv[cb][b].y = vc + 1 < a.m ? a.V[(int64_t)b * a.ldv + vc + 1] : 0.0;
+    }
+  }
+  double wacc[CBW][2][NB];
+#pragma unroll
+  for (int cb = 0; cb < CBW; ++cb)
+#pragma unroll
+    for (int b = 0; b < NB; ++b) wacc[cb][0][b] = wacc[cb][1][b] = 0.0;
+  const FastExpTable tab = fast_exp_table();
+
+  // One row-block step of phase 2 (block jt): w += K^T t from the K values this thread parked in shared memory.
+  // Split into loads and FMAs so that the loads can be issued ahead of a phase-1 step and hide under its FP64 work.
+  struct P2Regs {
+    double2 k[CBW];
+    double t[NB];
+  };
+  auto p2_load = [&](int rb, int par, P2Regs& r) {
+    const double* tf = tfull + par * BM * NB;
+    const double2* kb = kbuf + (size_t)par * RB * CBW * THREADS + tid;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) r.t[b] = tf[(rb * 8 + lr) * NB + b];
+#pragma unroll
+    for (int cb = 0; cb < CBW; ++cb) r.k[cb] = kb[(rb * CBW + cb) * THREADS];
+  };
+  auto p2_fma = [&](const P2Regs& r) {
+#pragma unroll
+    for (int cb = 0; cb < CBW; ++cb)
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        wacc[cb][0][b] = fma(r.k[cb].x, r.t[b], wacc[cb][0][b]);
+        wacc[cb][1][b] = fma(r.k[cb].y, r.t[b], wacc[cb][1][b]);
+      }
+  };
+  auto wait_F = [&](int64_t jt) { mbar_wait(&mbarF[jt & 1], (unsigned)((jt >> 1) & 1)); };
+
+  // Phase 2 of block it-1 rides inside the second half of phase 1 of block it: HB pure phase-1 steps give the
+  // exchange warp time to deliver t, then every phase-1 step also retires P2 steps of the previous block.
+  // HB == RB: no interleaving, phase 2 of block it-1 follows phase 1 of block it.
+  constexpr int HOSTS = RB - HB > 0 ? RB - HB : 1;
+  constexpr int P2MAX = HB < RB ? (RB + HOSTS - 1) / HOSTS : 1;
+
+  __syncthreads();  // (S)
+  for (int64_t it = 0; it < nit; ++it) {
+    const int s = (int)(it % XS), par = (int)(it & 1);
+    const bool prev = it >= 1;
+    if (!is_manual(it)) mbar_wait(&mbar[s], (unsigned)((it / XS) & 1));
+    const double* xs = xt + s * BM * LDX + lr * LDX + lk;
+    const double* xns = xn + s * BM + lr;
+    double2* kb = kbuf + (size_t)par * RB * CBW * THREADS + tid;
+    double* tr = tred + (par * WARPS + warp) * BM * NB;
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) {
+      // ---- loads of the phase-2 steps hosted by this phase-1 step
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int p2_lo = rb >= HB ? ((rb - HB) * RB) / HOSTS : 0;
+      const int p2_hi = rb >= HB ? ((rb - HB + 1) * RB) / HOSTS : 0;
+      P2Regs pr[P2MAX];
+      if (prev) {
+        if (rb == HB) wait_F(it - 1);
+#pragma unroll
+        for (int q = 0; q < P2MAX; ++q)
+          if (p2_lo + q < p2_hi) p2_load(p2_lo + q, par ^ 1, pr[q]);
+      }
+      // ---- phase 1, row block rb of block `it`
+      double af[KS];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) af[ks] = xs[rb * 8 * LDX + ks * 4];
+      const double xa = Fam<KIND>::alpha * xns[rb * 8];
+      double c[CBW][2];
+#pragma unroll
+      for (int cb = 0; cb < CBW; ++cb) {
+        c[cb][0] = c[cb][1] = xa;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) dmma884(c[cb][0], c[cb][1], af[ks], bf[cb][ks]);
+      }
+      double tp[NB];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) tp[b] = 0.0;
+#pragma unroll
+      for (int cb = 0; cb < CBW; ++cb) {
+        const double k0 = kval<KIND>(c[cb][0], tab);
+        const double k1 = kval<KIND>(c[cb][1], tab);
+        kb[(rb * CBW + cb) * THREADS] = make_double2(k0, k1);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) tp[b] = fma(k0, vv[cb][b].x, fma(k1, vv[cb][b].y, tp[b]));
+      }
+      // partial t of this warp's columns: the 4 lanes of a row
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        double v = tp[b];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (lk == 0) tr[(rb * 8 + lr) * NB + b] = v;
+      }
+      // ---- FMAs of the hosted phase-2 steps
+      if (prev) {
+#pragma unroll
+        for (int q = 0; q < P2MAX; ++q)
+          if (p2_lo + q < p2_hi) p2_fma(pr[q]);
+      }
+    }
+    __threadfence_block();
+    bar_arrive(BAR_T + par, ALL);  // hand the partials (and the X stage) to the exchange warp; do not wait
+    if (HB >= RB && prev) {
+      wait_F(it - 1);
+#pragma unroll
+      for (int rb = 0; rb < RB; ++rb) {
+        P2Regs r;
+        p2_load(rb, par ^ 1, r);
+        p2_fma(r);
+      }
+    }
+  }
+  if (nit >= 1) {  // phase 2 of the last block
+    wait_F(nit - 1);
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) {
+      P2Regs r;
+      p2_load(rb, (int)((nit - 1) & 1), r);
+      p2_fma(r);
+    }
+  }
+
+  // reduce the 8 row-lanes of every column, write this group's partial
+#pragma unroll
+  for (int cb = 0; cb < CBW; ++cb)
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        double v = wacc[cb][q][b];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        const int64_t col = col0 + cb * 8 + 2 * lk + q;
+        if (lr == 0 && col < a.m) a.Wp[((int64_t)g * NB + b) * a.m + col] = v;
+      }
+}
+
+__global__ void reduce_groups_kernel(const double* __restrict__ Wp, int G, int NB, int64_t m, double* __restrict__ W,
+                                     int64_t ldw, const int* __restrict__ active) {
+  if (cg_inactive(active)) return;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (c >= m) return;
+  double v = 0.0;
+  for (int g = 0; g < G; ++g) v += Wp[((int64_t)g * NB + b) * m + c];
+  W[(int64_t)b * ldw + c] = v;
+}
+
+struct Plan {
+  const void* fn;
+  int threads, BM, BN, NB;
+  size_t smem;
+};
+
+template <int KIND, int KS, int WARPS, int RB, int CBW, int NB, int HB>
+static Plan make_plan() {
+  using L = Layout<WARPS, RB, CBW, NB, KS>;
+  Plan p;
+  p.fn = (const void*)kfu_pipe_kernel<KIND, KS, WARPS, RB, CBW, NB, HB>;
+  p.threads = L::THREADS + 32;  // + the exchange warp
+  p.BM = L::BM;
+  p.BN = L::BN;
+  p.NB = NB;
+  p.smem = L::total;
+  return p;
+}
+
+template <int KIND, int KS>
+static bool plan_for_nb(int nb, Plan& p) {
+  static const int hb = getenv("CGGP_PIPE_HB") ? atoi(getenv("CGGP_PIPE_HB")) : 6;  // tuning knob (tools/)
+  switch (nb) {
+    case 1:
+      if (hb == 3) p = make_plan<KIND, KS, 16, 6, 2, 1, 3>();
+      else if (hb == 4) p = make_plan<KIND, KS, 16, 6, 2, 1, 4>();
+      else if (hb == 5) p = make_plan<KIND, KS, 16, 6, 2, 1, 5>();
+      else p = make_plan<KIND, KS, 16, 6, 2, 1, 6>();
+      return true;
+    case 2: p = make_plan<KIND, KS, 16, 5, 2, 2, 5>(); return true;  // 40-row blocks: two tred/tfull sets must fit
+    default: return false;
+  }
+}
+template <int KIND>
+static bool plan_for_ks(int ks, int nb, Plan& p) {
+  switch (ks) {
+    case 1: return plan_for_nb<KIND, 1>(nb, p);
+    case 2: return plan_for_nb<KIND, 2>(nb, p);
+    case 3: return plan_for_nb<KIND, 3>(nb, p);
+    case 4: return plan_for_nb<KIND, 4>(nb, p);
+    default: return false;
+  }
+}
+static bool plan_for(int kind, int ks, int nb, Plan& p) {
+  switch (kind) {
+    case CGGP_SE: return plan_for_ks<CGGP_SE>(ks, nb, p);
+    case CGGP_MATERN12: return plan_for_ks<CGGP_MATERN12>(ks, nb, p);
+    case CGGP_MATERN32: return plan_for_ks<CGGP_MATERN32>(ks, nb, p);
+    case CGGP_MATERN52: return plan_for_ks<CGGP_MATERN52>(ks, nb, p);
+    default: return false;
+  }
+}
+}  // namespace kpipe
+
+bool cggp_matvec_pipe_supported(cggp_ctx* ctx, int dtype, int64_t m, int D, int B) {
+  if (dtype != CGGP_F64 || B < 1) return false;
+  const int ks = (D + 1 + 3) / 4;
+  if (ks > 4) return false;
+  const int64_t C = (m + 255) / 256;  // one co-resident CTA per 256 columns
+  return C <= ctx->sm_count;
+}
+
+int cggp_matvec_pipe(cggp_ctx* ctx, int kind, double variance, const double* PX, const double* nX, int64_t n,
+                     const double* PZ, const double* nZ, int64_t m, int D, int64_t ldp, const double* V, int64_t ldv,
+                     int B, double* W, int64_t ldw, const int* active) {
+  using namespace kpipe;
+  const int ks = (D + 1 + 3) / 4;
+  int b0 = 0;
+  while (b0 < B) {
+    const int nb = (B - b0) >= 2 ? 2 : 1;
+    Plan p;
+    if (!plan_for(kind, ks, nb, p)) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "pipelined matvec: no plan for D=%d", D);
+    CGGP_CUDA(ctx, cudaFuncSetAttribute(p.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    int occ = 0;
+    CGGP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p.fn, p.threads, p.smem));
+    if (occ < 1) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "pipelined matvec kernel does not fit on an SM");
+    const int grid = ctx->sm_count;  // one persistent CTA per SM
+    const int C = (int)((m + p.BN - 1) / p.BN);
+    if (C > grid)
+      CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "pipelined matvec: M=%lld needs %d co-resident CTAs", (long long)m, C);
+    const int G = grid / C;
+    const int64_t nblocks = (n + p.BM - 1) / p.BM;
+    const size_t wp_bytes = sizeof(double) * (size_t)G * p.NB * (size_t)m;
+    const size_t part_bytes = sizeof(double) * (size_t)G * SLOTS * C * p.BM * p.NB;
+    const size_t cnt_bytes = sizeof(int) * (size_t)G * SLOTS;
+    int rc = cggp_ws_reserve(ctx, wp_bytes + part_bytes + cnt_bytes + 256);
+    if (rc) return rc;
+    char* base = (char*)ctx->ws;
+    Args a;
+    a.PX = PX; a.nX = nX; a.n = n; a.PZ = PZ; a.nZ = nZ; a.m = m; a.D = D; a.ldp = ldp;
+    a.V = V + (int64_t)b0 * ldv; a.ldv = ldv;
+    a.variance2 = variance * variance;
+    a.Wp = (double*)base;
+    a.part = (double*)(base + wp_bytes);
+    a.counters = (int*)(base + wp_bytes + part_bytes);
+    a.C = C; a.G = G; a.nblocks = nblocks; a.active = active;
+    a.tma_ok = (ldp == ks * 4) && (((uintptr_t)PX | (uintptr_t)nX) % 16 == 0) ? 1 : 0;
+    CGGP_CUDA(ctx, cudaMemsetAsync(a.counters, 0, cnt_bytes, ctx->stream));
+    void* kargs[] = {(void*)&a};
+    CGGP_CUDA(ctx, cudaLaunchCooperativeKernel(p.fn, dim3(grid), dim3(p.threads), kargs, p.smem, ctx->stream));
+    ctx->launches += 1;
+    reduce_groups_kernel<<<dim3((unsigned)((m + 255) / 256), (unsigned)p.NB), 256, 0, ctx->stream>>>(
+        a.Wp, G, p.NB, m, W + (int64_t)b0 * ldw, ldw, active);
+    CGGP_LAUNCH_CHECK(ctx);
+    b0 += nb;
+  }
+  return CGGP_OK;
+}

@@ -18,7 +18,8 @@ __global__ void prepare_points_kernel(const T* __restrict__ X, int64_t n, int D,
     P[i * ldp + d] = v;
     s += v * v;                      // reduce_sum(square(.)) in feature order
   }
-  for (int d = D; d < ldp; ++d) P[i * ldp + d] = T(0);
+  // spare column D holds 1 (it pairs with alpha |z|^2 in the fused matvec's DMMA), the rest of the padding is 0
+  for (int d = D; d < ldp; ++d) P[i * ldp + d] = d == D ? T(1) : T(0);
   norms[i] = s;
 }
 

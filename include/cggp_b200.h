@@ -53,6 +53,14 @@ const char* cggp_last_error(cggp_ctx* ctx);
 int64_t cggp_launch_count(cggp_ctx* ctx);
 const char* cggp_version(void);
 
+/* Per-section device timing for bench.py's roofline (CUDA events on the ctx stream around every launch group):
+ * section 0 = matrix-free Kuf Kfu product, 1 = dense symmetric product (Kuu / A), 2 = fused CG vector step,
+ * 3 = all-reduce.  enable(on != 0) clears the accumulated records; read() synchronises the stream and returns the
+ * summed milliseconds and the number of timed launch groups of that section. */
+#define CGGP_PROF_SECTIONS 4
+int cggp_profile_enable(cggp_ctx* ctx, int on);
+int cggp_profile_read(cggp_ctx* ctx, int section, double* host_ms_total, int64_t* host_count);
+
 /* Multi-GPU: one rank per GPU; the only collective on the path is the per-iteration all-reduce of the
  * partial [B, M] product.  The id is an ncclUniqueId (128 bytes) made on rank 0 and sent to the others by the
  * host (torch.distributed).  NCCL is dlopen'ed from the process (the torch-bundled libnccl.so.2). */
@@ -67,8 +75,9 @@ int cggp_allreduce_sum(cggp_ctx* ctx, int dtype, void* dev_buf, int64_t count);
  * cggp/distance.py:17-20,26-29: Stationary.scale, square_distance, K_r2 / K_r, Kuu, Kuf)
  * ------------------------------------------------------------------------------------------------------- */
 
-/* "Prepared points": P[i, 0:D] = X[i, :] / lengthscales, zero padding up to ldp (ldp = D rounded up to a multiple
- * of 4 after adding one spare column, see cggp_prepared_ld), norms[i] = sum_d P[i, d]^2.
+/* "Prepared points": P[i, 0:D] = X[i, :] / lengthscales, P[i, D] = 1 (the spare column: it carries the |z|^2 term
+ * through the fused matvec's DMMA), zero padding up to ldp (ldp = D + 1 rounded up to a multiple of 4, see
+ * cggp_prepared_ld), norms[i] = sum_d P[i, d]^2.
  * lengthscales: host double[D] (ARD) or host double[1] with ls_count = 1 (isotropic). */
 int64_t cggp_prepared_ld(int D);
 int cggp_prepare_points(cggp_ctx* ctx, int dtype, const void* dev_X, int64_t n, int D, int64_t ldx,
@@ -98,7 +107,9 @@ int cggp_cluster_stats(cggp_ctx* ctx, int dtype, const int64_t* dev_idx, const v
 /* ---------------------------------------------------------------------------------------------------------
  * Matrix-free product with Kuf Kfu  (the north-star operator's data term)
  *   W[b, :] = V[b, :] @ (Kuf Kfu),  Kfu[i, j] = k(x_i, z_j) never materialised; X is this rank's shard.
- *   variant: 0 = auto, 1 = simple two-sweep kernels, 2 = fused cluster kernel (one evaluation per entry).
+ *   variant: 0 = auto, 1 = simple two-sweep kernels (any dtype / D), 2 = fused register-tile kernel, 3 = fused
+ *   software-pipelined kernel (TMA-staged X tiles, K parked in shared memory; the default where supported:
+ *   float64, D <= 15).  Variants 2 and 3 evaluate every Gram entry once per application.
  *   The result is NOT all-reduced; call cggp_allreduce_sum (cggp_cg_solve does it per iteration).
  * ------------------------------------------------------------------------------------------------------- */
 int cggp_kuf_kfu_matvec(cggp_ctx* ctx, int dtype, int kind, double variance,

@@ -23,14 +23,21 @@ def cpu(t):
     return t.detach().cpu().numpy()
 
 
-def assert_history_parity(h, oracle_hist, oracle_hist_alt, rtol=2e-9, slack=50.0):
+def assert_history_parity(h, oracle_hist, oracle_hist_alts, rtol=2e-9, slack=50.0):
     """0.5|r|^2 per iteration within rtol of the oracle, or within `slack` x the oracle's OWN summation-order noise
-    (two chunkings of the same NumPy restatement) where CG has amplified rounding beyond rtol."""
-    k = min(len(h), len(oracle_hist), len(oracle_hist_alt))
-    h, a, b = np.asarray(h)[:k], np.asarray(oracle_hist)[:k], np.asarray(oracle_hist_alt)[:k]
-    floor = np.abs(a - b) / np.abs(a)
+    (the same NumPy restatement with its products summed in other orders / chunkings; one or several alternatives,
+    the floor is their maximum) where CG has amplified rounding beyond rtol.  On ill-conditioned systems that
+    amplification is chaotic (x500 per iteration on the reference's own cg_test system), hence several alternatives."""
+    alts = oracle_hist_alts if isinstance(oracle_hist_alts, (list, tuple)) and np.ndim(oracle_hist_alts[0]) >= 1 \
+        and np.ndim(oracle_hist_alts[0][0]) >= 1 else [oracle_hist_alts]
+    k = min([len(h), len(oracle_hist)] + [len(x) for x in alts])
+    h, a = np.asarray(h)[:k], np.asarray(oracle_hist)[:k]
+    floor = np.zeros_like(a)
+    den = np.where(a == 0, 1.0, np.abs(a))  # an all-zero right-hand side stays exactly zero (compared absolutely)
+    for alt in alts:
+        floor = np.maximum(floor, np.abs(a - np.asarray(alt)[:k]) / den)
     floor = np.maximum.accumulate(floor, axis=0)  # once noise has been amplified it stays
-    dev_ = np.abs(h - a) / np.abs(a)
+    dev_ = np.abs(h - a) / den
     bad = dev_ > np.maximum(rtol, slack * floor)
     assert not bad.any(), f"residual trajectory off at iterations {np.argwhere(bad)[:5].tolist()}: {dev_[bad][:5]}"
     assert (dev_[:3] <= rtol).all()
@@ -168,17 +175,21 @@ def test_cg_vs_reference_golden(cb, cg_golden, name):
     assert abs(int(steps) - int(c["steps"])) <= 1
     # the oracle's own rounding-noise floor: same algorithm, the products summed in a permuted order
     A = c["A"]
-    perm = np.random.default_rng(0).permutation(A.shape[0])
-    alt_hist = []
-    alt_sol, _ = ocg.conjugate_gradient(lambda V: V[:, perm] @ A[perm, :], c["rhs"], c["x0"], float(c["thr"]), None,
-                                        max_it, int(c["cycle"]), history=alt_hist)
-    assert_history_parity(cpu(hist), c["history"], np.array(alt_hist), rtol=2e-4 if f32 else 2e-9)
-    noise = np.abs(alt_sol - c["solution"]).max()
+    alt_hists, noise = [], 0.0
+    for seed in range(4):
+        perm = np.random.default_rng(seed).permutation(A.shape[0])
+        alt_hist = []
+        alt_sol, _ = ocg.conjugate_gradient(lambda V: V[:, perm] @ A[perm, :], c["rhs"], c["x0"], float(c["thr"]),
+                                            None, max_it, int(c["cycle"]), history=alt_hist)
+        alt_hists.append(np.array(alt_hist))
+        noise = max(noise, np.abs(alt_sol - c["solution"]).max())
+    assert_history_parity(cpu(hist), c["history"], alt_hists, rtol=2e-4 if f32 else 2e-9)
     tol = 20 * noise + (1e-4 if f32 else 1e-9)
     np.testing.assert_allclose(cpu(sol), c["solution"], rtol=0, atol=tol)
     if int(steps) == int(c["steps"]):
         k = int(steps)
-        floor = abs(alt_hist[k] - c["history"][k]) / c["history"][k]
+        den = np.where(c["history"][k] == 0, 1.0, c["history"][k])
+        floor = np.array([np.max(np.abs(ah[k] - c["history"][k]) / den) for ah in alt_hists if len(ah) > k] + [0.0])
         np.testing.assert_allclose(cpu(err)[:, 0], c["error"][:, 0], rtol=max(1e-3 if f32 else 1e-8, 50 * floor.max()))
 
 
@@ -187,7 +198,16 @@ def test_cg_adapter_and_callable_operator(cb, cg_golden):
     cg = cb.ConjugateGradient(float(c["thr"]), record_history=True)
     sol = cg(dev(c["A"]), dev(c["rhs"]))
     assert tuple(sol.shape) == c["rhs"].shape
-    np.testing.assert_allclose(cpu(sol), c["solution"], rtol=1e-8, atol=1e-9)
+    # at the reference's default threshold (1e-6) a solution is only defined up to the CG rounding noise: measure it
+    # on the oracle itself (same algorithm, products summed in permuted orders) and allow 20x that
+    A, n = c["A"], c["A"].shape[0]
+    noise = 0.0
+    for seed in range(4):
+        perm = np.random.default_rng(seed).permutation(n)
+        alt, _ = ocg.conjugate_gradient(lambda V: V[:, perm] @ A[perm, :], c["rhs"].T.copy(), np.zeros_like(c["rhs"].T),
+                                        float(c["thr"]), None, n, n + 1)
+        noise = max(noise, np.abs(alt.T - c["solution"]).max())
+    np.testing.assert_allclose(cpu(sol), c["solution"], rtol=0, atol=1e-9 + 20 * noise)
     assert abs(cg.last_history.shape[0] - c["history"].shape[0]) <= 1
     sol2 = cb.ConjugateGradient(float(c["thr"]))(cb.DenseOperator(dev(c["A"])), dev(c["rhs"]))
     np.testing.assert_array_equal(cpu(sol2), cpu(sol))
@@ -277,7 +297,7 @@ def test_block_preconditioner(cb):
 @pytest.mark.parametrize("name", KERNELS)
 @pytest.mark.parametrize("N,M,D,B", [(1000, 64, 2, 1), (2500, 200, 3, 5), (777, 129, 11, 2), (64, 500, 2, 1),
                                      (4099, 700, 7, 3), (300, 40, 15, 1)])
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_kuf_kfu_matvec_vs_oracle(cb, name, N, M, D, B, variant):
     rng = np.random.default_rng(N + M)
     X = rng.standard_normal((N, D))
@@ -295,12 +315,13 @@ def test_kuf_kfu_matvec_vs_oracle(cb, name, N, M, D, B, variant):
     np.testing.assert_allclose(cpu(full), oref, rtol=1e-11, atol=1e-12 * np.abs(oref).max())
 
 
-def test_fused_matvec_is_deterministic_and_linear(cb):
+@pytest.mark.parametrize("variant", [2, 3])
+def test_fused_matvec_is_deterministic_and_linear(cb, variant):
     rng = np.random.default_rng(9)
     N, M, D = 20000, 1024, 11
     X, Z = rng.standard_normal((N, D)), rng.standard_normal((M, D))
     k = cb.Matern52(variance=0.9, lengthscales=np.full(D, 2.0))
-    op = cb.SGPROperator(k, dev(X), dev(Z), 0.1, variant=2)
+    op = cb.SGPROperator(k, dev(X), dev(Z), 0.1, variant=variant)
     V = dev(rng.standard_normal((2, M)))
     W1, W2 = op.kuf_kfu_matmul(V), op.kuf_kfu_matmul(V)
     assert torch.equal(W1, W2)  # bitwise reproducible: fixed-order reductions, no atomics on data
@@ -312,7 +333,25 @@ def test_fused_matvec_is_deterministic_and_linear(cb):
     assert float((W1[0] * V[0]).sum()) > 0
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("N,M,D,name", [(300_007, 2048, 3, "se"), (150_001, 4096, 11, "matern52"),
+                                       (120_000, 1500, 7, "matern32")])
+def test_fused_matvec_many_row_blocks_matches_two_sweep(cb, N, M, D, name):
+    """Thousands of row blocks per CTA group (the exchange ring wraps many times), ragged last block, ragged M:
+    both fused kernels against the independent two-sweep kernels, which were checked against the oracle above."""
+    gen = torch.Generator(device="cuda").manual_seed(N)
+    X = torch.randn(N, D, dtype=torch.float64, device="cuda", generator=gen)
+    Z = torch.randn(M, D, dtype=torch.float64, device="cuda", generator=gen)
+    V = torch.randn(2, M, dtype=torch.float64, device="cuda", generator=gen)
+    k = cb.kernels.KERNELS[name](variance=1.3, lengthscales=[1.5] * D)
+    op = cb.SGPROperator(k, X, Z, 0.1)
+    ref = op.kuf_kfu_matmul(V, variant=1)
+    for variant in (2, 3):
+        W = op.kuf_kfu_matmul(V, variant=variant)
+        np.testing.assert_allclose(cpu(W), cpu(ref), rtol=1e-11, atol=1e-12 * float(ref.abs().max()))
+        assert torch.equal(W, op.kuf_kfu_matmul(V, variant=variant))  # bitwise reproducible
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_matrix_free_cg_matches_oracle(cb, variant):
     rng = np.random.default_rng(3)
     N, M, D = 3000, 96, 2

@@ -25,10 +25,13 @@ def main():
         V = torch.randn(1, M, dtype=torch.float64, device="cuda", generator=g)
         k = cb.kernels.KERNELS[kern](variance=1.0, lengthscales=[1.0] * D)
         op = cb.SGPROperator(k, X, Z, 0.1)
-        best, avg = timeit(lambda: op.kuf_kfu_matmul(V, variant=2))
         falg = 2.0 * N * M * (D + 2)
-        print(f"{name}: fused matvec N={N} M={M} D={D} {kern}: best {best:.3f} ms avg {avg:.3f} ms  "
-              f"-> {falg / best / 1e9:.2f} TFLOP/s F_alg, {N * M / best / 1e6:.1f} Gentry/s")
+        for variant in (3, 2):
+            best, avg = timeit(lambda: op.kuf_kfu_matmul(V, variant=variant))
+            print(f"{name}: fused matvec v{variant} N={N} M={M} D={D} {kern}: best {best:.3f} ms avg {avg:.3f} ms  "
+                  f"-> {falg / best / 1e9:.2f} TFLOP/s F_alg, {N * M / best / 1e6:.1f} Gentry/s", flush=True)
+        W3, W2 = op.kuf_kfu_matmul(V, variant=3), op.kuf_kfu_matmul(V, variant=2)
+        print(f"{name}: max rel diff v3 vs v2: {float((W3 - W2).abs().max() / W2.abs().max()):.3e}", flush=True)
         if N <= 500_000:
             best1, _ = timeit(lambda: op.kuf_kfu_matmul(V, variant=1), reps=3, warm=1)
             print(f"{name}: simple matvec best {best1:.3f} ms ({best1 / best:.1f}x fused)")
