@@ -139,7 +139,20 @@ __device__ __forceinline__ double fast_exp_neg(double a, const FastExpTable& tab
   return __hiloint2double(hi, lo) * q;
 }
 
-// Clamp-free cores used by the pipelined matvec, whose caller bounds the argument with two integer min / max on the
+// Table for the clamp-free cores below: the high word of entry j is pre-decremented by j << 15, so that the scaling
+// by 2^k (n = 32 k + j) is ONE integer multiply-add, hi = n * 2^15 + table_hi[j], instead of shift + mask + add.
+// (The kernel is bound by instruction issue - every FP64 instruction holds the dispatch port for 2 cycles, every other
+// instruction for 1 - so integer instructions are not free, see DESIGN.md.)
+__device__ __forceinline__ FastExpTable fast_exp_table_biased() {
+  const int lane = threadIdx.x & 31;
+  double t = exp2((double)lane * (1.0 / 32.0));
+  FastExpTable r;
+  r.hi = __double2hiint(t) - (lane << 15);
+  r.lo = __double2loint(t);
+  return r;
+}
+
+// Clamp-free cores used by the pipelined matvec (they take the BIASED table), whose caller bounds the argument with two integer min / max on the
 // high word (ALU pipe) instead: x in [-708.4, 709] resp. a in [0, 708.4], results are normal numbers.
 __device__ __forceinline__ double fast_exp_core(double x, const FastExpTable& tab) {
   const double L2E32 = 46.16624130844682903551758979206054839765;
@@ -156,7 +169,7 @@ __device__ __forceinline__ double fast_exp_core(double x, const FastExpTable& ta
   q = fma(q, d, 1.0);
   int hi = __shfl_sync(0xffffffffu, tab.hi, n);  // SHFL uses the lane index modulo 32
   int lo = __shfl_sync(0xffffffffu, tab.lo, n);
-  hi += (n >> 5) << 20;
+  hi += n << 15;  // = table_hi[j] + (k << 20)
   return __hiloint2double(hi, lo) * q;
 }
 __device__ __forceinline__ double fast_exp_neg_core(double a, const FastExpTable& tab) {
@@ -174,7 +187,7 @@ __device__ __forceinline__ double fast_exp_neg_core(double a, const FastExpTable
   q = fma(q, d, 1.0);
   int hi = __shfl_sync(0xffffffffu, tab.hi, n);
   int lo = __shfl_sync(0xffffffffu, tab.lo, n);
-  hi += (n >> 5) << 20;
+  hi += n << 15;
   return __hiloint2double(hi, lo) * q;
 }
 

@@ -51,6 +51,8 @@ struct Args {
   int C, G;
   int64_t nblocks;
   int tma_ok;     // PX / nX are 16-byte aligned and ldp == KS * 4: full tiles go through cp.async.bulk
+  int dbg;        // timing experiments only (env CGGP_PIPE_DBG; results are WRONG when set): 1 = skip phase 2,
+                  // 2 = skip the L2 exchange
   const int* active;
 };
 
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
         }
         sum[q] = v;
       }
-      if (a.C > 1) {
+      if (a.C > 1 && !(a.dbg & 2)) {
         double* mine = slots_g + ((int64_t)(it % SLOTS) * a.C + rank) * (BM * NB);
 #pragma unroll
         for (int q = 0; q < (BM * NB + 31) / 32; ++q)
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
   for (int cb = 0; cb < CBW; ++cb)
 #pragma unroll
     for (int b = 0; b < NB; ++b) wacc[cb][0][b] = wacc[cb][1][b] = 0.0;
-  const FastExpTable tab = fast_exp_table();
+  const FastExpTable tab = fast_exp_table_biased();
 
   // One row-block step of phase 2 (block jt): w += K^T t from the K values this thread parked in shared memory.
   // Split into loads and FMAs so that the loads can be issued ahead of a phase-1 step and hide under its FP64 work.
@@ -421,7 +423,7 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
     }
     __threadfence_block();
     bar_arrive(BAR_T + par, ALL);  // hand the partials (and the X stage) to the exchange warp; do not wait
-    if (HB >= RB && prev) {
+    if (HB >= RB && prev && !(a.dbg & 1)) {
       wait_F(it - 1);
 #pragma unroll
       for (int rb = 0; rb < RB; ++rb) {
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
       }
     }
   }
-  if (nit >= 1) {  // phase 2 of the last block
+  if (nit >= 1 && !(a.dbg & 1)) {  // phase 2 of the last block
     wait_F(nit - 1);
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) {
@@ -564,6 +566,7 @@ int cggp_matvec_pipe(cggp_ctx* ctx, int kind, double variance, const double* PX,
     a.part = (double*)(base + wp_bytes);
     a.counters = (int*)(base + wp_bytes + part_bytes);
     a.C = C; a.G = G; a.nblocks = nblocks; a.active = active;
+    a.dbg = getenv("CGGP_PIPE_DBG") ? atoi(getenv("CGGP_PIPE_DBG")) : 0;
     a.tma_ok = (ldp == ks * 4) && (((uintptr_t)PX | (uintptr_t)nX) % 16 == 0) ? 1 : 0;
     CGGP_CUDA(ctx, cudaMemsetAsync(a.counters, 0, cnt_bytes, ctx->stream));
     void* kargs[] = {(void*)&a};
