@@ -201,7 +201,10 @@ def run_native(args):
         ctx.init_comm()
 
     N, M, D, kern, desc = WORKLOADS[args.workload]
-    n_local = N // world + (1 if rank < N % world else 0)
+    from cggp_b200.sharding import shard_rows
+
+    r_lo, r_hi = shard_rows(N, rank, world)
+    n_local = r_hi - r_lo
     f64 = torch.float64
 
     # ---- synthetic data: HOST (pinned) copies for the e2e leg, device copies for the resident leg -------------
