@@ -20,7 +20,7 @@ SE, MATERN12, MATERN32, MATERN52 = 0, 1, 2, 3
 DIST_EUCLIDEAN, DIST_COVARIANCE, DIST_CORRELATION, DIST_SQEUCLIDEAN = 0, 1, 2, 3
 OUT_KERNEL, OUT_DISTANCE = 0, 1
 OP_DENSE, OP_SGPR = 0, 1
-PRECOND_EYE, PRECOND_BLOCK = 0, 1
+PRECOND_EYE, PRECOND_BLOCK, PRECOND_DENSE = 0, 1, 2
 DISTANCE_CODES = {"euclidean": DIST_EUCLIDEAN, "covariance": DIST_COVARIANCE, "correlation": DIST_CORRELATION,
                   "sqeuclidean": DIST_SQEUCLIDEAN}
 
@@ -48,6 +48,7 @@ class Precond(C.Structure):
     _fields_ = [
         ("type", C.c_int32), ("num_blocks", C.c_int32), ("block_size", C.c_int32), ("_pad", C.c_int32),
         ("dev_block_indices", C.c_void_p), ("dev_chol", C.c_void_p),
+        ("dev_pinv", C.c_void_p), ("ldpinv", C.c_int64),
     ]
 
 

@@ -95,6 +95,32 @@ class BlockPreconditioner(CGPreconditioner):
         return z, (z * vec).sum(-1, keepdim=True)
 
 
+class DensePreconditioner(CGPreconditioner):
+    """``z = r @ Pinv`` with a symmetric ``Pinv ~ A^-1`` resident on the device (``CGGP_PRECOND_DENSE``): the
+    Nystrom- / Cholesky-style preconditioner of the matrix-free operator (``SGPROperator.nystrom_preconditioner``).
+    Follows the reference's protocol ``__call__(vec [m, n], mat) -> (z [m, n], rz [m, 1])``
+    (conjugate_gradient.py:125-128); inside the device loop the product is one symmetric GEMV/GEMM per iteration."""
+
+    def __init__(self, pinv) -> None:
+        pinv = _lib.row_major(_lib.as_device_tensor(pinv))
+        if pinv.dim() != 2 or pinv.shape[0] != pinv.shape[1]:
+            raise ValueError("pinv must be a square matrix")
+        self.pinv = pinv
+
+    def c_struct(self, operator):
+        if self.pinv.shape[0] != operator.n or self.pinv.dtype != operator.dtype:
+            raise ValueError("preconditioner does not match the operator (size / dtype)")
+        pc = _lib.Precond()
+        pc.type = _lib.PRECOND_DENSE
+        pc.dev_pinv = self.pinv.data_ptr()
+        pc.ldpinv = self.pinv.stride(0)
+        return pc, (self.pinv,)
+
+    def __call__(self, vec, mat=None):
+        z = DenseOperator(self.pinv).matmul(_lib.row_major(vec))
+        return z, (z * vec).sum(-1, keepdim=True)
+
+
 def _solve(operator: LinearOperator, rhs: Tensor, initial_solution: Optional[Tensor], error_threshold: float,
            preconditioner: Optional[CGPreconditioner], max_iterations: int, max_steps_cycle: int,
            want_history: bool, check_every: int = 16):

@@ -54,6 +54,11 @@ struct StepArgs {
   int num_blocks, block_size;
   const int64_t* block_idx;
   const T* chol;
+  // dense preconditioner: the step kernel stops after r / 0.5|r|^2 (`defer` != 0); z = r @ Pinv is a separate
+  // symmetric product and cg_finish_kernel completes the iteration
+  int defer;
+  const T* pinv;
+  int64_t ldpinv;
 };
 
 constexpr int MAX_BS = 64;
@@ -125,6 +130,10 @@ __global__ void __launch_bounds__(512) cg_step_kernel(const StepArgs<T> a) {
     }
   }
   const T rr = block_sum(rr_part, red);
+  if (a.defer) {
+    if (threadIdx.x == 0) a.half_rr[b] = T(0.5) * rr;
+    return;
+  }
   T rz_new = rr;  // EyePreconditioner (:131-134): z = r, rz = sum r^2
   const T* zsrc = r;
   if (a.num_blocks > 0) {  // BlockPreconditioner (intent of :137-157)
@@ -175,11 +184,76 @@ __global__ void __launch_bounds__(512) cg_step_kernel(const StepArgs<T> a) {
   }
 }
 
+// Second half of an iteration with the dense preconditioner: given z = r @ Pinv, rz' = sum z*r (:157-style),
+// p = z + p rz'/rz (:78-83) or p = z (init / refresh), stats and loop control as in cg_step_kernel.
+template <typename T>
+__global__ void __launch_bounds__(512) cg_finish_kernel(const StepArgs<T> a) {
+  if (a.state && a.state[0] == 0) return;
+  __shared__ T red[33];
+  __shared__ int s_last;
+  const int b = blockIdx.x;
+  const int64_t n = a.n;
+  const T* r = a.r + (int64_t)b * n;
+  const T* z = a.z + (int64_t)b * n;
+  T* p = a.p + (int64_t)b * n;
+  const T min_float = T(1e-16);
+  T zp = T(0);
+  for (int64_t k = threadIdx.x; k < n; k += blockDim.x) zp = add_rn(zp, mul_rn(z[k], r[k]));
+  const T rz_new = block_sum(zp, red);
+  if (a.mode == MODE_STEP) {
+    const T rz_old = a.rz[b];
+    const bool dead = rz_old <= min_float;
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) {
+      const T upd = dead ? T(0) : div_rn(mul_rn(p[k], rz_new), rz_old);
+      p[k] = add_rn(z[k], upd);
+    }
+  } else {
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) p[k] = z[k];
+  }
+  __syncthreads();  // every thread has read rz_old before it is overwritten
+  if (threadIdx.x == 0) {
+    a.rz[b] = rz_new;
+    if (a.half_rz) a.half_rz[b] = T(0.5) * rz_new;
+  }
+  if (!a.state) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&a.state[2], 1) == a.B - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int it = (a.mode == MODE_INIT) ? 0 : a.state[1] + 1;
+  int over = 0;
+  const volatile T* hr = a.half_rr;
+  for (int k = threadIdx.x; k < a.B; k += blockDim.x) {
+    const T h = hr[k];
+    if (h > a.threshold) over = 1;
+    if (a.history && it < a.history_cap) a.history[(int64_t)it * a.B + k] = h;
+  }
+  over = __syncthreads_or(over);
+  if (threadIdx.x == 0) {
+    a.state[1] = it;
+    a.state[2] = 0;
+    a.state[0] = (over && it < a.max_iterations) ? 1 : 0;
+  }
+}
+
 template <typename T>
 static int launch_step(cggp_ctx* ctx, const StepArgs<T>& a) {
-  ProfScope prof(ctx, 2);
-  cg_step_kernel<T><<<a.B, 512, 0, ctx->stream>>>(a);
-  CGGP_LAUNCH_CHECK(ctx);
+  {
+    ProfScope prof(ctx, 2);
+    cg_step_kernel<T><<<a.B, 512, 0, ctx->stream>>>(a);
+    CGGP_LAUNCH_CHECK(ctx);
+  }
+  if (a.defer && a.mode != MODE_PRE) {
+    // z = r @ Pinv (symmetric, HBM-bound for few right-hand sides), then the second half of the iteration
+    int rc = cggp_symm_matmul_ex(ctx, sizeof(T) == 8 ? CGGP_F64 : CGGP_F32, a.pinv, a.ldpinv, a.n, a.r, a.n, a.B, a.z,
+                                 a.n, nullptr, 0, 0.0, a.state);
+    if (rc) return rc;
+    ProfScope prof(ctx, 2);
+    cg_finish_kernel<T><<<a.B, 512, 0, ctx->stream>>>(a);
+    CGGP_LAUNCH_CHECK(ctx);
+  }
   return CGGP_OK;
 }
 
@@ -239,6 +313,14 @@ static void fill_precond(StepArgs<T>& a, const cggp_precond* pc) {
   a.block_size = 0;
   a.block_idx = nullptr;
   a.chol = nullptr;
+  a.defer = 0;
+  a.pinv = nullptr;
+  a.ldpinv = 0;
+  if (pc && pc->type == CGGP_PRECOND_DENSE) {
+    a.defer = 1;
+    a.pinv = (const T*)pc->dev_pinv;
+    a.ldpinv = pc->ldpinv;
+  }
   if (pc && pc->type == CGGP_PRECOND_BLOCK) {
     a.num_blocks = pc->num_blocks;
     a.block_size = pc->block_size;
@@ -249,6 +331,10 @@ static void fill_precond(StepArgs<T>& a, const cggp_precond* pc) {
 
 static int check_precond(cggp_ctx* ctx, const cggp_precond* pc, int64_t n) {
   if (!pc || pc->type == CGGP_PRECOND_EYE) return CGGP_OK;
+  if (pc->type == CGGP_PRECOND_DENSE) {
+    if (!pc->dev_pinv || pc->ldpinv < n) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "dense preconditioner needs a [n, n] matrix");
+    return CGGP_OK;
+  }
   if (pc->type != CGGP_PRECOND_BLOCK) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "unknown preconditioner type %d", pc->type);
   if (pc->block_size < 1 || pc->block_size > MAX_BS)
     CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "block_size %d outside [1, %d]", pc->block_size, MAX_BS);
@@ -272,7 +358,7 @@ static int fused_step_impl(cggp_ctx* ctx, int B, int64_t n, const void* pA, void
   a.rz = (T*)rz;
   a.half_rr = (T*)half_rr;
   fill_precond(a, pc);
-  if (a.num_blocks > 0) {
+  if (a.num_blocks > 0 || a.defer) {
     int rc = cggp_ws2_reserve(ctx, sizeof(T) * (size_t)B * n);
     if (rc) return rc;
     a.z = (T*)cggp_ws2_ptr(ctx);
@@ -316,7 +402,7 @@ static int cg_solve_impl(cggp_ctx* ctx, const cggp_operator* op, const void* rhs
                          int64_t history_cap) {
   const int64_t n = op->n;
   const size_t vec = sizeof(T) * (size_t)B * n;
-  const bool block = pc && pc->type == CGGP_PRECOND_BLOCK;
+  const bool block = pc && (pc->type == CGGP_PRECOND_BLOCK || pc->type == CGGP_PRECOND_DENSE);  // needs a z buffer
   const bool sgpr = op->type == CGGP_OP_SGPR;
   // r, p, q (+ z) (+ w) and the per-row scalars
   size_t need = vec * (3 + (block ? 1 : 0) + (sgpr ? 1 : 0)) + sizeof(T) * 3 * (size_t)B + 256;

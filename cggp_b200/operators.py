@@ -130,5 +130,33 @@ class SGPROperator(LinearOperator):
         return out
 
 
+    def nystrom_preconditioner(self, num_rows: int = None, seed: int = 0):
+        """Preconditioner for ``Sigma``: ``P = Kuu + jitter I + (N / n_s) Kuf_s Kfu_s / noise`` from a uniform
+        subsample of ``n_s`` training rows (default ``4 M`` over all ranks), inverted once through a Cholesky
+        factorisation (setup cost ``n_s M^2 + M^3``; library factorisation, outside the hot loop).  Every rank draws
+        its share of the subsample from its own shard; the ``[M, M]`` Gram matrix and the row counts are all-reduced,
+        so all ranks hold the same ``Pinv``.  Returns a ``DensePreconditioner``."""
+        from .conjugate_gradient import DensePreconditioner
+
+        ctx = _lib.context(self.device)
+        world = ctx.world
+        n_loc = self.PX.n
+        want = (4 * self.n if num_rows is None else int(num_rows))
+        take = min(n_loc, max(1, want // world))
+        gen = torch.Generator(device="cpu").manual_seed(seed + 7919 * ctx.rank)
+        idx = torch.randperm(n_loc, generator=gen)[:take].sort().values.to(self.device)
+        sub = PreparedPoints(self.PX.P[idx].contiguous(), self.PX.norms[idx].contiguous(), self.PX.D)
+        Kzs = kernel_matrix(self.kernel.kind, self.kernel.variance, self.PZ, sub)  # [M, take]
+        gram = Kzs @ Kzs.t()
+        counts = torch.tensor([float(take), float(n_loc)], dtype=self.dtype, device=self.device)
+        if world > 1:
+            ctx.allreduce_sum_(gram)
+            ctx.allreduce_sum_(counts)
+        scale = float(counts[1] / counts[0]) / self.noise_variance
+        P = self.Kuu + scale * gram
+        L = torch.linalg.cholesky(P)
+        return DensePreconditioner(torch.cholesky_inverse(L))
+
+
 def as_operator(matrix) -> LinearOperator:
     return matrix if isinstance(matrix, LinearOperator) else DenseOperator(matrix)

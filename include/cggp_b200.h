@@ -152,8 +152,11 @@ typedef struct cggp_operator {
 } cggp_operator;
 
 enum cggp_precond_type {
-  CGGP_PRECOND_EYE = 0,   /* EyePreconditioner, cggp/conjugate_gradient.py:131-134 */
-  CGGP_PRECOND_BLOCK = 1  /* BlockPreconditioner (intent of :137-157): z[blk] = A[blk,blk]^-1 r[blk] */
+  CGGP_PRECOND_EYE = 0,    /* EyePreconditioner, cggp/conjugate_gradient.py:131-134 */
+  CGGP_PRECOND_BLOCK = 1,  /* BlockPreconditioner (intent of :137-157): z[blk] = A[blk,blk]^-1 r[blk] */
+  CGGP_PRECOND_DENSE = 2   /* z = r @ Pinv for a symmetric [n, n] matrix Pinv ~ A^-1 held on the device (Nystrom- /
+                              Cholesky-style preconditioner of the matrix-free operator: the reference's protocol
+                              `__call__(vec, mat) -> (z, rz)`, :125-128, with the factorisation done once up front) */
 };
 
 typedef struct cggp_precond {
@@ -164,6 +167,8 @@ typedef struct cggp_precond {
   const int64_t* dev_block_indices; /* [num_blocks, block_size], a partition of 0..n-1 */
   const void* dev_chol;             /* [num_blocks, block_size, block_size] lower Cholesky factors
                                        (cggp_block_cholesky), or NULL for EYE */
+  const void* dev_pinv;             /* CGGP_PRECOND_DENSE: symmetric [n, n], row-major */
+  int64_t ldpinv;
 } cggp_precond;
 
 /* Gather the diagonal blocks A[blk, blk] of a dense symmetric matrix and factorise them (lower Cholesky). */

@@ -50,6 +50,19 @@ class BlockPreconditioner:
         return new_vec, np.sum(new_vec * vec, axis=-1, keepdims=True)
 
 
+class DensePreconditioner:
+    """``z = vec @ Pinv`` for a symmetric ``Pinv ~ A^-1`` (a Nystrom- / Cholesky-style preconditioner in the reference's
+    protocol ``__call__(vec, mat) -> (z, rz)``, cggp/conjugate_gradient.py:125-128; the reference ships none for the
+    matrix-free operator, this is the restatement of the new path's ``DensePreconditioner``)."""
+
+    def __init__(self, pinv):
+        self.pinv = np.asarray(pinv)
+
+    def __call__(self, vec, mat):
+        z = vec @ self.pinv
+        return z, np.sum(z * vec, axis=-1, keepdims=True)
+
+
 def conjugate_gradient(
     matrix,
     rhs,

@@ -42,3 +42,15 @@ def assert_close_with_noise(actual, ref, alts, base_rtol, what=""):
     tol = base_rtol * scale + SLACK * deviation(ref, alts)
     err = float(np.max(np.abs(np.asarray(actual) - ref))) if ref.size else 0.0
     assert err <= tol, f"{what}: |cuda - reference| = {err:.3e} > {tol:.3e} (scale {scale:.3e}, noise {deviation(ref, alts):.3e})"
+
+
+class PermutedDensePreconditioner(ocg.DensePreconditioner):
+    """The oracle's DensePreconditioner with `vec @ Pinv` summed in a seeded permuted order."""
+
+    def __init__(self, pinv, seed):
+        super().__init__(pinv)
+        self.perm = np.random.default_rng(1000 + seed).permutation(self.pinv.shape[0])
+
+    def __call__(self, vec, mat):
+        z = vec[:, self.perm] @ self.pinv[self.perm, :]
+        return z, np.sum(z * vec, axis=-1, keepdims=True)
