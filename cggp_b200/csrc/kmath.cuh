@@ -71,6 +71,31 @@ __device__ __forceinline__ double fast_sqrt_pos(double u) {
   return g;
 }
 
+// Same, for the issue-bound pipelined matvec: the low word of the seed is left UNDEFINED instead of zeroed (one
+// integer move less per use).  Any low word perturbs the 2^-22.9 seed by < 2^-20 relative; the two corrected Newton
+// steps square the error twice (2^-20 -> 2^-39 -> 2^-77), so the result is unchanged to the last bit or two.
+__device__ __forceinline__ double fast_sqrt_pos_lean(double u) {
+  double y, h;
+  asm("{\n"
+      ".reg .b32 ulo, uhi, yhi, hhi;\n"
+      ".reg .f64 yy;\n"
+      "rsqrt.approx.ftz.f64 yy, %2;\n"
+      "mov.b64 {ulo, yhi}, yy;\n"
+      "mov.b64 {ulo, uhi}, %2;\n"
+      "add.s32 hhi, yhi, -1048576;\n"
+      "mov.b64 %0, {ulo, yhi};\n"
+      "mov.b64 %1, {ulo, hhi};\n"
+      "}\n"
+      : "=d"(y), "=d"(h)
+      : "d"(u));
+  double g = u * y;
+  double e = fma(-g, g, u);
+  g = fma(e, h, g);
+  e = fma(-g, g, u);
+  g = fma(e, h, g);
+  return g;
+}
+
 // exp(x) for x <= ~0 (any x in [-745, 700] works).  x*32/ln2 = n + f, n = 32 k + j:
 //   exp(x) = 2^k * 2^(j/32) * exp(d),  d = x - n ln2/32,  |d| <= ln2/64
 // 2^(j/32) comes from a 32-entry table held one entry per lane (two SHFLs, no shared memory), exp(d) from a

@@ -132,9 +132,18 @@ __device__ __forceinline__ double kval(double q, const FastExpTable& tab) {
     const unsigned h = min((unsigned)__double2hiint(q), 0xC0862000u);
     return fast_exp_core(__hiloint2double((int)h, __double2loint(q)), tab);
   } else {
-    const int h = min(max(__double2hiint(q), Fam<KIND>::clamp_hi), 0x411e9840);
-    const double qc = __hiloint2double(h, __double2loint(q));
-    const double a = fast_sqrt_pos(qc);
+    // in place on the register pair (the compiler otherwise copies the low word to a fresh pair)
+    double qc = q;
+    asm("{\n"
+        ".reg .b32 lo, hi;\n"
+        "mov.b64 {lo, hi}, %0;\n"
+        "max.s32 hi, hi, %1;\n"
+        "min.s32 hi, hi, 0x411e9840;\n"
+        "mov.b64 %0, {lo, hi};\n"
+        "}\n"
+        : "+d"(qc)
+        : "n"(Fam<KIND>::clamp_hi));
+    const double a = fast_sqrt_pos_lean(qc);
     const double e = fast_exp_neg_core(a, tab);
     if constexpr (KIND == CGGP_MATERN12) {
       return e;

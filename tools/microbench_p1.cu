@@ -41,12 +41,13 @@ __device__ __forceinline__ double fexpneg(double a, int thi, int tlo, const doub
   if (EXPMODE == 2) return q;
   int hi, lo;
   if (EXPMODE == 0) { hi = __shfl_sync(0xffffffffu, thi, n); lo = __shfl_sync(0xffffffffu, tlo, n); }
+  else if (EXPMODE == 3) { hi = __shfl_sync(0xffffffffu, thi, n); lo = 0; }
   else { double tv = stab[n & 31]; hi = __double2hiint(tv); lo = __double2loint(tv); }
-  hi += (n >> 5) << 20;
+  hi += n << 15;  // biased table
   return __hiloint2double(hi, lo) * q;
 }
 
-template <bool DMMA, int SQRT, bool EXP, int EXPMODE, int RB>
+template <bool DMMA, int SQRT, bool EXP, int EXPMODE, int RB, bool TPRED = false>
 __global__ void __launch_bounds__(1024) p1_kernel(double* out, int iters, double s) {
   __shared__ double stab[32];
   if (threadIdx.x < 32) stab[threadIdx.x] = exp2(threadIdx.x / 32.0);
@@ -94,6 +95,10 @@ __global__ void __launch_bounds__(1024) p1_kernel(double* out, int iters, double
         w[cb][0] = fma(k[0], xa, w[cb][0]);  // stands in for phase 2 (1 DFMA per entry)
         w[cb][1] = fma(k[1], xa, w[cb][1]);
       }
+      if (TPRED) {
+        tp += __shfl_xor_sync(0xffffffffu, tp, 1);
+        tp += __shfl_xor_sync(0xffffffffu, tp, 2);
+      }
       tsum += tp;
     }
   }
@@ -108,11 +113,11 @@ template <typename F> float run(F f, int reps = 3) {
   return best;
 }
 
-template <bool DMMA, int SQRT, bool EXP, int EXPMODE>
+template <bool DMMA, int SQRT, bool EXP, int EXPMODE, bool TPRED = false>
 void bench(const char* name, double* out, int sms, double fp64_per_entry) {
   const int iters = 2000;
-  for (int threads : {256, 512, 1024}) {
-    float ms = run([&] { p1_kernel<DMMA, SQRT, EXP, EXPMODE, 6><<<sms, threads>>>(out, iters, 0.999); });
+  for (int threads : {512, 1024}) {
+    float ms = run([&] { p1_kernel<DMMA, SQRT, EXP, EXPMODE, 6, TPRED><<<sms, threads>>>(out, iters, 0.999); });
     const double entries = (double)sms * threads * iters * 6 * 4;
     const double slots = fp64_per_entry + (DMMA ? 12.0 : 2.0);
     const double peak = sms * 64.0 * 1.965e9;  // DFMA-equivalent slots / s at the max clock
@@ -128,6 +133,8 @@ int main() {
   // FP64 (non-DMMA) instructions per entry: sqrt5 5 / sqrt3 3, poly 2 (DADD + DFMA), exp 9 (8 without table multiply),
   // K multiply 1, contractions 2
   bench<true, 5, true, 0>("full (DMMA, sqrt5, exp SHFL)", out, sms, 19);
+  bench<true, 5, true, 0, true>("full + quad reduction of t", out, sms, 19.5);
+  bench<true, 5, true, 3>("full, ONE SHFL (timing only)", out, sms, 19);
   bench<true, 5, true, 1>("full (DMMA, sqrt5, exp LDS)", out, sms, 19);
   bench<true, 5, true, 2>("full (DMMA, sqrt5, exp no table)", out, sms, 18);
   bench<true, 3, true, 0>("DMMA, sqrt3, exp SHFL", out, sms, 17);
