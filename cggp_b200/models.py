@@ -277,6 +277,41 @@ class SGPR:
             self._c = self.conjugate_gradient(self.operator, rhs)
         return self._c
 
+    def elbo(self) -> Tensor:
+        """GPflow ``SGPR.elbo`` (Titsias' collapsed bound; the objective behind ``cli_utils.sgpr_class``,
+        cli_utils.py:444-446), same terms in the same order as GPflow: needs ``log det B`` and ``tr(A A^T)``, hence the
+        materialised ``[M, M]`` Gram matrix ``Kuf Kfu`` (all-reduced over ranks) and two ``M x M`` Cholesky
+        factorisations (library calls; this is the reference's own algorithm for this quantity)."""
+        import math
+
+        op, ctx = self.operator, _lib.context(self.operator.device)
+        s2 = self.likelihood.variance
+        P = self.Y.shape[1]
+        G = op.gram()
+        KufY = op.kuf_times(self.Y)  # [M, P], all-reduced
+        stats = torch.stack([torch.tensor(float(self.X.shape[0]), dtype=self.Y.dtype, device=self.Y.device),
+                             (self.Y * self.Y).sum()])
+        if ctx.world > 1:
+            ctx.allreduce_sum_(stats)
+        n_total, sum_y2 = float(stats[0]), stats[1]
+        L = torch.linalg.cholesky(op.Kuu)
+        AAT = torch.linalg.solve_triangular(L, torch.linalg.solve_triangular(L, G, upper=False).t(), upper=False) / s2
+        AAT = 0.5 * (AAT + AAT.t())
+        B = AAT + torch.eye(op.n, dtype=AAT.dtype, device=AAT.device)
+        LB = torch.linalg.cholesky(B)
+        Aerr = torch.linalg.solve_triangular(L, KufY, upper=False) / s2  # A @ (Y / sigma)
+        c = torch.linalg.solve_triangular(LB, Aerr, upper=False)
+        const = -0.5 * n_total * P * math.log(2.0 * math.pi)
+        half_logdet_B = torch.log(torch.diagonal(LB)).sum()
+        trace_k = n_total * self.kernel.variance / s2
+        trace_q = torch.trace(AAT)
+        logdet = -P * (half_logdet_B + 0.5 * n_total * math.log(s2) + 0.5 * (trace_k - trace_q))
+        quad = -0.5 * (sum_y2 / s2 - (c * c).sum())
+        return const + logdet + quad
+
+    def maximum_log_likelihood_objective(self) -> Tensor:
+        return self.elbo()
+
     def predict_f(self, Xnew, full_cov: bool = False, full_output_cov: bool = False) -> Moments:
         assert not full_output_cov and not full_cov
         Xnew = _lib.as_device_tensor(Xnew, self.X.dtype)

@@ -130,6 +130,22 @@ class SGPROperator(LinearOperator):
         return out
 
 
+    def gram(self, rows: PreparedPoints = None) -> torch.Tensor:
+        """``Kuf Kfu`` as a dense ``[M, M]`` matrix over the local shard (+ all-reduce when ``rows`` is None): the
+        materialised form GPflow's SGPR builds (``A A^T``), needed where a log-determinant or a trace is required
+        (``SGPR.elbo``).  Row chunks of ``Kuf`` are evaluated on the fly by ``cggp_kernel_matrix``; the rank-k updates
+        are plain library GEMMs (cuBLAS DGEMM: ``N M^2`` flop, not on the per-iteration path)."""
+        src = self.PX if rows is None else rows
+        G = torch.zeros((self.n, self.n), dtype=self.dtype, device=self.device)
+        step = max(1, (1 << 27) // max(self.n, 1))
+        for s in range(0, src.n, step):
+            Kzx = kernel_matrix(self.kernel.kind, self.kernel.variance, self.PZ, src.rows(s, min(src.n, s + step)))
+            G.addmm_(Kzx, Kzx.t())
+        ctx = _lib.context(self.device)
+        if rows is None and ctx.world > 1:
+            ctx.allreduce_sum_(G)
+        return G
+
     def nystrom_preconditioner(self, num_rows: int = None, seed: int = 0):
         """Preconditioner for ``Sigma``: ``P = Kuu + jitter I + (N / n_s) Kuf_s Kfu_s / noise`` from a uniform
         subsample of ``n_s`` training rows (default ``4 M`` over all ranks), inverted once through a Cholesky
@@ -146,8 +162,7 @@ class SGPROperator(LinearOperator):
         gen = torch.Generator(device="cpu").manual_seed(seed + 7919 * ctx.rank)
         idx = torch.randperm(n_loc, generator=gen)[:take].sort().values.to(self.device)
         sub = PreparedPoints(self.PX.P[idx].contiguous(), self.PX.norms[idx].contiguous(), self.PX.D)
-        Kzs = kernel_matrix(self.kernel.kind, self.kernel.variance, self.PZ, sub)  # [M, take]
-        gram = Kzs @ Kzs.t()
+        gram = self.gram(sub)
         counts = torch.tensor([float(take), float(n_loc)], dtype=self.dtype, device=self.device)
         if world > 1:
             ctx.allreduce_sum_(gram)

@@ -569,6 +569,21 @@ def test_sgpr_predict_matrix_free_vs_gpflow_restatement(cb):
     np.testing.assert_allclose(cpu(var), ref_var, rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("name", ["se", "matern32", "matern52"])
+def test_sgpr_elbo_vs_gpflow_restatement(cb, name):
+    rng = np.random.default_rng(14)
+    N, M, D = 2100, 50, 3
+    X = rng.uniform(-2, 2, (N, D))
+    Y = np.sin(2 * X[:, :1]) + 0.1 * rng.standard_normal((N, 2))
+    Z = rng.uniform(-2, 2, (M, D))
+    ls = [0.9, 1.4, 1.1]
+    ok = g.KERNELS[name](variance=1.2, lengthscales=ls)
+    k = cb.kernels.KERNELS[name](variance=1.2, lengthscales=ls)
+    ref = g.SGPR((X, Y), ok, Z, noise_variance=0.2).elbo()
+    model = cb.sgpr_class((dev(X), dev(Y)), k, cb.Gaussian(0.2), dev(Z))
+    np.testing.assert_allclose(float(model.elbo()), ref, rtol=1e-8)
+
+
 def test_dlpack_zero_copy_import(cb):
     """Foreign device tensors come in through __dlpack__ without a copy (TF: tf.experimental.dlpack)."""
 
