@@ -311,7 +311,7 @@ def run_native(args):
         except Exception:
             traffic = None
     roofline = {
-        "kernel": "kfu_fused_kernel (fused Kuf Kfu product)",
+        "kernel": "kpipe::kfu_pipe_kernel (fused, software-pipelined Kuf Kfu product)",
         "bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
         "frac": (achieved / peak_tflops) if (achieved and peak_tflops) else None,
         "traffic": traffic, "peak_source": peak_src,

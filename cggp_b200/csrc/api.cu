@@ -17,6 +17,9 @@ int cggp_matvec_pipe(cggp_ctx* ctx, int kind, double variance, const double* PX,
                      const double* PZ, const double* nZ, int64_t m, int D, int64_t ldp, const double* V, int64_t ldv,
                      int B, double* W, int64_t ldw, const int* active);
 bool cggp_matvec_pipe_supported(cggp_ctx* ctx, int dtype, int64_t m, int D, int B);
+int cggp_kuf_times_pipe(cggp_ctx* ctx, int kind, double variance, const double* PX, const double* nX, int64_t n,
+                        const double* PZ, const double* nZ, int64_t m, int D, int64_t ldp, const double* Y, int64_t ldy,
+                        int P, double* W, int64_t ldw);
 
 static std::string g_err;  // errors raised without a ctx
 
@@ -279,6 +282,19 @@ extern "C" int cggp_kuf_kfu_matvec(cggp_ctx* ctx, int dtype, int kind, double va
   if (variant < 0 || variant > 3) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "variant must be 0, 1, 2 or 3");
   return cggp_matvec_dispatch(ctx, dtype, kind, variance, PX, nX, n, PZ, nZ, m, D, ldp, V, ldv, B, W, ldw, variant,
                               nullptr);
+}
+
+extern "C" int cggp_kuf_times(cggp_ctx* ctx, int dtype, int kind, double variance, const void* PX, const void* nX,
+                              int64_t n, const void* PZ, const void* nZ, int64_t m, int D, int64_t ldp, const void* Y,
+                              int64_t ldy, int P, void* W, int64_t ldw) {
+  if (!ctx) return CGGP_ERR_INVALID;
+  if (P <= 0 || m <= 0) return CGGP_OK;
+  if (kind < CGGP_SE || kind > CGGP_MATERN52) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "unknown kernel kind %d", kind);
+  if (!cggp_matvec_pipe_supported(ctx, dtype, m, D, P))
+    CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "fused Kuf @ Y needs float64 and D <= 15 (dtype=%d, D=%d)", dtype, D);
+  ProfScope prof(ctx, 0);
+  return cggp_kuf_times_pipe(ctx, kind, variance, (const double*)PX, (const double*)nX, n, (const double*)PZ,
+                             (const double*)nZ, m, D, ldp, (const double*)Y, ldy, P, (double*)W, ldw);
 }
 
 // ---------------------------------------------------------------------------------------------------------

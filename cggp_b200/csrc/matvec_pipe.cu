@@ -51,6 +51,8 @@ struct Args {
   int C, G;
   int64_t nblocks;
   int tma_ok;     // PX / nX are 16-byte aligned and ldp == KS * 4: full tiles go through cp.async.bulk
+  const double* Tin;  // "t given" mode (Kuf @ Y): per-row weights [n, ldt] instead of the phase-1 contraction
+  int64_t ldt;
   int dbg;        // timing experiments only (env CGGP_PIPE_DBG; results are WRONG when set): 1 = skip phase 2,
                   // 2 = skip the L2 exchange
   const int* active;
@@ -267,6 +269,19 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
         }
         sum[q] = v;
       }
+      if (a.Tin) {
+        // Kuf @ Y: the row weights are given, no contraction / exchange; K carries one factor `variance`
+#pragma unroll
+        for (int q = 0; q < (BM * NB + 31) / 32; ++q) {
+          const int e = q * 32 + lane;
+          if (e < BM * NB) {
+            const int64_t row = r0 + e / NB;
+            tf[e] = row < a.n ? a.Tin[row * a.ldt + e % NB] * a.variance2 : 0.0;
+          }
+        }
+        mbar_arrive(&mbarF[par]);
+        continue;
+      }
       if (a.C > 1 && !(a.dbg & 2)) {
         double* mine = slots_g + ((int64_t)(it % SLOTS) * a.C + rank) * (BM * NB);
 #pragma unroll
@@ -327,8 +342,8 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
     const int64_t vc = col0 + cb * 8 + 2 * lk;  // C fragment: columns 2 lk, 2 lk + 1
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-      vv[cb][b].x = vc < a.m ? a.V[(int64_t)b * a.ldv + vc] : 0.0;
-      vv[cb][b].y = vc + 1 < a.m ? a.V[(int64_t)b * a.ldv + vc + 1] : 0.0;
+      vv[cb][b].x = (a.V && vc < a.m) ? a.V[(int64_t)b * a.ldv + vc] : 0.0;
+      vv[cb][b].y = (a.V && vc + 1 < a.m) ? a.V[(int64_t)b * a.ldv + vc + 1] : 0.0;
     }
   }
   double wacc[CBW][2][NB];
@@ -541,9 +556,27 @@ bool cggp_matvec_pipe_supported(cggp_ctx* ctx, int dtype, int64_t m, int D, int 
   return C <= ctx->sm_count;
 }
 
+static int pipe_launch(cggp_ctx* ctx, int kind, double variance, const double* PX, const double* nX, int64_t n,
+                       const double* PZ, const double* nZ, int64_t m, int D, int64_t ldp, const double* V, int64_t ldv,
+                       int B, double* W, int64_t ldw, const int* active, const double* Tin, int64_t ldt);
+
 int cggp_matvec_pipe(cggp_ctx* ctx, int kind, double variance, const double* PX, const double* nX, int64_t n,
                      const double* PZ, const double* nZ, int64_t m, int D, int64_t ldp, const double* V, int64_t ldv,
                      int B, double* W, int64_t ldw, const int* active) {
+  return pipe_launch(ctx, kind, variance, PX, nX, n, PZ, nZ, m, D, ldp, V, ldv, B, W, ldw, active, nullptr, 0);
+}
+
+// W[b, :] = sum_i k(z_:, x_i) Y[i, b]  (Kuf @ Y for the local shard): the phase-2 contraction of the pipelined kernel
+// with the row weights given.  V is a dummy (any [B, m] buffer of finite numbers, e.g. W itself is NOT allowed).
+int cggp_kuf_times_pipe(cggp_ctx* ctx, int kind, double variance, const double* PX, const double* nX, int64_t n,
+                        const double* PZ, const double* nZ, int64_t m, int D, int64_t ldp, const double* Y, int64_t ldy,
+                        int P, double* W, int64_t ldw) {
+  return pipe_launch(ctx, kind, variance, PX, nX, n, PZ, nZ, m, D, ldp, nullptr, 0, P, W, ldw, nullptr, Y, ldy);
+}
+
+static int pipe_launch(cggp_ctx* ctx, int kind, double variance, const double* PX, const double* nX, int64_t n,
+                       const double* PZ, const double* nZ, int64_t m, int D, int64_t ldp, const double* V, int64_t ldv,
+                       int B, double* W, int64_t ldw, const int* active, const double* Tin, int64_t ldt) {
   using namespace kpipe;
   const int ks = (D + 1 + 3) / 4;
   int b0 = 0;
@@ -569,8 +602,10 @@ int cggp_matvec_pipe(cggp_ctx* ctx, int kind, double variance, const double* PX,
     char* base = (char*)ctx->ws;
     Args a;
     a.PX = PX; a.nX = nX; a.n = n; a.PZ = PZ; a.nZ = nZ; a.m = m; a.D = D; a.ldp = ldp;
-    a.V = V + (int64_t)b0 * ldv; a.ldv = ldv;
-    a.variance2 = variance * variance;
+    a.V = V ? V + (int64_t)b0 * ldv : nullptr; a.ldv = ldv;
+    a.variance2 = Tin ? variance : variance * variance;
+    a.Tin = Tin ? Tin + b0 : nullptr;
+    a.ldt = ldt;
     a.Wp = (double*)base;
     a.part = (double*)(base + wp_bytes);
     a.counters = (int*)(base + wp_bytes + part_bytes);

@@ -117,7 +117,20 @@ class SGPROperator(LinearOperator):
     def kuf_times(self, Y):
         """``Kuf @ Y`` for the local shard ``Y [n_local, P]`` (+ all-reduce): the right-hand side ``Kuf y``.
         Computed in row batches so that nothing of size N x M is ever resident."""
-        Y = _lib.as_device_tensor(Y, self.dtype)
+        Y = _lib.row_major(_lib.as_device_tensor(Y, self.dtype))
+        ctx = _lib.context(self.device)
+        if self.dtype == torch.float64 and self.PZ.D <= 15 and self.n <= 256 * 148 and self.variant in (0, 3):
+            # fused: phase 2 of the pipelined kernel with the row weights given (cggp_kuf_times)
+            ctx.use_current_stream()
+            W = torch.empty((Y.shape[1], self.n), dtype=self.dtype, device=self.device)
+            ctx.check(ctx.lib.cggp_kuf_times(
+                ctx.handle, _lib.dtype_code(self.dtype), self.kernel.kind, self.kernel.variance, _lib.ptr(self.PX.P),
+                _lib.ptr(self.PX.norms), self.PX.n, _lib.ptr(self.PZ.P), _lib.ptr(self.PZ.norms), self.n, self.PZ.D,
+                self.PZ.ldp, _lib.ptr(Y), Y.stride(0), Y.shape[1], _lib.ptr(W), W.stride(0)))
+            out = W.t().contiguous()
+            if ctx.world > 1:
+                ctx.allreduce_sum_(out)
+            return out
         out = torch.zeros((self.n, Y.shape[1]), dtype=self.dtype, device=self.device)
         step = max(1, (1 << 27) // max(self.n, 1))
         for s in range(0, self.PX.n, step):

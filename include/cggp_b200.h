@@ -117,6 +117,15 @@ int cggp_kuf_kfu_matvec(cggp_ctx* ctx, int dtype, int kind, double variance,
                         const void* dev_PZ, const void* dev_normsZ, int64_t m, int D, int64_t ldp,
                         const void* dev_V, int64_t ldv, int B, void* dev_W, int64_t ldw, int variant);
 
+/* W[p, j] = sum_i k(z_j, x_i) Y[i, p]   (Kuf @ Y over this rank's shard, the right-hand side `Kuf y` of the SGPR
+ * system and GPflow's `A @ err`): fused, Kuf never materialised (the second contraction of the pipelined kernel with
+ * the row weights given).  Y is [n, ldy] row-major with P columns, W is [P, ldw].  float64, D <= 15; CGGP_ERR_UNSUPPORTED
+ * otherwise (the Python layer then forms Kuf in row chunks with cggp_kernel_matrix).  Not all-reduced. */
+int cggp_kuf_times(cggp_ctx* ctx, int dtype, int kind, double variance,
+                   const void* dev_PX, const void* dev_normsX, int64_t n,
+                   const void* dev_PZ, const void* dev_normsZ, int64_t m, int D, int64_t ldp,
+                   const void* dev_Y, int64_t ldy, int P, void* dev_W, int64_t ldw);
+
 /* Y[B, n] = V[B, n] @ A[n, n] for SYMMETRIC A (CG's `state.p @ A`, cggp/conjugate_gradient.py:65,74,87). */
 int cggp_symm_matmul(cggp_ctx* ctx, int dtype, const void* dev_A, int64_t lda, int64_t n,
                      const void* dev_V, int64_t ldv, int B, void* dev_Y, int64_t ldy);

@@ -444,6 +444,12 @@ def test_fused_matvec_many_row_blocks_matches_two_sweep(cb, N, M, D, name):
         W = op.kuf_kfu_matmul(V, variant=variant)
         np.testing.assert_allclose(cpu(W), cpu(ref), rtol=1e-11, atol=1e-12 * float(ref.abs().max()))
         assert torch.equal(W, op.kuf_kfu_matmul(V, variant=variant))  # bitwise reproducible
+    # Kuf @ Y: fused (row weights given to the pipelined kernel) vs Kuf formed in row chunks, 3 columns
+    Y = torch.randn(N, 3, dtype=torch.float64, device="cuda", generator=gen)
+    fused = op.kuf_times(Y)
+    chunked = cb.SGPROperator(k, X, Z, 0.1, variant=1).kuf_times(Y)
+    assert tuple(fused.shape) == (M, 3)
+    np.testing.assert_allclose(cpu(fused), cpu(chunked), rtol=1e-11, atol=1e-12 * float(chunked.abs().max()))
 
 
 @pytest.mark.parametrize("variant", [1, 2, 3])
