@@ -39,6 +39,9 @@ class Operator(C.Structure):
         ("dev_PX", C.c_void_p), ("dev_normsX", C.c_void_p), ("n_local", C.c_int64),
         ("dev_PZ", C.c_void_p), ("dev_normsZ", C.c_void_p), ("ldp", C.c_int64),
         ("variant", C.c_int32), ("_pad", C.c_int32),
+        ("dev_X32_big", C.c_void_p), ("dev_X32_small", C.c_void_p), ("dev_x32_norms", C.c_void_p),
+        ("dev_Z32_big", C.c_void_p), ("dev_Z32_small", C.c_void_p), ("dev_z32_norms", C.c_void_p),
+        ("tf32_nsplit", C.c_int32), ("_pad2", C.c_int32),
     ]
 
 
@@ -74,6 +77,11 @@ SIGNATURES = {
     "cggp_cluster_stats": (_i, [_vp, _i, _vp, _vp, _i64, _i64, _vp, _vp]),
     "cggp_kuf_kfu_matvec": (_i, [_vp, _i, _i, _d, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i64, _vp, _i64, _i, _vp,
                                   _i64, _i]),
+    "cggp_tf32_kp": (_i, [_i]),
+    "cggp_tf32_rows": (_i64, [_i64]),
+    "cggp_tf32_prepare": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _vp, _vp, _vp]),
+    "cggp_kuf_kfu_matvec_tf32": (_i, [_vp, _i, _d, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _vp,
+                                       _i64, _i]),
     "cggp_kuf_times": (_i, [_vp, _i, _i, _d, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i64, _vp, _i64, _i, _vp, _i64]),
     "cggp_symm_matmul": (_i, [_vp, _i, _vp, _i64, _i64, _vp, _i64, _i, _vp, _i64]),
     "cggp_block_cholesky": (_i, [_vp, _i, _vp, _i64, _i64, _vp, _i, _i, _vp]),

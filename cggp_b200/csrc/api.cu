@@ -284,6 +284,24 @@ extern "C" int cggp_kuf_kfu_matvec(cggp_ctx* ctx, int dtype, int kind, double va
                               nullptr);
 }
 
+int cggp_matvec_tf32(cggp_ctx* ctx, int kind, double variance, const float* Xb, const float* Xs, const float* xn,
+                     int64_t n, const float* Zb, const float* Zs, const float* zn, int64_t m, int D, const float* V,
+                     int64_t ldv, int B, float* W, int64_t ldw, int nsplit, const int* active);
+
+extern "C" int cggp_kuf_kfu_matvec_tf32(cggp_ctx* ctx, int kind, double variance, const void* Xb, const void* Xs,
+                                        const void* xn, int64_t n, const void* Zb, const void* Zs, const void* zn,
+                                        int64_t m, int D, const void* V, int64_t ldv, int B, void* W, int64_t ldw,
+                                        int nsplit) {
+  if (!ctx) return CGGP_ERR_INVALID;
+  if (B <= 0 || m <= 0) return CGGP_OK;
+  if (kind < CGGP_SE || kind > CGGP_MATERN52) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "unknown kernel kind %d", kind);
+  if (nsplit != 1 && nsplit != 3) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "nsplit must be 1 or 3");
+  ProfScope prof(ctx, 0);
+  return cggp_matvec_tf32(ctx, kind, variance, (const float*)Xb, (const float*)Xs, (const float*)xn, n,
+                          (const float*)Zb, (const float*)Zs, (const float*)zn, m, D, (const float*)V, ldv, B,
+                          (float*)W, ldw, nsplit, nullptr);
+}
+
 extern "C" int cggp_kuf_times(cggp_ctx* ctx, int dtype, int kind, double variance, const void* PX, const void* nX,
                               int64_t n, const void* PZ, const void* nZ, int64_t m, int D, int64_t ldp, const void* Y,
                               int64_t ldy, int P, void* W, int64_t ldw) {

@@ -19,6 +19,9 @@ int cggp_symm_matmul_ex(cggp_ctx* ctx, int dtype, const void* A, int64_t lda, in
 int cggp_matvec_dispatch(cggp_ctx* ctx, int dtype, int kind, double variance, const void* PX, const void* nX,
                          int64_t n, const void* PZ, const void* nZ, int64_t m, int D, int64_t ldp, const void* V,
                          int64_t ldv, int B, void* W, int64_t ldw, int variant, const int* active);
+int cggp_matvec_tf32(cggp_ctx* ctx, int kind, double variance, const float* Xb, const float* Xs, const float* xn,
+                     int64_t n, const float* Zb, const float* Zs, const float* zn, int64_t m, int D, const float* V,
+                     int64_t ldv, int B, float* W, int64_t ldw, int nsplit, const int* active);
 int cggp_ws2_reserve(cggp_ctx* ctx, size_t bytes);
 void* cggp_ws2_ptr(cggp_ctx* ctx);
 
@@ -385,7 +388,15 @@ static int apply_operator(cggp_ctx* ctx, const cggp_operator* op, const void* V,
   if (op->type == CGGP_OP_DENSE)
     return cggp_symm_matmul_ex(ctx, op->dtype, op->dev_A, op->lda, n, V, n, B, Y, n, nullptr, 0, 0.0, active);
   // W = V @ (Kuf_r Kfu_r) on this rank's shard
-  int rc = cggp_matvec_dispatch(ctx, op->dtype, op->kind, op->variance, op->dev_PX, op->dev_normsX, op->n_local,
+  int rc;
+  if (op->dtype == CGGP_F32 && op->dev_X32_big) {
+    ProfScope prof(ctx, 0);
+    rc = cggp_matvec_tf32(ctx, op->kind, op->variance, (const float*)op->dev_X32_big, (const float*)op->dev_X32_small,
+                          (const float*)op->dev_x32_norms, op->n_local, (const float*)op->dev_Z32_big,
+                          (const float*)op->dev_Z32_small, (const float*)op->dev_z32_norms, n, op->D, (const float*)V,
+                          n, B, (float*)wbuf, n, op->tf32_nsplit == 1 ? 1 : 3, active);
+  } else
+    rc = cggp_matvec_dispatch(ctx, op->dtype, op->kind, op->variance, op->dev_PX, op->dev_normsX, op->n_local,
                                 op->dev_PZ, op->dev_normsZ, n, op->D, op->ldp, V, n, B, wbuf, n, op->variant, active);
   if (rc) return rc;
   // the one collective of the path: sum the partial [B, M] products over ranks

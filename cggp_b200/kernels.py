@@ -54,6 +54,35 @@ def prepare_points(X, lengthscales, dtype=None) -> PreparedPoints:
     return PreparedPoints(P, norms, D)
 
 
+@dataclass
+class TF32Points:
+    """Prepared float32 points in the layout the tensor cores read (``cggp_tf32_prepare``): canonical K-major order,
+    rows padded to 128, split into a TF32 big and small part; norms padded with zeros."""
+
+    big: torch.Tensor
+    small: torch.Tensor
+    norms: torch.Tensor
+    n: int
+    D: int
+
+
+def prepare_tf32(points: PreparedPoints) -> TF32Points:
+    if points.P.dtype != torch.float32:
+        raise TypeError("the TF32 tensor-core path is for float32 points")
+    ctx = _lib.context(points.P.device)
+    ctx.use_current_stream()
+    kp = int(ctx.lib.cggp_tf32_kp(points.D))
+    rows = int(ctx.lib.cggp_tf32_rows(points.n))
+    dev = points.P.device
+    big = torch.empty((rows * kp,), dtype=torch.float32, device=dev)
+    small = torch.empty((rows * kp,), dtype=torch.float32, device=dev)
+    norms = torch.empty((rows,), dtype=torch.float32, device=dev)
+    P = points.P if points.P.stride(1) == 1 else points.P.contiguous()
+    ctx.check(ctx.lib.cggp_tf32_prepare(ctx.handle, _lib.ptr(P), _lib.ptr(points.norms.contiguous()), points.n,
+                                        points.D, P.stride(0), _lib.ptr(big), _lib.ptr(small), _lib.ptr(norms)))
+    return TF32Points(big, small, norms, points.n, points.D)
+
+
 def kernel_matrix(kind, variance, A: PreparedPoints, B: PreparedPoints, *, output=_lib.OUT_KERNEL,
                   distance=_lib.DIST_EUCLIDEAN, jitter=0.0, out=None) -> torch.Tensor:
     if A.D != B.D or A.ldp != B.ldp or A.P.dtype != B.P.dtype:

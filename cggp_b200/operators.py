@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .kernels import PreparedPoints, Stationary, kernel_matrix
+from .kernels import PreparedPoints, Stationary, kernel_matrix, prepare_tf32
 
 
 class LinearOperator:
@@ -63,7 +63,10 @@ class SGPROperator(LinearOperator):
     ``X`` is THIS RANK's shard of the training inputs (rows); ``Z`` and ``Kuu`` are replicated.  With a communicator
     initialised on the context (``_lib.context().init_comm()``) every application all-reduces the partial product."""
 
-    def __init__(self, kernel: Stationary, X, Z, noise_variance: float, jitter: float = 1e-6, variant: int = 0):
+    def __init__(self, kernel: Stationary, X, Z, noise_variance: float, jitter: float = 1e-6, variant: int = 0,
+                 tf32_nsplit: int = 3):
+        """``variant``: 0 auto, 1 two-sweep kernels, 2 / 3 float64 fused kernels, 4 float32 tensor-core (tcgen05 TF32)
+        kernels - the default for float32 on sm_100 where the tiles fit (D <= 104 with ``tf32_nsplit = 3``)."""
         self.kernel = kernel
         self.PZ = kernel.prepare(Z)
         self.PX = kernel.prepare(X, self.PZ.P.dtype)
@@ -74,6 +77,17 @@ class SGPROperator(LinearOperator):
         self.dtype = self.PZ.P.dtype
         self.device = self.PZ.P.device
         self.Kuu = kernel_matrix(kernel.kind, kernel.variance, self.PZ, self.PZ, jitter=self.jitter)
+        self.tf32_nsplit = int(tf32_nsplit)
+        self.X32 = self.Z32 = None
+        if self.dtype == torch.float32 and self.variant in (0, 4):
+            ctx = _lib.context(self.device)
+            kp = int(ctx.lib.cggp_tf32_kp(self.PZ.D))
+            fits = (4 if self.tf32_nsplit > 1 else 2) * 128 * kp * 4 + 4096 <= 227 * 1024
+            sm100 = torch.cuda.get_device_capability(self.device)[0] >= 10
+            if fits and sm100:
+                self.X32, self.Z32 = prepare_tf32(self.PX), prepare_tf32(self.PZ)
+            elif self.variant == 4:
+                raise _lib.CggpError("the tcgen05 TF32 path needs sm_100 and D <= 104 (3xTF32) / 216 (1xTF32)")
 
     def c_struct(self):
         op = _lib.Operator()
@@ -92,7 +106,13 @@ class SGPROperator(LinearOperator):
         op.dev_PZ = self.PZ.P.data_ptr()
         op.dev_normsZ = self.PZ.norms.data_ptr()
         op.ldp = self.PZ.ldp
-        op.variant = self.variant
+        op.variant = self.variant if self.variant != 4 else 0
+        if self.X32 is not None:
+            op.dev_X32_big, op.dev_X32_small = self.X32.big.data_ptr(), self.X32.small.data_ptr()
+            op.dev_x32_norms = self.X32.norms.data_ptr()
+            op.dev_Z32_big, op.dev_Z32_small = self.Z32.big.data_ptr(), self.Z32.small.data_ptr()
+            op.dev_z32_norms = self.Z32.norms.data_ptr()
+            op.tf32_nsplit = self.tf32_nsplit
         return op
 
     def kuf_kfu_matmul(self, V, variant=None, allreduce=True):
@@ -101,11 +121,23 @@ class SGPROperator(LinearOperator):
         ctx = _lib.context(self.device)
         ctx.use_current_stream()
         W = torch.empty_like(V)
+        use = self.variant if variant is None else int(variant)
+        if self.X32 is not None and use in (0, 4):
+            ctx.check(ctx.lib.cggp_kuf_kfu_matvec_tf32(
+                ctx.handle, self.kernel.kind, self.kernel.variance, _lib.ptr(self.X32.big), _lib.ptr(self.X32.small),
+                _lib.ptr(self.X32.norms), self.PX.n, _lib.ptr(self.Z32.big), _lib.ptr(self.Z32.small),
+                _lib.ptr(self.Z32.norms), self.n, self.PZ.D, _lib.ptr(V), V.stride(0), V.shape[0], _lib.ptr(W),
+                W.stride(0), self.tf32_nsplit))
+            if allreduce and ctx.world > 1:
+                ctx.allreduce_sum_(W)
+            return W
+        if use == 4:
+            raise _lib.CggpError("variant 4 (tcgen05 TF32) is not available for this operator")
         ctx.check(ctx.lib.cggp_kuf_kfu_matvec(
             ctx.handle, _lib.dtype_code(self.dtype), self.kernel.kind, self.kernel.variance,
             _lib.ptr(self.PX.P), _lib.ptr(self.PX.norms), self.PX.n, _lib.ptr(self.PZ.P), _lib.ptr(self.PZ.norms),
             self.n, self.PZ.D, self.PZ.ldp, _lib.ptr(V), V.stride(0), V.shape[0], _lib.ptr(W), W.stride(0),
-            self.variant if variant is None else int(variant)))
+            use))
         if allreduce and ctx.world > 1:
             ctx.allreduce_sum_(W)
         return W

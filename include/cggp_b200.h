@@ -109,13 +109,30 @@ int cggp_cluster_stats(cggp_ctx* ctx, int dtype, const int64_t* dev_idx, const v
  *   W[b, :] = V[b, :] @ (Kuf Kfu),  Kfu[i, j] = k(x_i, z_j) never materialised; X is this rank's shard.
  *   variant: 0 = auto, 1 = simple two-sweep kernels (any dtype / D), 2 = fused register-tile kernel, 3 = fused
  *   software-pipelined kernel (TMA-staged X tiles, K parked in shared memory; the default where supported:
- *   float64, D <= 15).  Variants 2 and 3 evaluate every Gram entry once per application.
+ *   float64, D <= 15).  Variants 2 and 3 evaluate every Gram entry once per application.  float32 has its own
+ *   tensor-core entry point, cggp_kuf_kfu_matvec_tf32 below.
  *   The result is NOT all-reduced; call cggp_allreduce_sum (cggp_cg_solve does it per iteration).
  * ------------------------------------------------------------------------------------------------------- */
 int cggp_kuf_kfu_matvec(cggp_ctx* ctx, int dtype, int kind, double variance,
                         const void* dev_PX, const void* dev_normsX, int64_t n,
                         const void* dev_PZ, const void* dev_normsZ, int64_t m, int D, int64_t ldp,
                         const void* dev_V, int64_t ldv, int B, void* dev_W, int64_t ldw, int variant);
+
+/* float32 on the 5th-generation tensor cores (tcgen05.mma kind::tf32, FP32 accumulators in TMEM; csrc/matvec_tf32.cu).
+ * cggp_tf32_prepare converts prepared float32 points ONCE into the layout the tensor cores read: features padded to
+ * KP = cggp_tf32_kp(D), rows padded to cggp_tf32_rows(n), canonical K-major order [row/8][k/4][row%8][k%4], split into
+ * a TF32 "big" and a TF32 "small" part (x = big + small to 2^-22), plus the norms padded with zeros.  Buffers:
+ * big, small: rows_pad * KP floats each; norms_pad: rows_pad floats.
+ * cggp_kuf_kfu_matvec_tf32: W[B, m] = V[B, m] @ (Kuf Kfu) from those arrays; nsplit = 3 -> 3xTF32 (float32-accurate
+ * distances), nsplit = 1 -> single TF32 pass (3x fewer tensor-core flops, ~1e-3 relative on the distances). */
+int cggp_tf32_kp(int D);
+int64_t cggp_tf32_rows(int64_t n);
+int cggp_tf32_prepare(cggp_ctx* ctx, const void* dev_P, const void* dev_norms, int64_t n, int D, int64_t ldp,
+                      void* dev_big, void* dev_small, void* dev_norms_pad);
+int cggp_kuf_kfu_matvec_tf32(cggp_ctx* ctx, int kind, double variance,
+                             const void* dev_Xbig, const void* dev_Xsmall, const void* dev_xnorms_pad, int64_t n,
+                             const void* dev_Zbig, const void* dev_Zsmall, const void* dev_znorms_pad, int64_t m,
+                             int D, const void* dev_V, int64_t ldv, int B, void* dev_W, int64_t ldw, int nsplit);
 
 /* W[p, j] = sum_i k(z_j, x_i) Y[i, p]   (Kuf @ Y over this rank's shard, the right-hand side `Kuf y` of the SGPR
  * system and GPflow's `A @ err`): fused, Kuf never materialised (the second contraction of the pipelined kernel with
@@ -158,6 +175,16 @@ typedef struct cggp_operator {
   int64_t ldp;
   int32_t variant;      /* as cggp_kuf_kfu_matvec */
   int32_t _pad;
+  /* float32 tensor-core path (optional, CGGP_OP_SGPR with dtype CGGP_F32): arrays from cggp_tf32_prepare; when
+   * dev_X32_big is non-NULL every application of the operator goes through cggp_kuf_kfu_matvec_tf32 */
+  const void* dev_X32_big;
+  const void* dev_X32_small;
+  const void* dev_x32_norms;
+  const void* dev_Z32_big;
+  const void* dev_Z32_small;
+  const void* dev_z32_norms;
+  int32_t tf32_nsplit;  /* 3 or 1 */
+  int32_t _pad2;
 } cggp_operator;
 
 enum cggp_precond_type {

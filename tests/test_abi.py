@@ -47,7 +47,7 @@ def test_ctypes_signatures_cover_header():
 def test_struct_layout_matches_header():
     from cggp_b200 import _lib
 
-    assert ctypes.sizeof(_lib.Operator) == 112
+    assert ctypes.sizeof(_lib.Operator) == 168
     assert ctypes.sizeof(_lib.Precond) == 48
     assert _lib.Operator.dev_PZ.offset == 80 and _lib.Operator.variant.offset == 104
 

@@ -452,6 +452,53 @@ def test_fused_matvec_many_row_blocks_matches_two_sweep(cb, N, M, D, name):
     np.testing.assert_allclose(cpu(fused), cpu(chunked), rtol=1e-11, atol=1e-12 * float(chunked.abs().max()))
 
 
+@pytest.mark.parametrize("name", KERNELS)
+@pytest.mark.parametrize("N,M,D,B", [(6000, 192, 90, 2), (1000, 130, 11, 1), (4097, 300, 3, 3), (129, 257, 24, 1)])
+def test_tf32_tensor_core_matvec_vs_oracle(cb, name, N, M, D, B):
+    """float32 product on tcgen05 (TF32 inputs split 3x, FP32 accumulators in TMEM) vs the float64 oracle on the same
+    float32 inputs: 1e-4 relative (north_star float32 tolerance); a single TF32 pass is held to 1e-2."""
+    rng = np.random.default_rng(N + D)
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    Z = rng.standard_normal((M, D)).astype(np.float32)
+    V = rng.standard_normal((B, M)).astype(np.float32)
+    ls = np.full(D, np.sqrt(D), np.float32)
+    ok = g.KERNELS[name](variance=1.3, lengthscales=ls.astype(np.float64))
+    ref = om.kuf_kfu_matmul(ok, X.astype(np.float64), Z.astype(np.float64), V.astype(np.float64))
+    k = cb.kernels.KERNELS[name](variance=1.3, lengthscales=ls)
+    op = cb.SGPROperator(k, dev(X), dev(Z), 0.1, variant=4)
+    assert op.X32 is not None
+    W = cpu(op.kuf_kfu_matmul(dev(V)))
+    assert W.dtype == np.float32
+    np.testing.assert_allclose(W, ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+    assert np.array_equal(W, cpu(op.kuf_kfu_matmul(dev(V))))  # bitwise reproducible
+    # against the FFMA two-sweep kernels (same float32 formulas)
+    W1 = cpu(op.kuf_kfu_matmul(dev(V), variant=1))
+    np.testing.assert_allclose(W, W1, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+    op1 = cb.SGPROperator(k, dev(X), dev(Z), 0.1, variant=4, tf32_nsplit=1)
+    np.testing.assert_allclose(cpu(op1.kuf_kfu_matmul(dev(V))), ref, rtol=1e-2, atol=1e-2 * np.abs(ref).max())
+
+
+def test_tf32_operator_inside_cg(cb):
+    rng = np.random.default_rng(77)
+    N, M, D = 5000, 128, 40
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    Z = X[rng.choice(N, M, replace=False)].copy()
+    y = np.sin(X[:, :2].sum(-1, keepdims=True)).astype(np.float32)
+    ls = np.full(D, np.sqrt(D), np.float32)
+    k = cb.SquaredExponential(1.0, ls)
+    ok = g.SquaredExponential(1.0, ls.astype(np.float64))
+    op = cb.SGPROperator(k, dev(X), dev(Z), 0.1)  # float32 -> tensor-core path by default
+    assert op.X32 is not None
+    rhs = (op.kuf_times(dev(y)) / 0.1).t().contiguous()
+    sol, (steps, _, h) = cb.conjugate_gradient(op, rhs, None, 0.0, None, 6, 100, return_history=True)
+    hist = []
+    orhs = (ok.K(Z.astype(np.float64), X.astype(np.float64)) @ y.astype(np.float64) / 0.1).T
+    ocg.conjugate_gradient(om.sgpr_operator(ok, X.astype(np.float64), Z.astype(np.float64), 0.1), orhs,
+                           np.zeros_like(orhs), 0.0, None, 6, 100, history=hist)
+    assert int(steps) == 6 and sol.dtype == torch.float32
+    np.testing.assert_allclose(cpu(h)[:3], np.array(hist)[:3], rtol=2e-3)
+
+
 @pytest.mark.parametrize("variant", [1, 2, 3])
 def test_matrix_free_cg_matches_oracle(cb, variant):
     rng = np.random.default_rng(3)

@@ -43,5 +43,30 @@ def main():
         best, avg = timeit(solve, reps=3, warm=1)
         print(f"{name}: CG {its} its: {best:.2f} ms -> {its / best * 1e3:.1f} it/s")
 
+def main_f32():
+    """config 5 shape (float32, D = 90, M = 8192): tensor-core path vs the FFMA two-sweep kernels, reduced N."""
+    g = torch.Generator(device="cuda").manual_seed(0)
+    N, M, D = 500_000, 8192, 90
+    X = torch.randn(N, D, dtype=torch.float32, device="cuda", generator=g)
+    Z = torch.randn(M, D, dtype=torch.float32, device="cuda", generator=g)
+    V = torch.randn(1, M, dtype=torch.float32, device="cuda", generator=g)
+    k = cb.SquaredExponential(1.0, [D ** 0.5] * D)
+    for nsplit in (3, 1):
+        op = cb.SGPROperator(k, X, Z, 0.1, variant=4, tf32_nsplit=nsplit)
+        best, avg = timeit(lambda: op.kuf_kfu_matmul(V), reps=3, warm=1)
+        flop = 2.0 * 2.0 * N * M * 96 * (3 if nsplit == 3 else 1)
+        print(f"c5/4 (N={N}): tcgen05 TF32 x{nsplit}: best {best:.3f} ms -> {flop / best / 1e9:.1f} TFLOP/s tensor, "
+              f"{2 * N * M / best / 1e6:.1f} Gentry/s (two sweeps)", flush=True)
+    op = cb.SGPROperator(k, X, Z, 0.1, variant=4)
+    W4 = op.kuf_kfu_matmul(V)
+    best1, _ = timeit(lambda: op.kuf_kfu_matmul(V, variant=1), reps=2, warm=1)
+    W1 = op.kuf_kfu_matmul(V, variant=1)
+    print(f"c5/4: FFMA two-sweep: best {best1:.3f} ms; max rel diff tf32x3 vs ffma "
+          f"{float((W4 - W1).abs().max() / W1.abs().max()):.3e}", flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if "c5" in sys.argv[1:]:
+        main_f32()
+    else:
+        main()
