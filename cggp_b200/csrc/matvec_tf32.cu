@@ -2,18 +2,20 @@
 // accumulators in TMEM), the float32 counterpart of matvec_pipe.cu (BASELINE configs[4]: N = 2M, D = 90, M = 8192).
 //
 // At D = 90 the distance contraction dominates (2 N M D flop per sweep), so it runs as a TF32 GEMM:
-//   * the scaled points are converted ONCE (cggp_tf32_prepare) into the UMMA "canonical K-major, no swizzle" order
-//     [row / 8][k / 4][row % 8][k % 4] and split  x = x_big + x_small  (both round-to-nearest TF32), so that a
-//     128-row tile is one contiguous block that a single TMA bulk copy (cp.async.bulk) drops into shared memory in
-//     exactly the layout the tcgen05 shared-memory descriptors describe (LBO = 128 B, SBO = KP / 4 * 128 B);
-//   * 3xTF32:  x.z ~ xb.zb + xs.zb + xb.zs  (three accumulating MMAs; the dropped xs.zs term is 2^-22 relative), which
-//     keeps the expanded squared distance at float32 accuracy - a single TF32 pass (NSPLIT = 1) loses ~3 digits to the
-//     cancellation in |x|^2 + |z|^2 - 2 x.z;
-//   * generic "gram contraction"  out[b, p] = sum_q k(P_p, Q_q) U[b, q]:  a CTA owns 128 P rows (= the 128 TMEM lanes)
-//     and loops over 128-column Q tiles.  Warp 4 is the producer (one elected lane: TMA of the next Q tile, the
-//     tcgen05.mma chain, tcgen05.commit onto mbarriers); warps 0-3 are the epilogue: tcgen05.ld of a finished
-//     accumulator (thread = row, registers = columns), r2 = |p|^2 + |q|^2 - 2 p.q, kernel value with MUFU ex2 / sqrt,
-//     dot with U.  Two TMEM accumulators (2 x 128 columns) let the MMAs of tile j+1 run under the epilogue of tile j.
+//   * the scaled points are converted ONCE (cggp_tf32_prepare) into the order the tensor cores read: 128-row tiles x
+//     32-feature chunks, each chunk a contiguous 16 KB block in the UMMA "canonical K-major, no swizzle" order
+//     [row / 8][k / 4][row % 8][k % 4] (LBO = 128 B, SBO = 1 KB), split  x = x_big + x_small  (both round-to-nearest
+//     TF32).  One TMA bulk copy (cp.async.bulk) per chunk drops it into shared memory exactly as the tcgen05
+//     shared-memory descriptors describe it;
+//   * 3xTF32:  x.z ~ xb.zb + xs.zb + xb.zs  (three accumulating MMA groups; the dropped xs.zs term is 2^-22 relative),
+//     which keeps the expanded squared distance at float32 accuracy - a single TF32 pass (NSPLIT = 1) loses ~3 digits
+//     to the cancellation in |x|^2 + |z|^2 - 2 x.z;
+//   * generic "gram contraction"  out[b, p] = sum_q k(P_p, Q_q) U[b, q]:  a CTA owns 128 P rows (= the 128 TMEM lanes,
+//     both parts resident in shared memory) and loops over 128-column Q tiles that stream through a ring of K-chunk
+//     stages.  Warp 8 is the TMA producer, warp 9 issues the tcgen05.mma chain (one elected lane each) and commits
+//     onto mbarriers, warp 10 stages the per-column scalars (|q|^2, U); warps 0-7 are the epilogue: tcgen05.ld of a finished accumulator (thread = row, registers = 64
+//     columns), r2 = |p|^2 + |q|^2 - 2 p.q, kernel value with MUFU ex2 / sqrt, dot with U.  Two TMEM accumulators
+//     (2 x 128 columns) let the MMAs of tile j+1 run under the epilogue of tile j.
 //   The product is two such sweeps:  T = gram(X, Z, V)  then  W = gram(Z, X, T)  (roles swapped, X split over
 //   grid.y with a fixed-order reduction), i.e. every Gram entry is evaluated twice - parking a 128 x 128 FP32 tile per
 //   block would be the next step, as matvec_pipe.cu does for float64.
@@ -85,10 +87,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// offset (in floats) of element (r, k) in the canonical order for a point set with KP padded features
-__host__ __device__ inline int64_t canon_off(int64_t r, int k, int KP) {
-  return ((r >> 3) * (KP >> 2) + (k >> 2)) * 32 + (r & 7) * 4 + (k & 3);
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
 }
+
+// offset (in floats) of element (r, k): [r / 128][k / 32] chunks of 4096 floats, inside a chunk the UMMA canonical
+// K-major order [(r % 128) / 8][(k % 32) / 4][r % 8][k % 4]
+__host__ __device__ inline int64_t canon_off(int64_t r, int k, int KP) {
+  const int64_t chunk = (r >> 7) * (KP >> 5) + (k >> 5);
+  return chunk * 4096 + ((((r & 127) >> 3) * 8 + ((k & 31) >> 2)) * 32) + (r & 7) * 4 + (k & 3);
+}
+constexpr int CHUNK_FLOATS = 4096;                      // 128 rows x 32 features
+constexpr unsigned CHUNK_BYTES = CHUNK_FLOATS * 4;      // 16 KB
+constexpr int MAX_STAGES = 8;
 
 // ---------------------------------------------------------------------------------------------------------
 // one-time conversion of prepared points into the canonical TF32 big / small arrays (rows padded to 128)
@@ -117,23 +136,31 @@ __global__ void prepare_kernel(const float* __restrict__ P, const float* __restr
 // ---------------------------------------------------------------------------------------------------------
 // float32 kernel values (GPflow formulas; float32 constants as GPflow builds them in the default float)
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {  // MUFU.EX2, 2 ulp, flushes results below 2^-126 to 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {  // MUFU.SQRT
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Matern families from r2 (SE takes the fused path in the epilogue: its exponent is linear in the accumulator)
 template <int KIND>
 __device__ __forceinline__ float kval32(float r2) {
-  if constexpr (KIND == CGGP_SE) {
-    return exp2f(-0.72134752044448170368f * r2);  // exp(-r2 / 2), MUFU.EX2
+  const float r = sqrt_approx(fmaxf(r2, 1e-36f));
+  if constexpr (KIND == CGGP_MATERN12) {
+    return ex2_approx(-1.44269504088896340736f * r);
+  } else if constexpr (KIND == CGGP_MATERN32) {
+    const float s = 1.7320508075688772f * r;
+    return (1.f + s) * ex2_approx(-1.44269504088896340736f * s);
   } else {
-    const float r = sqrtf(fmaxf(r2, 1e-36f));
-    if constexpr (KIND == CGGP_MATERN12) {
-      return exp2f(-1.44269504088896340736f * r);
-    } else if constexpr (KIND == CGGP_MATERN32) {
-      const float s = 1.7320508075688772f * r;
-      return (1.f + s) * exp2f(-1.44269504088896340736f * s);
-    } else {
-      const float s = 2.23606797749979f * r;
-      return (1.f + s + (float)(5.0 / 3.0) * (r * r)) * exp2f(-1.44269504088896340736f * s);
-    }
+    const float s = 2.23606797749979f * r;
+    return (1.f + s + (float)(5.0 / 3.0) * (r * r)) * ex2_approx(-1.44269504088896340736f * s);
   }
 }
+constexpr float HALF_LOG2E = 0.72134752044448170368f;  // exp(-r2 / 2) = 2^(-HALF_LOG2E r2)
 
 struct Args {
   const float* Pb;   // canonical big / small parts of the row set (TMEM lanes)
@@ -150,21 +177,24 @@ struct Args {
   int64_t ldo;
   int64_t q_tiles_per_split;
   float variance;
+  int stages;        // Q chunk ring depth (what fits next to the resident P tile)
   const int* active;
 };
 
 template <int KIND, int NSPLIT, int NB>
-__global__ void __launch_bounds__(160, 1) gram_contract_kernel(const Args a, const int KP) {
+__global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, const int KP) {
   if (cg_inactive(a.active)) return;
+  constexpr int PARTS = NSPLIT > 1 ? 2 : 1;
+  constexpr int BN = 128;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const unsigned tile_bytes = (unsigned)BM * KP * sizeof(float);
-  float* sPb = reinterpret_cast<float*>(smem_raw);
-  float* sPs = reinterpret_cast<float*>(smem_raw + (NSPLIT > 1 ? tile_bytes : 0));
-  float* sQb = reinterpret_cast<float*>(smem_raw + (NSPLIT > 1 ? 2 : 1) * tile_bytes);
-  float* sQs = reinterpret_cast<float*>(smem_raw + (NSPLIT > 1 ? 3 : 1) * tile_bytes);
-  float* aux = reinterpret_cast<float*>(smem_raw + (NSPLIT > 1 ? 4 : 2) * tile_bytes);  // [2][(1 + NB) * BN]
-  __shared__ uint64_t bar_p, bar_q, bar_qfree, bar_full[2], bar_empty[2], bar_aux[2];
+  const int nchunk = KP >> 5;
+  const int STAGES = a.stages;
+  float* sP = reinterpret_cast<float*>(smem_raw);                       // [PARTS][nchunk][4096]
+  float* sQ = sP + (size_t)PARTS * nchunk * CHUNK_FLOATS;               // [STAGES][PARTS][4096]
+  float* aux = sQ + (size_t)STAGES * PARTS * CHUNK_FLOATS;              // [2][(1 + NB) * BN]
+  __shared__ uint64_t bar_p, bar_qfull[MAX_STAGES], bar_qfree[MAX_STAGES], bar_full[2], bar_empty[2], bar_aux[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float comb[BM * NB];  // partial sums of the second column half, combined at the end
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t p0 = (int64_t)blockIdx.x * BM;
@@ -176,11 +206,13 @@ __global__ void __launch_bounds__(160, 1) gram_contract_kernel(const Args a, con
 
   if (tid == 0) {
     mbar_init(&bar_p, 1);
-    mbar_init(&bar_q, 1);
-    mbar_init(&bar_qfree, 1);
+    for (int b = 0; b < MAX_STAGES; ++b) {
+      mbar_init(&bar_qfull[b], 1);
+      mbar_init(&bar_qfree[b], 1);
+    }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bar_full[b], 1);
-      mbar_init(&bar_empty[b], 128);
+      mbar_init(&bar_empty[b], 256);
       mbar_init(&bar_aux[b], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -194,61 +226,100 @@ __global__ void __launch_bounds__(160, 1) gram_contract_kernel(const Args a, con
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp == 4) {
-    // =============================== producer warp ===============================
-    const unsigned lbo = 128, sbo = (unsigned)(KP / 4) * 128;
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    if (lane == 0) {
-      mbar_expect_tx(&bar_p, NSPLIT > 1 ? 2 * tile_bytes : tile_bytes);
-      tma_bulk_g2s(sPb, a.Pb + p0 * KP, tile_bytes, &bar_p);
-      if (NSPLIT > 1) tma_bulk_g2s(sPs, a.Ps + p0 * KP, tile_bytes, &bar_p);
+  if (warp == 8) {
+    // =============================== TMA producer warp ===============================
+    if (njt > 0 && lane == 0) {  // the P tile: both parts, all chunks (contiguous per part)
+      const unsigned pbytes = (unsigned)nchunk * CHUNK_BYTES;
+      mbar_expect_tx(&bar_p, PARTS * pbytes);
+      tma_bulk_g2s(sP, a.Pb + p0 * KP, pbytes, &bar_p);
+      if (PARTS > 1) tma_bulk_g2s(sP + (size_t)nchunk * CHUNK_FLOATS, a.Ps + p0 * KP, pbytes, &bar_p);
     }
+    if (lane == 0) {
+      int64_t g = 0;  // running chunk counter over the whole loop
+      for (int64_t j = 0; j < njt; ++j) {
+        const int64_t q0 = (jt0 + j) * BN;
+        for (int c = 0; c < nchunk; ++c, ++g) {
+          const int s = (int)(g % STAGES);
+          if (g >= STAGES) mbar_wait(&bar_qfree[s], (unsigned)(((g / STAGES) - 1) & 1));  // MMAs done with this stage
+          float* dst = sQ + (size_t)s * PARTS * CHUNK_FLOATS;
+          const int64_t src = (q0 >> 7) * (int64_t)nchunk * CHUNK_FLOATS + (int64_t)c * CHUNK_FLOATS;
+          mbar_expect_tx(&bar_qfull[s], PARTS * CHUNK_BYTES);
+          tma_bulk_g2s(dst, a.Qb + src, CHUNK_BYTES, &bar_qfull[s]);
+          if (PARTS > 1) tma_bulk_g2s(dst + CHUNK_FLOATS, a.Qs + src, CHUNK_BYTES, &bar_qfull[s]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 10) {
+    // =============================== column-scalar warp ===============================
+    // per-column scalars of every tile for the epilogue: |q|^2 (SE: its share of the exponent) and the weights U
+    // (zero past the end); kept off the TMA warp so that the global-load latency never delays a bulk copy
     for (int64_t j = 0; j < njt; ++j) {
       const int buf = (int)(j & 1);
       const int64_t q0 = (jt0 + j) * BN;
-      if (j >= 2) mbar_wait(&bar_empty[buf], (unsigned)(((j >> 1) - 1) & 1));  // epilogue of tile j-2 left buf / aux
-      // per-column scalars of this tile for the epilogue: |q|^2 and the weights U (zero past the end)
-      float* ax = aux + buf * (1 + NB) * BN;
-      for (int c = lane; c < BN; c += 32) {
-        const int64_t q = q0 + c;
-        ax[c] = a.qn[q];  // padded array
+      float vals[BN / 32][1 + NB];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) ax[(1 + b) * BN + c] = q < a.nq ? a.U[(int64_t)b * a.ldu + q] : 0.f;
+      for (int i = 0; i < BN / 32; ++i) {
+        const int64_t q = q0 + i * 32 + lane;
+        vals[i][0] = KIND == CGGP_SE ? -HALF_LOG2E * a.qn[q] : a.qn[q];  // padded array
+#pragma unroll
+        for (int b = 0; b < NB; ++b) vals[i][1 + b] = q < a.nq ? a.U[(int64_t)b * a.ldu + q] : 0.f;
       }
+      if (j >= 2) mbar_wait(&bar_empty[buf], (unsigned)(((j >> 1) - 1) & 1));  // epilogue of tile j-2 left aux[buf]
+      float* ax = aux + buf * (1 + NB) * BN;
+#pragma unroll
+      for (int i = 0; i < BN / 32; ++i)
+#pragma unroll
+        for (int b = 0; b < 1 + NB; ++b) ax[b * BN + i * 32 + lane] = vals[i][b];
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&bar_aux[buf]);
-        if (j >= 1) mbar_wait(&bar_qfree, (unsigned)((j - 1) & 1));  // the MMAs of tile j-1 have read the Q tile
-        mbar_expect_tx(&bar_q, NSPLIT > 1 ? 2 * tile_bytes : tile_bytes);
-        tma_bulk_g2s(sQb, a.Qb + q0 * KP, tile_bytes, &bar_q);
-        if (NSPLIT > 1) tma_bulk_g2s(sQs, a.Qs + q0 * KP, tile_bytes, &bar_q);
-        if (j == 0) mbar_wait(&bar_p, 0);
-        mbar_wait(&bar_q, (unsigned)(j & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;");
+      if (lane == 0) mbar_arrive(&bar_aux[buf]);
+    }
+  } else if (warp == 9) {
+    // =============================== MMA issuer warp ===============================
+    if (lane == 0 && njt > 0) {
+      const unsigned lbo = 128, sbo = 1024;
+      const uint32_t idesc =
+          (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      mbar_wait(&bar_p, 0);
+      int64_t g = 0;
+      for (int64_t j = 0; j < njt; ++j) {
+        const int buf = (int)(j & 1);
+        if (j >= 2) mbar_wait(&bar_empty[buf], (unsigned)(((j >> 1) - 1) & 1));  // accumulator drained by the epilogue
         const uint32_t d = tmem_base + (uint32_t)(buf * BN);
         uint32_t acc = 0;
-        for (int k = 0; k < KP / 8; ++k) {  // D (+)= Pb Qb^T
-          umma_tf32(d, smem_desc(smem_u32(sPb) + k * 256, lbo, sbo), smem_desc(smem_u32(sQb) + k * 256, lbo, sbo), idesc,
-                    acc);
-          acc = 1;
+        for (int c = 0; c < nchunk; ++c, ++g) {
+          const int s = (int)(g % STAGES);
+          mbar_wait(&bar_qfull[s], (unsigned)((g / STAGES) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          const unsigned pb = smem_u32(sP) + (unsigned)c * CHUNK_BYTES, ps = pb + (unsigned)nchunk * CHUNK_BYTES;
+          const unsigned qb = smem_u32(sQ) + (unsigned)s * PARTS * CHUNK_BYTES, qs = qb + CHUNK_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // D (+)= Pb Qb^T
+            umma_tf32(d, smem_desc(pb + k * 256, lbo, sbo), smem_desc(qb + k * 256, lbo, sbo), idesc, acc);
+            acc = 1;
+          }
+          if (PARTS > 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)  // + Ps Qb^T
+              umma_tf32(d, smem_desc(ps + k * 256, lbo, sbo), smem_desc(qb + k * 256, lbo, sbo), idesc, 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)  // + Pb Qs^T
+              umma_tf32(d, smem_desc(pb + k * 256, lbo, sbo), smem_desc(qs + k * 256, lbo, sbo), idesc, 1);
+          }
+          umma_commit(&bar_qfree[s]);  // the stage may be refilled once these MMAs are done
         }
-        if (NSPLIT > 1) {
-          for (int k = 0; k < KP / 8; ++k)  // + Ps Qb^T
-            umma_tf32(d, smem_desc(smem_u32(sPs) + k * 256, lbo, sbo), smem_desc(smem_u32(sQb) + k * 256, lbo, sbo),
-                      idesc, 1);
-          for (int k = 0; k < KP / 8; ++k)  // + Pb Qs^T
-            umma_tf32(d, smem_desc(smem_u32(sPb) + k * 256, lbo, sbo), smem_desc(smem_u32(sQs) + k * 256, lbo, sbo),
-                      idesc, 1);
-        }
-        umma_commit(&bar_qfree);      // Q tile may be overwritten
         umma_commit(&bar_full[buf]);  // accumulator ready for the epilogue
       }
-      __syncwarp();
     }
+    __syncwarp();
   } else {
-    // =============================== epilogue warps (thread = row) ===============================
-    const int64_t p = p0 + tid;
+    // =============================== epilogue warps ===============================
+    // 8 warps: warp w reads TMEM lanes 32 (w % 4) .. + 31 (thread = row) and the column half w / 4 of every tile
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const int64_t p = p0 + row;
     const float pn = a.pn[p];  // padded array
+    const float cp = -HALF_LOG2E * pn;
     float acc[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) acc[b] = 0.f;
@@ -257,31 +328,58 @@ __global__ void __launch_bounds__(160, 1) gram_contract_kernel(const Args a, con
       mbar_wait(&bar_aux[buf], (unsigned)((j >> 1) & 1));
       mbar_wait(&bar_full[buf], (unsigned)((j >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;");
-      const float* ax = aux + buf * (1 + NB) * BN;
+      const float* ax = aux + buf * (1 + NB) * BN + half * 64;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + half * 64);
+      uint32_t v[2][32];
+      tmem_ld32_nowait(taddr, v[0]);
+      tmem_ld32_nowait(taddr + 32, v[1]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      // the accumulator is in registers: hand the TMEM buffer back before the math
+      asm volatile("tcgen05.fence::before_thread_sync;");
       float part[NB];
 #pragma unroll
       for (int b = 0; b < NB; ++b) part[b] = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN + c0), v);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          // GPflow: dist = -2 p.q; dist += |p|^2 + |q|^2
-          const float r2 = fmaf(-2.f, __uint_as_float(v[c]), pn + ax[c0 + c]);
-          const float kv = kval32<KIND>(r2);
+      for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int b = 0; b < NB; ++b) part[b] = fmaf(kv, ax[(1 + b) * BN + c0 + c], part[b]);
+        for (int c4 = 0; c4 < 32; c4 += 4) {
+          const float4 qv = *reinterpret_cast<const float4*>(ax + h * 32 + c4);
+          float4 uv[NB];
+#pragma unroll
+          for (int b = 0; b < NB; ++b) uv[b] = *reinterpret_cast<const float4*>(ax + (1 + b) * BN + h * 32 + c4);
+          const float qs[4] = {qv.x, qv.y, qv.z, qv.w};
+          float kv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float d = __uint_as_float(v[h][c4 + i]);
+            if constexpr (KIND == CGGP_SE) {
+              // exp(-r2 / 2) with r2 = |p|^2 + |q|^2 - 2 p.q: one FADD + one FFMA + MUFU.EX2
+              kv[i] = ex2_approx(fmaf(2.f * HALF_LOG2E, d, cp + qs[i]));
+            } else {
+              kv[i] = kval32<KIND>(fmaf(-2.f, d, pn + qs[i]));  // GPflow: dist = -2 p.q; dist += |p|^2 + |q|^2
+            }
+          }
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            part[b] = fmaf(kv[0], uv[b].x, part[b]);
+            part[b] = fmaf(kv[1], uv[b].y, part[b]);
+            part[b] = fmaf(kv[2], uv[b].z, part[b]);
+            part[b] = fmaf(kv[3], uv[b].w, part[b]);
+          }
         }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;");
-      mbar_arrive(&bar_empty[buf]);
+      mbar_arrive(&bar_empty[buf]);  // (aux[buf] has been read as well)
 #pragma unroll
       for (int b = 0; b < NB; ++b) acc[b] += part[b];
     }
-    if (p < a.np) {
+    if (half == 1) {
 #pragma unroll
-      for (int b = 0; b < NB; ++b) a.out[((int64_t)blockIdx.y * NB + b) * a.ldo + p] = a.variance * acc[b];
+      for (int b = 0; b < NB; ++b) comb[row * NB + b] = acc[b];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+    if (half == 0 && p < a.np) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+        a.out[((int64_t)blockIdx.y * NB + b) * a.ldo + p] = a.variance * (acc[b] + comb[row * NB + b]);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
@@ -318,12 +416,23 @@ static KernelFn pick(int kind, int nsplit, int nb) {
   }
 }
 
-static size_t smem_bytes(int KP, int nsplit, int nb) {
-  return (size_t)(nsplit > 1 ? 4 : 2) * BM * KP * sizeof(float) + (size_t)2 * (1 + nb) * BN * sizeof(float) + 128;
+constexpr size_t SMEM_BUDGET = 227 * 1024 - 1024;  // leave room for the static barriers
+// ring depth that fits next to the resident P tile (0 = does not fit)
+static int stages_for(int KP, int nsplit, int nb) {
+  const size_t parts = nsplit > 1 ? 2 : 1;
+  const size_t fixed = parts * (size_t)(KP / 32) * CHUNK_BYTES + (size_t)2 * (1 + nb) * 128 * sizeof(float) + 128;
+  if (fixed >= SMEM_BUDGET) return 0;
+  size_t st = (SMEM_BUDGET - fixed) / (parts * CHUNK_BYTES);
+  if (st > MAX_STAGES) st = MAX_STAGES;
+  return st >= 2 ? (int)st : 0;
+}
+static size_t smem_bytes(int KP, int nsplit, int nb, int stages) {
+  const size_t parts = nsplit > 1 ? 2 : 1;
+  return parts * (size_t)(KP / 32 + stages) * CHUNK_BYTES + (size_t)2 * (1 + nb) * 128 * sizeof(float) + 128;
 }
 }  // namespace tf32
 
-extern "C" int cggp_tf32_kp(int D) { return (D + 7) / 8 * 8; }
+extern "C" int cggp_tf32_kp(int D) { return (D + 31) / 32 * 32; }
 extern "C" int64_t cggp_tf32_rows(int64_t n) { return (n + 127) / 128 * 128; }
 
 extern "C" int cggp_tf32_prepare(cggp_ctx* ctx, const void* P, const void* norms, int64_t n, int D, int64_t ldp,
@@ -340,9 +449,15 @@ extern "C" int cggp_tf32_prepare(cggp_ctx* ctx, const void* P, const void* norms
   return CGGP_OK;
 }
 
+extern "C" int cggp_tf32_supported(cggp_ctx* ctx, int D, int nsplit);
 bool cggp_matvec_tf32_supported(cggp_ctx* ctx, int D, int nsplit) {
   const int KP = cggp_tf32_kp(D);
-  return ctx->cc_major >= 10 && tf32::smem_bytes(KP, nsplit, 2) <= 227 * 1024;
+  return ctx->cc_major >= 10 && tf32::stages_for(KP, nsplit, 2) >= 2;
+}
+
+extern "C" int cggp_tf32_supported(cggp_ctx* ctx, int D, int nsplit) {
+  if (!ctx || D < 1 || (nsplit != 1 && nsplit != 3)) return 0;
+  return cggp_matvec_tf32_supported(ctx, D, nsplit) ? 1 : 0;
 }
 
 // W[B, m] = V[B, m] @ (Kuf Kfu): T = gram(X; Z, V), W = gram(Z; X, T)
@@ -375,7 +490,8 @@ int cggp_matvec_tf32(cggp_ctx* ctx, int kind, double variance, const float* Xb, 
   for (int b0 = 0; b0 < B; b0 += 2) {
     const int nb = (B - b0) >= 2 ? 2 : 1;
     KernelFn fn = pick(kind, nsplit, nb);
-    const size_t smem = smem_bytes(KP, nsplit, nb);
+    const int stages = stages_for(KP, nsplit, nb);
+    const size_t smem = smem_bytes(KP, nsplit, nb, stages);
     CGGP_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     Args a1;
     a1.Pb = Xb; a1.Ps = Xs; a1.pn = xn; a1.np = n;
@@ -384,8 +500,9 @@ int cggp_matvec_tf32(cggp_ctx* ctx, int kind, double variance, const float* Xb, 
     a1.out = T; a1.ldo = n_pad;
     a1.q_tiles_per_split = (m + BN - 1) / BN;
     a1.variance = (float)variance;
+    a1.stages = stages;
     a1.active = active;
-    fn<<<dim3((unsigned)p_blocks_x, 1), 160, smem, ctx->stream>>>(a1, KP);
+    fn<<<dim3((unsigned)p_blocks_x, 1), 352, smem, ctx->stream>>>(a1, KP);
     CGGP_LAUNCH_CHECK(ctx);
     Args a2;
     a2.Pb = Zb; a2.Ps = Zs; a2.pn = zn; a2.np = m;
@@ -394,8 +511,9 @@ int cggp_matvec_tf32(cggp_ctx* ctx, int kind, double variance, const float* Xb, 
     a2.out = Wp; a2.ldo = m;
     a2.q_tiles_per_split = tiles_per_split;
     a2.variance = (float)variance;
+    a2.stages = stages;
     a2.active = active;
-    fn<<<dim3((unsigned)p_blocks_z, (unsigned)splits), 160, smem, ctx->stream>>>(a2, KP);
+    fn<<<dim3((unsigned)p_blocks_z, (unsigned)splits), 352, smem, ctx->stream>>>(a2, KP);
     CGGP_LAUNCH_CHECK(ctx);
     reduce_splits_kernel<<<dim3((unsigned)((m + 255) / 256), (unsigned)nb), 256, 0, ctx->stream>>>(
         Wp, (int)splits, nb, m, m, W + (int64_t)b0 * ldw, ldw, active);

@@ -81,13 +81,10 @@ class SGPROperator(LinearOperator):
         self.X32 = self.Z32 = None
         if self.dtype == torch.float32 and self.variant in (0, 4):
             ctx = _lib.context(self.device)
-            kp = int(ctx.lib.cggp_tf32_kp(self.PZ.D))
-            fits = (4 if self.tf32_nsplit > 1 else 2) * 128 * kp * 4 + 4096 <= 227 * 1024
-            sm100 = torch.cuda.get_device_capability(self.device)[0] >= 10
-            if fits and sm100:
+            if ctx.lib.cggp_tf32_supported(ctx.handle, self.PZ.D, self.tf32_nsplit):
                 self.X32, self.Z32 = prepare_tf32(self.PX), prepare_tf32(self.PZ)
             elif self.variant == 4:
-                raise _lib.CggpError("the tcgen05 TF32 path needs sm_100 and D <= 104 (3xTF32) / 216 (1xTF32)")
+                raise _lib.CggpError("the tcgen05 TF32 path needs sm_100 and D <= 160 (3xTF32) / 320 (1xTF32)")
 
     def c_struct(self):
         op = _lib.Operator()

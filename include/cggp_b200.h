@@ -120,13 +120,17 @@ int cggp_kuf_kfu_matvec(cggp_ctx* ctx, int dtype, int kind, double variance,
 
 /* float32 on the 5th-generation tensor cores (tcgen05.mma kind::tf32, FP32 accumulators in TMEM; csrc/matvec_tf32.cu).
  * cggp_tf32_prepare converts prepared float32 points ONCE into the layout the tensor cores read: features padded to
- * KP = cggp_tf32_kp(D), rows padded to cggp_tf32_rows(n), canonical K-major order [row/8][k/4][row%8][k%4], split into
+ * KP = cggp_tf32_kp(D) (a multiple of 32), rows padded to cggp_tf32_rows(n) (a multiple of 128), 128-row x 32-feature
+ * chunks of 16 KB in the UMMA canonical K-major order [row/8][k/4][row%8][k%4], split into
  * a TF32 "big" and a TF32 "small" part (x = big + small to 2^-22), plus the norms padded with zeros.  Buffers:
  * big, small: rows_pad * KP floats each; norms_pad: rows_pad floats.
  * cggp_kuf_kfu_matvec_tf32: W[B, m] = V[B, m] @ (Kuf Kfu) from those arrays; nsplit = 3 -> 3xTF32 (float32-accurate
  * distances), nsplit = 1 -> single TF32 pass (3x fewer tensor-core flops, ~1e-3 relative on the distances). */
 int cggp_tf32_kp(int D);
 int64_t cggp_tf32_rows(int64_t n);
+/* 1 if the device is sm_100+ and the resident row tile plus a ring of K-chunk stages fit in shared memory
+ * (D <= 160 for nsplit = 3, D <= 320 for nsplit = 1), else 0 */
+int cggp_tf32_supported(cggp_ctx* ctx, int D, int nsplit);
 int cggp_tf32_prepare(cggp_ctx* ctx, const void* dev_P, const void* dev_norms, int64_t n, int D, int64_t ldp,
                       void* dev_big, void* dev_small, void* dev_norms_pad);
 int cggp_kuf_kfu_matvec_tf32(cggp_ctx* ctx, int kind, double variance,
