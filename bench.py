@@ -33,9 +33,18 @@ WORKLOADS = {
     "c3": (2_000_000, 4096, 11, "matern52", "CDGP/SGPR CG solve, synthetic houseelectric-shaped (BASELINE configs[2])"),
     "c2": (434_874, 2048, 3, "se", "synthetic 3droad-shaped (BASELINE configs[1])"),
     "c1": (10_000, 500, 2, "se", "synthetic 2-D regression (BASELINE configs[0])"),
+    "c5": (2_000_000, 8192, 90, "se", "float32, YearPredictionMSD-shaped, TF32 distance GEMM (BASELINE configs[4])"),
 }
+FLOAT32 = {"c5"}   # every other workload is float64
 NOISE = 0.1        # likelihood variance, cggp/cli_utils.py:153
-METRIC = "fp64 CG iter/s at N=2M,M=4096,D=11 on 1/2/4/8 B200; % of FP64 peak"
+METRIC = "fp64 CG iter/s at N=2M,M=4096,D=11 on 1/2/4/8 B200; % of FP64 peak"  # BASELINE.json's metric (c3)
+
+
+def metric_for(workload):
+    if workload == "c3":
+        return METRIC
+    N, M, D, kern, _ = WORKLOADS[workload]
+    return f"{'fp32' if workload in FLOAT32 else 'fp64'} CG iter/s at N={N},M={M},D={D} ({kern}); not BASELINE.json's headline config"
 
 
 def f_alg_matvec(n_rows, m, d, b=1):
@@ -121,12 +130,13 @@ def cpu_reference_arm(workload: str, steps: int, warmup: int, budget_s: float):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(7)
-    ls = torch.ones(D, dtype=torch.float64)
-    Z = torch.randn(M, D, dtype=torch.float64, generator=g)
-    rhs = torch.randn(1, M, dtype=torch.float64, generator=g)
+    dt = torch.float32 if workload in FLOAT32 else torch.float64
+    ls = torch.full((D,), math.sqrt(D) if workload in FLOAT32 else 1.0, dtype=dt)
+    Z = torch.randn(M, D, dtype=dt, generator=g)
+    rhs = torch.randn(1, M, dtype=dt, generator=g)
 
     def time_iters(n_rows, iters, warm):
-        X = torch.randn(n_rows, D, dtype=torch.float64, generator=g)
+        X = torch.randn(n_rows, D, dtype=dt, generator=g)
         mm = tc.sgpr_operator(kern, 1.0, ls, X, Z, NOISE, chunk=8192)
         if warm:
             tc.cg_iterations(mm, rhs, warm)
@@ -148,7 +158,7 @@ def cpu_reference_arm(workload: str, steps: int, warmup: int, budget_s: float):
         "unit": "CG iterations/s",
         "cores": cores,
         "kind": "port",
-        "sample": f"{rows} of {N} rows (same M={M}, D={D}, {kern}, float64), {steps} timed CG iterations after "
+        "sample": f"{rows} of {N} rows (same M={M}, D={D}, {kern}, {str(dt)[6:]}), {steps} timed CG iterations after "
                   f"{warmup} warm-up, per-iteration time scaled by N/rows = {N / rows:.2f} (cost is linear in N)",
         "ms_per_step_sample": t_iter_sample * 1e3,
         "ms_per_step_scaled": t_iter_full * 1e3,
@@ -163,9 +173,10 @@ def run_reference(args):
     base = cpu_reference_arm(args.workload, args.steps, args.warmup, budget_s=90.0)
     line = {
         "impl": "reference",
-        "metric": METRIC, "value": base["value"], "unit": "CG iterations/s", "n_gpus": args.gpus,
+        "metric": metric_for(args.workload), "value": base["value"], "unit": "CG iterations/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step_scaled"],
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32" if args.workload in FLOAT32 else "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: N={N}, M={M}, D={D}, {kern}, B=1 right-hand side; {desc}",
                    "operator": "Kuu + jitter I + Kuf Kfu / noise_variance (matrix-free, chunked)",
                    "note": "CPU path uses host cores only; n_gpus is echoed from the command line"},
@@ -205,7 +216,9 @@ def run_native(args):
 
     r_lo, r_hi = shard_rows(N, rank, world)
     n_local = r_hi - r_lo
-    f64 = torch.float64
+    f32w = args.workload in FLOAT32
+    f64 = torch.float32 if f32w else torch.float64  # the workload's dtype
+    esize = 4 if f32w else 8
 
     # ---- synthetic data: HOST (pinned) copies for the e2e leg, device copies for the resident leg -------------
     g = torch.Generator().manual_seed(1234 + rank)
@@ -223,7 +236,7 @@ def run_native(args):
         dist.broadcast(Zd, src=0)
         Zh = Zd.cpu()
     Zh = Zh.pin_memory()
-    kernel = cb.kernels.KERNELS[kern](variance=1.0, lengthscales=[1.0] * D)
+    kernel = cb.kernels.KERNELS[kern](variance=1.0, lengthscales=[math.sqrt(D) if f32w else 1.0] * D)
 
     Xd, yd = Xh.to(device), yh.to(device)
     op = cb.SGPROperator(kernel, Xd, Zd, NOISE)
@@ -286,20 +299,39 @@ def run_native(args):
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_ms = float(t2.item())
-    h2d = (Xh.numel() + yh.numel() + Zh.numel()) * 8
-    d2h = out.numel() * 8
+    h2d = (Xh.numel() + yh.numel() + Zh.numel()) * esize
+    d2h = out.numel() * esize
 
     # ---- roofline of the dominant kernel (the fused Kuf Kfu product), timed live with CUDA events ---------------
     mv_ms, mv_cnt = prof["kuf_kfu_matvec"]
     peak_tflops, peak_src = None, None
     try:
-        import ctypes as C
+        if f32w:
+            # TF32 dense peak: a library GEMM timed here only as the roofline denominator
+            torch.backends.cuda.matmul.allow_tf32 = True
+            A_ = torch.randn(8192, 8192, device=device)
+            B_ = torch.randn(8192, 8192, device=device)
+            for _ in range(2):
+                A_ @ B_
+            t0_, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0_.record()
+            for _ in range(5):
+                A_ @ B_
+            t1_.record()
+            torch.cuda.synchronize()
+            peak_tflops = 5 * 2 * 8192 ** 3 / (t0_.elapsed_time(t1_) * 1e-3) / 1e12
+            torch.backends.cuda.matmul.allow_tf32 = False
+            del A_, B_
+            peak_src = ("measured in this run: cuBLAS TF32 GEMM 8192^3 (torch.matmul, allow_tf32); "
+                        "MEASURED_PEAKS.json has no TF32 figure")
+        else:
+            import ctypes as C
 
-        gops = C.c_double(0.0)
-        ctx.check(ctx.lib.cggp_microbench(ctx.handle, 1, 4096, C.byref(gops)))
-        peak_tflops = gops.value / 1e3
-        peak_src = ("measured in this run: FP64 DMMA m8n8k4 issue-rate micro-benchmark (cggp_microbench); "
-                    "MEASURED_PEAKS.json has no FP64 figure")
+            gops = C.c_double(0.0)
+            ctx.check(ctx.lib.cggp_microbench(ctx.handle, 1, 4096, C.byref(gops)))
+            peak_tflops = gops.value / 1e3
+            peak_src = ("measured in this run: FP64 DMMA m8n8k4 issue-rate micro-benchmark (cggp_microbench); "
+                        "MEASURED_PEAKS.json has no FP64 figure")
     except Exception as exc:  # pragma: no cover
         peak_src = f"unavailable: {exc}"
     achieved = f_alg_matvec(n_local, M, D) / (mv_ms / max(mv_cnt, 1) * 1e-3) / 1e12 if mv_cnt else None
@@ -311,7 +343,8 @@ def run_native(args):
         except Exception:
             traffic = None
     roofline = {
-        "kernel": "kpipe::kfu_pipe_kernel (fused, software-pipelined Kuf Kfu product)",
+        "kernel": ("tf32::gram_contract_kernel x2 (tcgen05 TF32 3x-split gram contraction, two sweeps)" if f32w else
+                   "kpipe::kfu_pipe_kernel (fused, software-pipelined Kuf Kfu product)"),
         "bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
         "frac": (achieved / peak_tflops) if (achieved and peak_tflops) else None,
         "traffic": traffic, "peak_source": peak_src,
@@ -334,16 +367,16 @@ def run_native(args):
             cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
         its = args.steps / (ms_max * 1e-3)
         line = {
-            "metric": METRIC, "value": its, "unit": "CG iterations/s", "n_gpus": world, "steps": args.steps,
+            "metric": metric_for(args.workload), "value": its, "unit": "CG iterations/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if f32w else "f64", "data": "synthetic",
             "config": {
                 "workload": f"{args.workload}: N={N} (rows sharded over {world} GPU(s), {n_local} on rank 0), M={M}, "
                             f"D={D}, {kern}, B=1 right-hand side; {desc}",
                 "operator": "Kuu + jitter I + Kuf Kfu / noise_variance, matrix-free (Kfu never materialised)",
                 "step": "one CG iteration: fused Kuf Kfu product + all-reduce + Kuu product + fused vector update",
                 "l2": "inputs larger than L2: prepared X shard %.0f MB + Kuu %.0f MB streamed every iteration (126 MB L2)"
-                      % (n_local * 12 * 8 / 1e6, M * M * 8 / 1e6),
+                      % (n_local * (4 * ((D + 4) // 4)) * esize / 1e6, M * M * esize / 1e6),
                 "seconds_per_solve": f"{ms_max * 1e-3:.4f} s for {args.steps} iterations (threshold 0, fixed count)",
                 "f_alg_per_iteration": f_alg_iteration(N, M, D),
                 "fp64_frac_whole_iteration": (f_alg_iteration(N, M, D) * its / world / 1e12 / peak_tflops)

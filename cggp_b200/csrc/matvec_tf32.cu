@@ -460,11 +460,56 @@ extern "C" int cggp_tf32_supported(cggp_ctx* ctx, int D, int nsplit) {
   return cggp_matvec_tf32_supported(ctx, D, nsplit) ? 1 : 0;
 }
 
+// out[b, p] = variance * sum_q k(P_p, Q_q) U[b, q] for b < B: one sweep, the Q tiles split over grid.y when the row set
+// alone does not fill the machine (fixed-order reduction of the partials)
+static int gram_sweep(cggp_ctx* ctx, int kind, double variance, int nsplit, int KP, const float* Pb, const float* Ps,
+                      const float* pn, int64_t np, const float* Qb, const float* Qs, const float* qn, int64_t nq,
+                      const float* U, int64_t ldu, int B, float* out, int64_t ldo, float* scratch, const int* active) {
+  using namespace tf32;
+  const int64_t p_blocks = (np + BM - 1) / BM, q_tiles = (nq + BN - 1) / BN;
+  int64_t splits = p_blocks >= 2LL * ctx->sm_count ? 1 : (3LL * ctx->sm_count + p_blocks - 1) / p_blocks;
+  if (splits > q_tiles) splits = q_tiles;
+  if (splits < 1) splits = 1;
+  const int64_t tiles_per_split = (q_tiles + splits - 1) / splits;
+  splits = (q_tiles + tiles_per_split - 1) / tiles_per_split;
+  for (int b0 = 0; b0 < B; b0 += 2) {
+    const int nb = (B - b0) >= 2 ? 2 : 1;
+    KernelFn fn = pick(kind, nsplit, nb);
+    const int stages = stages_for(KP, nsplit, nb);
+    const size_t smem = smem_bytes(KP, nsplit, nb, stages);
+    CGGP_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    Args a;
+    a.Pb = Pb; a.Ps = Ps; a.pn = pn; a.np = np;
+    a.Qb = Qb; a.Qs = Qs; a.qn = qn; a.nq = nq;
+    a.U = U + (int64_t)b0 * ldu; a.ldu = ldu;
+    a.out = splits == 1 ? out + (int64_t)b0 * ldo : scratch;
+    a.ldo = splits == 1 ? ldo : np;
+    a.q_tiles_per_split = tiles_per_split;
+    a.variance = (float)variance;
+    a.stages = stages;
+    a.active = active;
+    fn<<<dim3((unsigned)p_blocks, (unsigned)splits), 352, smem, ctx->stream>>>(a, KP);
+    CGGP_LAUNCH_CHECK(ctx);
+    if (splits > 1) {
+      reduce_splits_kernel<<<dim3((unsigned)((np + 255) / 256), (unsigned)nb), 256, 0, ctx->stream>>>(
+          scratch, (int)splits, nb, np, np, out + (int64_t)b0 * ldo, ldo, active);
+      CGGP_LAUNCH_CHECK(ctx);
+    }
+  }
+  return CGGP_OK;
+}
+// scratch for the split partials of a sweep over `np` rows (only row sets that do not fill the machine are split)
+static size_t gram_scratch_bytes(cggp_ctx* ctx, int64_t np) {
+  const int64_t p_blocks = (np + tf32::BM - 1) / tf32::BM;
+  if (p_blocks >= 2LL * ctx->sm_count) return 0;
+  const int64_t splits = (3LL * ctx->sm_count + p_blocks - 1) / (p_blocks > 0 ? p_blocks : 1) + 1;
+  return sizeof(float) * (size_t)splits * 2 * (size_t)np;
+}
+
 // W[B, m] = V[B, m] @ (Kuf Kfu): T = gram(X; Z, V), W = gram(Z; X, T)
 int cggp_matvec_tf32(cggp_ctx* ctx, int kind, double variance, const float* Xb, const float* Xs, const float* xn,
                      int64_t n, const float* Zb, const float* Zs, const float* zn, int64_t m, int D, const float* V,
                      int64_t ldv, int B, float* W, int64_t ldw, int nsplit, const int* active) {
-  using namespace tf32;
   const int KP = cggp_tf32_kp(D);
   if (!cggp_matvec_tf32_supported(ctx, D, nsplit))
     CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "tcgen05 TF32 matvec: D=%d with nsplit=%d does not fit shared memory", D, nsplit);
@@ -472,52 +517,47 @@ int cggp_matvec_tf32(cggp_ctx* ctx, int kind, double variance, const float* Xb, 
     for (int b = 0; b < B; ++b) CGGP_CUDA(ctx, cudaMemsetAsync(W + (int64_t)b * ldw, 0, sizeof(float) * m, ctx->stream));
     return CGGP_OK;
   }
-  const int64_t p_blocks_x = (n + BM - 1) / BM, p_blocks_z = (m + BM - 1) / BM;
-  const int64_t x_tiles = (n + BN - 1) / BN;
-  // sweep 2 splits the X tiles over grid.y so that ~3 waves of CTAs are in flight
-  int64_t splits = (3LL * ctx->sm_count + p_blocks_z - 1) / p_blocks_z;
-  if (splits > x_tiles) splits = x_tiles;
-  if (splits < 1) splits = 1;
-  const int64_t tiles_per_split = (x_tiles + splits - 1) / splits;
-  splits = (x_tiles + tiles_per_split - 1) / tiles_per_split;
   const int64_t n_pad = cggp_tf32_rows(n);
-  // scratch: T [2][n_pad] and the sweep-2 partials [splits][2][m]
-  const size_t t_bytes = sizeof(float) * 2 * (size_t)n_pad, wp_bytes = sizeof(float) * (size_t)splits * 2 * (size_t)m;
-  int rc = cggp_ws_reserve(ctx, t_bytes + wp_bytes + 256);
+  // scratch: T [2][n_pad], then the split partials of whichever sweep needs them
+  const size_t t_bytes = sizeof(float) * 2 * (size_t)n_pad;
+  const size_t sa = gram_scratch_bytes(ctx, n), sb = gram_scratch_bytes(ctx, m);
+  const size_t s_bytes = sa > sb ? sa : sb;
+  int rc = cggp_ws_reserve(ctx, t_bytes + s_bytes + 256);
   if (rc) return rc;
   float* T = (float*)ctx->ws;
-  float* Wp = (float*)((char*)ctx->ws + t_bytes);
+  float* scratch = (float*)((char*)ctx->ws + t_bytes);
   for (int b0 = 0; b0 < B; b0 += 2) {
     const int nb = (B - b0) >= 2 ? 2 : 1;
-    KernelFn fn = pick(kind, nsplit, nb);
-    const int stages = stages_for(KP, nsplit, nb);
-    const size_t smem = smem_bytes(KP, nsplit, nb, stages);
-    CGGP_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    Args a1;
-    a1.Pb = Xb; a1.Ps = Xs; a1.pn = xn; a1.np = n;
-    a1.Qb = Zb; a1.Qs = Zs; a1.qn = zn; a1.nq = m;
-    a1.U = V + (int64_t)b0 * ldv; a1.ldu = ldv;
-    a1.out = T; a1.ldo = n_pad;
-    a1.q_tiles_per_split = (m + BN - 1) / BN;
-    a1.variance = (float)variance;
-    a1.stages = stages;
-    a1.active = active;
-    fn<<<dim3((unsigned)p_blocks_x, 1), 352, smem, ctx->stream>>>(a1, KP);
-    CGGP_LAUNCH_CHECK(ctx);
-    Args a2;
-    a2.Pb = Zb; a2.Ps = Zs; a2.pn = zn; a2.np = m;
-    a2.Qb = Xb; a2.Qs = Xs; a2.qn = xn; a2.nq = n;
-    a2.U = T; a2.ldu = n_pad;
-    a2.out = Wp; a2.ldo = m;
-    a2.q_tiles_per_split = tiles_per_split;
-    a2.variance = (float)variance;
-    a2.stages = stages;
-    a2.active = active;
-    fn<<<dim3((unsigned)p_blocks_z, (unsigned)splits), 352, smem, ctx->stream>>>(a2, KP);
-    CGGP_LAUNCH_CHECK(ctx);
-    reduce_splits_kernel<<<dim3((unsigned)((m + 255) / 256), (unsigned)nb), 256, 0, ctx->stream>>>(
-        Wp, (int)splits, nb, m, m, W + (int64_t)b0 * ldw, ldw, active);
-    CGGP_LAUNCH_CHECK(ctx);
+    rc = gram_sweep(ctx, kind, variance, nsplit, KP, Xb, Xs, xn, n, Zb, Zs, zn, m, V + (int64_t)b0 * ldv, ldv, nb, T,
+                    n_pad, scratch, active);
+    if (rc) return rc;
+    rc = gram_sweep(ctx, kind, variance, nsplit, KP, Zb, Zs, zn, m, Xb, Xs, xn, n, T, n_pad, nb, W + (int64_t)b0 * ldw,
+                    ldw, scratch, active);
+    if (rc) return rc;
   }
   return CGGP_OK;
+}
+
+// W[p, j] = sum_i k(z_j, x_i) Yt[p, i]  (Kuf @ Y with Y given transposed, [P, ldy])
+extern "C" int cggp_kuf_times_tf32(cggp_ctx* ctx, int kind, double variance, const void* Xb, const void* Xs,
+                                   const void* xn, int64_t n, const void* Zb, const void* Zs, const void* zn,
+                                   int64_t m, int D, const void* Yt, int64_t ldy, int P, void* W, int64_t ldw,
+                                   int nsplit) {
+  if (!ctx) return CGGP_ERR_INVALID;
+  if (P <= 0 || m <= 0) return CGGP_OK;
+  if (kind < CGGP_SE || kind > CGGP_MATERN52) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "unknown kernel kind %d", kind);
+  if (nsplit != 1 && nsplit != 3) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "nsplit must be 1 or 3");
+  if (!cggp_matvec_tf32_supported(ctx, D, nsplit))
+    CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "tcgen05 TF32 path: D=%d with nsplit=%d does not fit shared memory", D, nsplit);
+  if (n == 0) {
+    for (int b = 0; b < P; ++b)
+      CGGP_CUDA(ctx, cudaMemsetAsync((float*)W + (int64_t)b * ldw, 0, sizeof(float) * m, ctx->stream));
+    return CGGP_OK;
+  }
+  int rc = cggp_ws_reserve(ctx, gram_scratch_bytes(ctx, m) + 256);
+  if (rc) return rc;
+  ProfScope prof(ctx, 0);
+  return gram_sweep(ctx, kind, variance, nsplit, cggp_tf32_kp(D), (const float*)Zb, (const float*)Zs, (const float*)zn,
+                    m, (const float*)Xb, (const float*)Xs, (const float*)xn, n, (const float*)Yt, ldy, P, (float*)W, ldw,
+                    (float*)ctx->ws, nullptr);
 }

@@ -160,6 +160,20 @@ class SGPROperator(LinearOperator):
             if ctx.world > 1:
                 ctx.allreduce_sum_(out)
             return out
+        if self.X32 is not None and self.variant in (0, 4):
+            # float32: one gram-contraction sweep on the tensor cores (rows = Z, columns = X, weights = Y^T)
+            ctx.use_current_stream()
+            Yt = Y.t().contiguous()
+            W = torch.empty((Y.shape[1], self.n), dtype=self.dtype, device=self.device)
+            ctx.check(ctx.lib.cggp_kuf_times_tf32(
+                ctx.handle, self.kernel.kind, self.kernel.variance, _lib.ptr(self.X32.big), _lib.ptr(self.X32.small),
+                _lib.ptr(self.X32.norms), self.PX.n, _lib.ptr(self.Z32.big), _lib.ptr(self.Z32.small),
+                _lib.ptr(self.Z32.norms), self.n, self.PZ.D, _lib.ptr(Yt), Yt.stride(0), Yt.shape[0], _lib.ptr(W),
+                W.stride(0), self.tf32_nsplit))
+            out = W.t().contiguous()
+            if ctx.world > 1:
+                ctx.allreduce_sum_(out)
+            return out
         out = torch.zeros((self.n, Y.shape[1]), dtype=self.dtype, device=self.device)
         step = max(1, (1 << 27) // max(self.n, 1))
         for s in range(0, self.PX.n, step):

@@ -138,6 +138,12 @@ int cggp_kuf_kfu_matvec_tf32(cggp_ctx* ctx, int kind, double variance,
                              const void* dev_Zbig, const void* dev_Zsmall, const void* dev_znorms_pad, int64_t m,
                              int D, const void* dev_V, int64_t ldv, int B, void* dev_W, int64_t ldw, int nsplit);
 
+/* float32 Kuf @ Y on the tensor cores: W[p, j] = sum_i k(z_j, x_i) Yt[p, i], Y given TRANSPOSED ([P, ldy] row-major) */
+int cggp_kuf_times_tf32(cggp_ctx* ctx, int kind, double variance,
+                        const void* dev_Xbig, const void* dev_Xsmall, const void* dev_xnorms_pad, int64_t n,
+                        const void* dev_Zbig, const void* dev_Zsmall, const void* dev_znorms_pad, int64_t m,
+                        int D, const void* dev_Yt, int64_t ldy, int P, void* dev_W, int64_t ldw, int nsplit);
+
 /* W[p, j] = sum_i k(z_j, x_i) Y[i, p]   (Kuf @ Y over this rank's shard, the right-hand side `Kuf y` of the SGPR
  * system and GPflow's `A @ err`): fused, Kuf never materialised (the second contraction of the pipelined kernel with
  * the row weights given).  Y is [n, ldy] row-major with P columns, W is [P, ldw].  float64, D <= 15; CGGP_ERR_UNSUPPORTED

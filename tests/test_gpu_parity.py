@@ -476,6 +476,10 @@ def test_tf32_tensor_core_matvec_vs_oracle(cb, name, N, M, D, B):
     np.testing.assert_allclose(W, W1, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
     op1 = cb.SGPROperator(k, dev(X), dev(Z), 0.1, variant=4, tf32_nsplit=1)
     np.testing.assert_allclose(cpu(op1.kuf_kfu_matmul(dev(V))), ref, rtol=1e-2, atol=1e-2 * np.abs(ref).max())
+    # Kuf @ Y through one tensor-core sweep
+    Y = rng.standard_normal((N, 3)).astype(np.float32)
+    kref = ok.K(Z.astype(np.float64), X.astype(np.float64)) @ Y.astype(np.float64)
+    np.testing.assert_allclose(cpu(op.kuf_times(dev(Y))), kref, rtol=1e-4, atol=1e-4 * np.abs(kref).max())
 
 
 def test_tf32_operator_inside_cg(cb):
