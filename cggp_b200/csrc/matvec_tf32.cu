@@ -467,9 +467,21 @@ static int gram_sweep(cggp_ctx* ctx, int kind, double variance, int nsplit, int 
                       const float* U, int64_t ldu, int B, float* out, int64_t ldo, float* scratch, const int* active) {
   using namespace tf32;
   const int64_t p_blocks = (np + BM - 1) / BM, q_tiles = (nq + BN - 1) / BN;
-  int64_t splits = p_blocks >= 2LL * ctx->sm_count ? 1 : (3LL * ctx->sm_count + p_blocks - 1) / p_blocks;
-  if (splits > q_tiles) splits = q_tiles;
-  if (splits < 1) splits = 1;
+  // grid.y: 1 when the row set alone fills the machine; else the split count (<= ~6 waves) whose CTA total wastes the
+  // least of its last wave (1 CTA per SM: 64 row blocks x 7 splits = 448 CTAs would leave a 4-CTA fourth wave)
+  int64_t splits = 1;
+  if (p_blocks < 2LL * ctx->sm_count) {
+    const int64_t sms = ctx->sm_count;
+    const int64_t lo = (sms + p_blocks - 1) / p_blocks, hi = (6 * sms + p_blocks - 1) / p_blocks;
+    double best = -1.0;
+    for (int64_t sp = lo; sp <= hi && sp <= q_tiles; ++sp) {
+      const int64_t total = p_blocks * sp;
+      const double eff = (double)total / (double)(((total + sms - 1) / sms) * sms);
+      if (eff > best + 1e-9) { best = eff; splits = sp; }
+    }
+    if (splits > q_tiles) splits = q_tiles;
+    if (splits < 1) splits = 1;
+  }
   const int64_t tiles_per_split = (q_tiles + splits - 1) / splits;
   splits = (q_tiles + tiles_per_split - 1) / tiles_per_split;
   for (int b0 = 0; b0 < B; b0 += 2) {
@@ -502,7 +514,7 @@ static int gram_sweep(cggp_ctx* ctx, int kind, double variance, int nsplit, int 
 static size_t gram_scratch_bytes(cggp_ctx* ctx, int64_t np) {
   const int64_t p_blocks = (np + tf32::BM - 1) / tf32::BM;
   if (p_blocks >= 2LL * ctx->sm_count) return 0;
-  const int64_t splits = (3LL * ctx->sm_count + p_blocks - 1) / (p_blocks > 0 ? p_blocks : 1) + 1;
+  const int64_t splits = (6LL * ctx->sm_count + p_blocks - 1) / (p_blocks > 0 ? p_blocks : 1) + 1;
   return sizeof(float) * (size_t)splits * 2 * (size_t)np;
 }
 
