@@ -10,6 +10,7 @@ from .kernels import (Gaussian, InducingPoints, Kuf, Kuu, Matern12, Matern32, Ma
                       prepare_points)
 from .models import CGGP, SGPR, ClusterGP, LpSVGP, eval_logdet  # noqa: F401
 from .operators import DenseOperator, SGPROperator  # noqa: F401
+from .prediction import batch_posterior_computation, test_metrics  # noqa: F401
 from .utils import add_diagonal  # noqa: F401
 
 

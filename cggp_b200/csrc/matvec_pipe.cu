@@ -187,7 +187,7 @@ __device__ __forceinline__ void mbar_arrive(void* bar) {
 }
 constexpr int BAR_T = 1;  // + parity of the block
 
-template <int KIND, int KS, int WARPS, int RB, int CBW, int NB, int HB>
+template <int KIND, int KS, int WARPS, int RB, int CBW, int NB>
 __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args a) {
   if (cg_inactive(a.active)) return;
   using L = Layout<WARPS, RB, CBW, NB, KS>;
@@ -353,41 +353,34 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
     for (int b = 0; b < NB; ++b) wacc[cb][0][b] = wacc[cb][1][b] = 0.0;
   const FastExpTable tab = fast_exp_table_biased();
 
-  // One row-block step of phase 2 (block jt): w += K^T t from the K values this thread parked in shared memory.
-  // Split into loads and FMAs so that the loads can be issued ahead of a phase-1 step and hide under its FP64 work.
-  struct P2Regs {
-    double2 k[CBW];
-    double t[NB];
-  };
-  auto p2_load = [&](int rb, int par, P2Regs& r) {
+  // phase 2 of block `jt`: w += K^T t from the K values this thread parked in shared memory.  (Interleaving these
+  // steps into phase 1 of the next block was measured slower than running them back to back: 22.8-25.6 vs 20.5 ms.)
+  auto phase2 = [&](int64_t jt) {
+    const int par = (int)(jt & 1);
+    mbar_wait(&mbarF[par], (unsigned)((jt >> 1) & 1));  // t of block jt is complete (normally long before)
     const double* tf = tfull + par * BM * NB;
     const double2* kb = kbuf + (size_t)par * RB * CBW * THREADS + tid;
 #pragma unroll
-    for (int b = 0; b < NB; ++b) r.t[b] = tf[(rb * 8 + lr) * NB + b];
+    for (int rb = 0; rb < RB; ++rb) {
+      double t[NB];
 #pragma unroll
-    for (int cb = 0; cb < CBW; ++cb) r.k[cb] = kb[(rb * CBW + cb) * THREADS];
-  };
-  auto p2_fma = [&](const P2Regs& r) {
+      for (int b = 0; b < NB; ++b) t[b] = tf[(rb * 8 + lr) * NB + b];
 #pragma unroll
-    for (int cb = 0; cb < CBW; ++cb)
+      for (int cb = 0; cb < CBW; ++cb) {
+        const double2 k = kb[(rb * CBW + cb) * THREADS];
 #pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        wacc[cb][0][b] = fma(r.k[cb].x, r.t[b], wacc[cb][0][b]);
-        wacc[cb][1][b] = fma(r.k[cb].y, r.t[b], wacc[cb][1][b]);
+        for (int b = 0; b < NB; ++b) {
+          wacc[cb][0][b] = fma(k.x, t[b], wacc[cb][0][b]);
+          wacc[cb][1][b] = fma(k.y, t[b], wacc[cb][1][b]);
+        }
       }
+    }
   };
-  auto wait_F = [&](int64_t jt) { mbar_wait(&mbarF[jt & 1], (unsigned)((jt >> 1) & 1)); };
-
-  // Phase 2 of block it-1 rides inside the second half of phase 1 of block it: HB pure phase-1 steps give the
-  // exchange warp time to deliver t, then every phase-1 step also retires P2 steps of the previous block.
-  // HB == RB: no interleaving, phase 2 of block it-1 follows phase 1 of block it.
-  constexpr int HOSTS = RB - HB > 0 ? RB - HB : 1;
-  constexpr int P2MAX = HB < RB ? (RB + HOSTS - 1) / HOSTS : 1;
 
   __syncthreads();  // (S)
   for (int64_t it = 0; it < nit; ++it) {
+    // ------------------------------- phase 1 of block `it` -------------------------------
     const int s = (int)(it % XS), par = (int)(it & 1);
-    const bool prev = it >= 1;
     if (!is_manual(it)) mbar_wait(&mbar[s], (unsigned)((it / XS) & 1));
     const double* xs = xt + s * BM * LDX + lr * LDX + lk;
     const double* xns = xn + s * BM + lr;
@@ -395,19 +388,6 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
     double* tr = tred + (par * WARPS + warp) * BM * NB;
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) {
-      // ---- loads of the phase-2 steps hosted by this phase-1 step
-      constexpr int dummy = 0;
-      (void)dummy;
-      const int p2_lo = rb >= HB ? ((rb - HB) * RB) / HOSTS : 0;
-      const int p2_hi = rb >= HB ? ((rb - HB + 1) * RB) / HOSTS : 0;
-      P2Regs pr[P2MAX];
-      if (prev) {
-        if (rb == HB) wait_F(it - 1);
-#pragma unroll
-        for (int q = 0; q < P2MAX; ++q)
-          if (p2_lo + q < p2_hi) p2_load(p2_lo + q, par ^ 1, pr[q]);
-      }
-      // ---- phase 1, row block rb of block `it`
       double af[KS];
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) af[ks] = xs[rb * 8 * LDX + ks * 4];
@@ -438,34 +418,13 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
         v += __shfl_xor_sync(0xffffffffu, v, 2);
         if (lk == 0) tr[(rb * 8 + lr) * NB + b] = v;
       }
-      // ---- FMAs of the hosted phase-2 steps
-      if (prev) {
-#pragma unroll
-        for (int q = 0; q < P2MAX; ++q)
-          if (p2_lo + q < p2_hi) p2_fma(pr[q]);
-      }
     }
     __threadfence_block();
     bar_arrive(BAR_T + par, ALL);  // hand the partials (and the X stage) to the exchange warp; do not wait
-    if (HB >= RB && prev && !(a.dbg & 1)) {
-      wait_F(it - 1);
-#pragma unroll
-      for (int rb = 0; rb < RB; ++rb) {
-        P2Regs r;
-        p2_load(rb, par ^ 1, r);
-        p2_fma(r);
-      }
-    }
+    // ------------------------------- phase 2 of block `it - 1` -------------------------------
+    if (it >= 1 && !(a.dbg & 1)) phase2(it - 1);
   }
-  if (nit >= 1 && !(a.dbg & 1)) {  // phase 2 of the last block
-    wait_F(nit - 1);
-#pragma unroll
-    for (int rb = 0; rb < RB; ++rb) {
-      P2Regs r;
-      p2_load(rb, (int)((nit - 1) & 1), r);
-      p2_fma(r);
-    }
-  }
+  if (nit >= 1 && !(a.dbg & 1)) phase2(nit - 1);
 
   // reduce the 8 row-lanes of every column, write this group's partial
 #pragma unroll
@@ -500,11 +459,11 @@ struct Plan {
   size_t smem;
 };
 
-template <int KIND, int KS, int WARPS, int RB, int CBW, int NB, int HB>
+template <int KIND, int KS, int WARPS, int RB, int CBW, int NB>
 static Plan make_plan() {
   using L = Layout<WARPS, RB, CBW, NB, KS>;
   Plan p;
-  p.fn = (const void*)kfu_pipe_kernel<KIND, KS, WARPS, RB, CBW, NB, HB>;
+  p.fn = (const void*)kfu_pipe_kernel<KIND, KS, WARPS, RB, CBW, NB>;
   p.threads = L::THREADS + 32;  // + the exchange warp
   p.BM = L::BM;
   p.BN = L::BN;
@@ -515,15 +474,9 @@ static Plan make_plan() {
 
 template <int KIND, int KS>
 static bool plan_for_nb(int nb, Plan& p) {
-  static const int hb = getenv("CGGP_PIPE_HB") ? atoi(getenv("CGGP_PIPE_HB")) : 6;  // tuning knob (tools/)
   switch (nb) {
-    case 1:
-      if (hb == 3) p = make_plan<KIND, KS, 16, 6, 2, 1, 3>();
-      else if (hb == 4) p = make_plan<KIND, KS, 16, 6, 2, 1, 4>();
-      else if (hb == 5) p = make_plan<KIND, KS, 16, 6, 2, 1, 5>();
-      else p = make_plan<KIND, KS, 16, 6, 2, 1, 6>();
-      return true;
-    case 2: p = make_plan<KIND, KS, 16, 5, 2, 2, 5>(); return true;  // 40-row blocks: two tred/tfull sets must fit
+    case 1: p = make_plan<KIND, KS, 16, 6, 2, 1>(); return true;
+    case 2: p = make_plan<KIND, KS, 16, 5, 2, 2>(); return true;  // 40-row blocks: two tred/tfull sets must fit
     default: return false;
   }
 }

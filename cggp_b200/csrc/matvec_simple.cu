@@ -154,6 +154,10 @@ template <typename T>
 static int matvec_simple_impl(cggp_ctx* ctx, int kind, double variance, const T* PX, const T* nX, int64_t n,
                               const T* PZ, const T* nZ, int64_t m, int D, int64_t ldp, const T* V, int64_t ldv, int B,
                               T* W, int64_t ldw, const int* active) {
+  if (n == 0) {  // an empty shard contributes exactly zero
+    for (int b = 0; b < B; ++b) CGGP_CUDA(ctx, cudaMemsetAsync(W + (int64_t)b * ldw, 0, sizeof(T) * m, ctx->stream));
+    return CGGP_OK;
+  }
   const int64_t row_tiles = (n + TILE - 1) / TILE;
   const int64_t col_tiles = (m + TILE - 1) / TILE;
   // enough (col tile, split) CTAs to fill the machine a few times over

@@ -641,6 +641,61 @@ def test_sgpr_elbo_vs_gpflow_restatement(cb, name):
     np.testing.assert_allclose(float(model.elbo()), ref, rtol=1e-8)
 
 
+def test_edge_cases_empty_tiny_and_zero_iterations(cb):
+    rng = np.random.default_rng(8)
+    k = cb.Matern32(variance=0.7, lengthscales=[1.3])
+    ok = g.Matern32(variance=0.7, lengthscales=[1.3])
+    # an EMPTY shard (a rank that got no rows) contributes exactly zero, on every matvec variant
+    Z = rng.standard_normal((37, 1))
+    V = rng.standard_normal((3, 37))
+    empty = cb.SGPROperator(k, torch.zeros((0, 1), dtype=torch.float64, device="cuda"), dev(Z), 0.1)
+    for variant in (1, 2, 3):
+        assert float(empty.kuf_kfu_matmul(dev(V), variant=variant).abs().max()) == 0.0
+    assert float(empty.kuf_times(torch.zeros((0, 2), dtype=torch.float64, device="cuda")).abs().max()) == 0.0
+    # one data row, one inducing point, one feature, three right-hand sides (odd count: 2 + 1 plan split)
+    X1, Z1 = rng.standard_normal((1, 1)), rng.standard_normal((1, 1))
+    V1 = rng.standard_normal((3, 1))
+    op = cb.SGPROperator(k, dev(X1), dev(Z1), 0.1)
+    ref = om.kuf_kfu_matmul(ok, X1, Z1, V1)
+    for variant in (1, 2, 3):
+        np.testing.assert_allclose(cpu(op.kuf_kfu_matmul(dev(V1), variant=variant)), ref, rtol=1e-12)
+    # max_iterations = 0: the initial state comes back, steps = 0, history has the single initial row
+    A = ok.K(Z) + 0.1 * np.eye(37)
+    rhs = rng.standard_normal((2, 37))
+    x0 = rng.standard_normal((2, 37))
+    sol, (steps, err, h) = cb.conjugate_gradient(dev(A), dev(rhs), dev(x0), 1e-9, None, 0, 10, return_history=True)
+    osol, (osteps, oerr) = ocg.conjugate_gradient(A, rhs, x0, 1e-9, None, 0, 10)
+    assert int(steps) == int(osteps) == 0 and tuple(h.shape) == (1, 2)
+    np.testing.assert_array_equal(cpu(sol), osol)
+    np.testing.assert_allclose(cpu(err), oerr, rtol=1e-12)
+    # already converged at the start (threshold above the initial residual): no iteration is taken
+    sol, (steps, _) = cb.conjugate_gradient(dev(A), dev(rhs), None, 1e9, None, None, 10)
+    assert int(steps) == 0 and float(sol.abs().max()) == 0.0
+    # shape / dtype errors surface as Python exceptions, as in the reference
+    with pytest.raises(ValueError):
+        cb.conjugate_gradient(dev(A), dev(rhs[:, :5]), None, 1e-6)
+    with pytest.raises(TypeError):
+        cb.conjugate_gradient(empty, dev(rhs.astype(np.float32)), None, 1e-6)
+
+
+def test_batched_prediction_and_metrics(cb, models_golden):
+    """cli_utils.batch_posterior_computation / the RMSE + NLPD of optimize.make_metrics_callback, on the device."""
+    c = models_golden["matern32_probes"]
+    m, cl = build_models(cb, c)
+    X, y = c["X"], c["y"]
+    mean, var = cb.batch_posterior_computation(cl.predict_f, (dev(X), dev(y)), 128)
+    ok = g.KERNELS[str(c["kernel"])](variance=float(c["variance"]), lengthscales=c["lengthscales"])
+    mo = om.ClusterGP(ok, g.Gaussian(float(c["noise"])), c["Z"], cluster_counts=c["counts"], pseudo_u=c["u"])
+    omu, ovar = mo.predict_f(X)
+    np.testing.assert_allclose(cpu(mean), omu, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(cpu(var), ovar, rtol=1e-8, atol=1e-10)
+    met = cb.test_metrics(cl, (dev(X), dev(y)), 100)
+    s2 = ovar + float(c["noise"])
+    lpd = -0.5 * (np.log(2 * np.pi) + np.log(s2) + (y - omu) ** 2 / s2)
+    np.testing.assert_allclose(met["test/rmse"], np.sqrt(np.mean((y - omu) ** 2)), rtol=1e-9)
+    np.testing.assert_allclose(met["test/nlpd"], -lpd.sum() / X.shape[0], rtol=1e-9)
+
+
 def test_dlpack_zero_copy_import(cb):
     """Foreign device tensors come in through __dlpack__ without a copy (TF: tf.experimental.dlpack)."""
 
