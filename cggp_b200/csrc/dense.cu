@@ -13,51 +13,70 @@ struct Vec2<double> { using type = double2; };
 template <>
 struct Vec2<float> { using type = float2; };
 
-template <typename T, int BB>
+// One warp per ROWS consecutive rows of A (ROWS x BB accumulators): the right-hand sides are read once per ROWS rows
+// instead of once per row, and ROWS independent 16-byte loads per lane are in flight - short rows (M = 4096: 32 KB)
+// are latency-bound otherwise.
+template <typename T, int BB, int ROWS>
 __global__ void __launch_bounds__(256)
 symm_gemv_kernel(const T* __restrict__ A, int64_t lda, int64_t n, const T* __restrict__ V, int64_t ldv,
                  T* __restrict__ Y, int64_t ldy, const T* __restrict__ addend, int64_t ldadd, T scale,
                  const int* __restrict__ active) {
   if (cg_inactive(active)) return;
   const int lane = threadIdx.x & 31;
-  const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (j >= n) return;
-  const T* __restrict__ row = A + j * lda;
-  T acc[BB];
+  const int64_t j0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
+  if (j0 >= n) return;
+  const T* __restrict__ row[ROWS];
 #pragma unroll
-  for (int b = 0; b < BB; ++b) acc[b] = T(0);
+  for (int r = 0; r < ROWS; ++r) row[r] = A + (j0 + r < n ? j0 + r : n - 1) * lda;  // clamp: tail rows recompute n-1
+  T acc[ROWS][BB];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+    for (int b = 0; b < BB; ++b) acc[r][b] = T(0);
   using V2 = typename Vec2<T>::type;
   const bool vec_ok = ((lda | ldv) % 2 == 0) && ((((uintptr_t)A) | ((uintptr_t)V)) % (2 * sizeof(T)) == 0);
   if (vec_ok) {
     const int64_t n2 = n / 2;
     for (int64_t k = lane; k < n2; k += 32) {
-      const V2 a = reinterpret_cast<const V2*>(row)[k];
+      V2 a[ROWS];
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) a[r] = reinterpret_cast<const V2*>(row[r])[k];
 #pragma unroll
       for (int b = 0; b < BB; ++b) {
         const V2 v = reinterpret_cast<const V2*>(V + b * ldv)[k];
-        acc[b] = fma(a.x, v.x, acc[b]);
-        acc[b] = fma(a.y, v.y, acc[b]);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+          acc[r][b] = fma(a[r].x, v.x, acc[r][b]);
+          acc[r][b] = fma(a[r].y, v.y, acc[r][b]);
+        }
       }
     }
     if ((n & 1) && lane == 0) {
 #pragma unroll
-      for (int b = 0; b < BB; ++b) acc[b] = fma(row[n - 1], V[b * ldv + n - 1], acc[b]);
+      for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int b = 0; b < BB; ++b) acc[r][b] = fma(row[r][n - 1], V[b * ldv + n - 1], acc[r][b]);
     }
   } else {
     for (int64_t k = lane; k < n; k += 32) {
-      const T a = row[k];
 #pragma unroll
-      for (int b = 0; b < BB; ++b) acc[b] = fma(a, V[b * ldv + k], acc[b]);
+      for (int b = 0; b < BB; ++b) {
+        const T v = V[b * ldv + k];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) acc[r][b] = fma(row[r][k], v, acc[r][b]);
+      }
     }
   }
 #pragma unroll
-  for (int b = 0; b < BB; ++b) {
-    T s = warp_sum(acc[b]);
-    if (lane == 0) {
-      if (addend) s += scale * addend[b * ldadd + j];
-      Y[b * ldy + j] = s;
+  for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+    for (int b = 0; b < BB; ++b) {
+      T s = warp_sum(acc[r][b]);
+      if (lane == 0 && j0 + r < n) {
+        if (addend) s += scale * addend[b * ldadd + j0 + r];
+        Y[b * ldy + j0 + r] = s;
+      }
     }
-  }
 }
 
 template <typename T>
@@ -69,16 +88,31 @@ static int symm_matmul_impl(cggp_ctx* ctx, const T* A, int64_t lda, int64_t n, c
     int rc = dmma_gemm_nt<T>(ctx, V, ldv, B, A, lda, n, n, Y, ldy, addend, ldadd, scale, active);
     return rc;
   }
+  // rows per warp: enough warps to fill the machine first (n / ROWS >= ~8 warps per SM), then amortise the reads of V
   const int warps = 8;
-  const unsigned grid = (unsigned)((n + warps - 1) / warps);
   while (b0 < B) {
-    const int bb = B - b0;
+    const int bb = B - b0 < 8 ? B - b0 : 8;
+    // measured on B200 (tools/bench_dense.py): one right-hand side streams best with 1 row per warp once there are
+    // enough rows to fill the machine; several right-hand sides want their reads of V amortised over 2-4 rows
+    const int rows = bb == 1 ? ((n >= 2048 && n < 8192) ? 2 : 1) : ((n >= 8192 && bb <= 4) ? 4 : (n >= 2048 ? 2 : 1));
+    const int64_t nw = (n + rows - 1) / rows;
+    const unsigned grid = (unsigned)((nw + warps - 1) / warps);
     const T* Vb = V + (int64_t)b0 * ldv;
     T* Yb = Y + (int64_t)b0 * ldy;
     const T* Ab = addend ? addend + (int64_t)b0 * ldadd : nullptr;
-#define GEMV(BBV)                                                                                              \
-  symm_gemv_kernel<T, BBV><<<grid, warps * 32, 0, ctx->stream>>>(A, lda, n, Vb, ldv, Yb, ldy, Ab, ldadd, scale, \
-                                                                 active)
+#define GEMV_R(BBV, R)                                                                                          \
+  symm_gemv_kernel<T, BBV, R><<<grid, warps * 32, 0, ctx->stream>>>(A, lda, n, Vb, ldv, Yb, ldy, Ab, ldadd, scale, \
+                                                                    active)
+#define GEMV(BBV)                         \
+  do {                                    \
+    if (rows == 4 && BBV <= 4) {          \
+      GEMV_R((BBV <= 4 ? BBV : 1), 4);    \
+    } else if (rows >= 2) {               \
+      GEMV_R(BBV, 2);                     \
+    } else {                              \
+      GEMV_R(BBV, 1);                     \
+    }                                     \
+  } while (0)
     switch (bb) {
       case 1: GEMV(1); break;
       case 2: GEMV(2); break;
@@ -90,8 +124,9 @@ static int symm_matmul_impl(cggp_ctx* ctx, const T* A, int64_t lda, int64_t n, c
       default: GEMV(8); break;
     }
 #undef GEMV
+#undef GEMV_R
     CGGP_LAUNCH_CHECK(ctx);
-    b0 += bb < 8 ? bb : 8;
+    b0 += bb;
   }
   return CGGP_OK;
 }
