@@ -12,7 +12,7 @@
 #include "tile.cuh"
 
 namespace dg {
-constexpr int BN = 128, BK = 16, LDS = 20;  // LDS: smem row stride in doubles, = 4 mod 8 -> conflict-free frags
+constexpr int BN = 128, BK = 32, LDS = 36;  // LDS: smem row stride in doubles, = 4 mod 8 -> conflict-free frags
 constexpr int STAGES = 3;
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool valid) {
@@ -36,18 +36,61 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
                                           int64_t nrows, int64_t k0, int64_t K) {
 #pragma unroll
   for (int e = threadIdx.x; e < ROWS * BK; e += 256) {
-    const int r = e >> 4, k = e & 15;
+    const int r = e / BK, k = e % BK;
     const int64_t gr = row0 + r, gk = k0 + k;
     const bool ok = gr < nrows && gk < K;
     cp_async8(s + r * LDS + k, ok ? (G + gr * ld + gk) : G, ok);
   }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+
+// Per-thread loader state for the 16-byte path: every thread owns ROWS / 32 fixed (row, k-pair) slots of the tile; the
+// global pointers advance by BK per k-tile, so the steady state is one LDGSTS per slot with no address arithmetic or
+// bounds logic (the issue port, not the DMMA pipe, is what the 8-byte loader was spending: 3.2 other instructions per
+// DMMA = 81 % tensor-pipe utilisation, profiles/r01_final_kernels.md).
+template <int ROWS>
+struct TileLoader {
+  static constexpr int SLOTS = ROWS * (BK / 2) / 256;
+  const double* g[SLOTS];
+  unsigned soff[SLOTS];   // offset in doubles inside a stage
+  bool row_ok[SLOTS];
+  int kk[SLOTS];
+  __device__ __forceinline__ void init(const double* G, int64_t ld, int64_t row0, int64_t nrows) {
+#pragma unroll
+    for (int i = 0; i < SLOTS; ++i) {
+      const int c = threadIdx.x + 256 * i;
+      const int r = c / (BK / 2);
+      kk[i] = (c % (BK / 2)) * 2;
+      const int64_t gr = row0 + r;
+      row_ok[i] = gr < nrows;
+      g[i] = G + (row_ok[i] ? gr : 0) * ld + kk[i];
+      soff[i] = r * LDS + kk[i];
+    }
+  }
+  // k0: first k of this tile; K: total.  Full tiles copy 16 bytes, the ragged last one zero-fills past K.
+  __device__ __forceinline__ void issue(double* stage, int64_t k0, int64_t K) {
+#pragma unroll
+    for (int i = 0; i < SLOTS; ++i) {
+      int bytes = 16;
+      if (k0 + BK > K) {
+        const int64_t left = K - (k0 + kk[i]);
+        bytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);
+      }
+      if (!row_ok[i]) bytes = 0;
+      cp_async16(stage + soff[i], bytes ? (const void*)(g[i] + k0) : (const void*)g[i], bytes);
+    }
+  }
+};
+
 template <int WMB>  // m8-blocks per warp along rows: 8 (BM = 128) or 4 (BM = 64)
 __global__ void __launch_bounds__(256)
 dmma_gemm_nt_kernel(const double* __restrict__ A, int64_t lda, int64_t M, const double* __restrict__ Bm, int64_t ldb,
                     int64_t N, int64_t K, double* __restrict__ C, int64_t ldc, const double* __restrict__ addend,
-                    int64_t ldadd, double scale, const int* __restrict__ active) {
+                    int64_t ldadd, double scale, const int* __restrict__ active, const int vec16) {
   if (cg_inactive(active)) return;
   constexpr int BM = WMB * 16;
   extern __shared__ __align__(16) double smem[];
@@ -65,13 +108,25 @@ dmma_gemm_nt_kernel(const double* __restrict__ A, int64_t lda, int64_t M, const 
     for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
   const int64_t nk = (K + BK - 1) / BK;
+  TileLoader<BM> la;
+  TileLoader<BN> lb;
+  if (vec16) {
+    la.init(A, lda, row0, M);
+    lb.init(Bm, ldb, col0, N);
+  }
+  auto load_stage = [&](int s, int64_t k0) {
+    if (vec16) {
+      la.issue(sA + s * BM * LDS, k0, K);
+      lb.issue(sB + s * BN * LDS, k0, K);
+    } else {
+      load_tile<BM>(sA + s * BM * LDS, A, lda, row0, M, k0, K);
+      load_tile<BN>(sB + s * BN * LDS, Bm, ldb, col0, N, k0, K);
+    }
+  };
   // prologue
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < nk) {
-      load_tile<BM>(sA + s * BM * LDS, A, lda, row0, M, (int64_t)s * BK, K);
-      load_tile<BN>(sB + s * BN * LDS, Bm, ldb, col0, N, (int64_t)s * BK, K);
-    }
+    if (s < nk) load_stage(s, (int64_t)s * BK);
     cp_async_commit();
   }
   for (int64_t kt = 0; kt < nk; ++kt) {
@@ -79,11 +134,7 @@ dmma_gemm_nt_kernel(const double* __restrict__ A, int64_t lda, int64_t M, const 
     __syncthreads();
     {  // prefetch tile kt + STAGES - 1 into the slot freed at iteration kt - 1
       const int64_t nt = kt + STAGES - 1;
-      if (nt < nk) {
-        const int s = (int)(nt % STAGES);
-        load_tile<BM>(sA + s * BM * LDS, A, lda, row0, M, nt * BK, K);
-        load_tile<BN>(sB + s * BN * LDS, Bm, ldb, col0, N, nt * BK, K);
-      }
+      if (nt < nk) load_stage((int)(nt % STAGES), nt * BK);
       cp_async_commit();
     }
     const int s = (int)(kt % STAGES);
@@ -172,7 +223,12 @@ inline int dmma_gemm_nt<double>(cggp_ctx* ctx, const double* A, int64_t lda, int
                                 int64_t N, int64_t K, double* C, int64_t ldc, const double* addend, int64_t ldadd,
                                 double scale, const int* active) {
   using namespace dg;
-  const bool small = M <= 64;
+  // 16-byte cp.async needs 16-byte aligned rows on both operands
+  const int vec16 = ((lda | ldb) % 2 == 0) && ((((uintptr_t)A) | ((uintptr_t)Bm)) % 16 == 0) ? 1 : 0;
+  // 64-row tiles when there are few rows, or when 128-row tiles would leave most of the machine idle (measured:
+  // at half a wave and above the 128-row tile wins despite the quantisation, tools/bench_dense.py)
+  const int64_t ctas128 = ((N + BN - 1) / BN) * ((M + 127) / 128);
+  const bool small = M <= 64 || 2 * ctas128 < ctx->sm_count;
   const int BM = small ? 64 : 128;
   const size_t smem = (size_t)STAGES * (BM + BN) * LDS * sizeof(double);
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
@@ -184,7 +240,7 @@ inline int dmma_gemm_nt<double>(cggp_ctx* ctx, const double* A, int64_t lda, int
       attr = true;
     }
     dmma_gemm_nt_kernel<4><<<grid, 256, smem, ctx->stream>>>(A, lda, M, Bm, ldb, N, K, C, ldc, addend, ldadd, scale,
-                                                             active);
+                                                             active, vec16);
   } else {
     static bool attr = false;
     if (!attr) {
@@ -193,7 +249,7 @@ inline int dmma_gemm_nt<double>(cggp_ctx* ctx, const double* A, int64_t lda, int
       attr = true;
     }
     dmma_gemm_nt_kernel<8><<<grid, 256, smem, ctx->stream>>>(A, lda, M, Bm, ldb, N, K, C, ldc, addend, ldadd, scale,
-                                                             active);
+                                                             active, vec16);
   }
   CGGP_LAUNCH_CHECK(ctx);
   return CGGP_OK;
