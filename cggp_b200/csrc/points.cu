@@ -117,6 +117,107 @@ nearest_center_kernel(const T* __restrict__ PX, const T* __restrict__ nX, int64_
   }
 }
 
+// float64 squared-Euclidean assignment (cggp/optimize.py:50-51, `argmin(square_distance(iv, inputs), axis=0)`) on the
+// DMMA path: the expanded distance |x|^2 + |z|^2 - 2 x.z of an 8 x 8 block comes out of mma.sync.m8n8k4.f64 (|z|^2 rides
+// in the spare feature slot, |x|^2 initialises the accumulator), 12 FMA-slots per pair instead of a DFMA each plus the
+// shared-memory traffic of the register-tile engine.  A warp owns 32 rows (4 A-fragment sets in registers) and sweeps
+// the centres, which all 8 warps of the CTA stage through shared memory in chunks of 256.  Each lane keeps the first
+// minimum of its column subset (columns ascend per lane, strict <), the 4 lanes of a row merge with ties going to the
+// smaller index: the result is tf.argmin's first minimum.
+namespace ncd {
+constexpr int ZC = 256, RBW = 4, WARPS = 8;
+__host__ __device__ constexpr int ldz_for(int KS) { return ((KS * 4) % 8 == 4) ? KS * 4 : KS * 4 + 4; }
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int KS>
+__global__ void __launch_bounds__(WARPS * 32)
+nearest_center_dmma_kernel(const double* __restrict__ PX, const double* __restrict__ nX, int64_t n,
+                           const double* __restrict__ PZ, const double* __restrict__ nZ, int64_t m, int D, int64_t ldp,
+                           int64_t* __restrict__ idx, double* __restrict__ dist) {
+  constexpr int LDZ = ldz_for(KS);
+  extern __shared__ __align__(16) double zt[];  // [ZC][LDZ]: -2 z | |z|^2 | 0
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lr = lane >> 2, lk = lane & 3;
+  const int64_t row0 = ((int64_t)blockIdx.x * WARPS + warp) * (RBW * 8);
+  double af[RBW][KS], xn[RBW], best[RBW];
+  int bidx[RBW];
+#pragma unroll
+  for (int rb = 0; rb < RBW; ++rb) {
+    const int64_t r = row0 + rb * 8 + lr;
+    const bool valid = r < n;
+    xn[rb] = valid ? nX[r] : 0.0;
+    best[rb] = INFINITY;
+    bidx[rb] = 0;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int k = ks * 4 + lk;
+      af[rb][ks] = valid ? (k < D ? PX[r * ldp + k] : (k == D ? 1.0 : 0.0)) : 0.0;
+    }
+  }
+  for (int64_t c0 = 0; c0 < m; c0 += ZC) {
+    __syncthreads();
+    for (int e = tid; e < ZC * LDZ; e += WARPS * 32) {
+      const int c = e / LDZ, k = e % LDZ;
+      const int64_t gc = c0 + c;
+      double v = 0.0;
+      if (gc < m) {
+        if (k < D) v = -2.0 * PZ[gc * ldp + k];
+        else if (k == D) v = nZ[gc];
+      } else if (k == D) {
+        v = INFINITY;  // past the last centre: never the minimum
+      }
+      zt[e] = v;
+    }
+    __syncthreads();
+    const double* zw = zt + lr * LDZ + lk;
+#pragma unroll 4
+    for (int cb = 0; cb < ZC / 8; ++cb) {
+      double bf[KS];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) bf[ks] = zw[cb * 8 * LDZ + ks * 4];
+      const int col = (int)c0 + cb * 8 + 2 * lk;
+#pragma unroll
+      for (int rb = 0; rb < RBW; ++rb) {
+        double d0 = xn[rb], d1 = xn[rb];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) dmma884(d0, d1, af[rb][ks], bf[ks]);
+        if (d0 < best[rb]) { best[rb] = d0; bidx[rb] = col; }
+        if (d1 < best[rb]) { best[rb] = d1; bidx[rb] = col + 1; }
+      }
+    }
+  }
+#pragma unroll
+  for (int rb = 0; rb < RBW; ++rb) {
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best[rb], o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx[rb], o);
+      if (ov < best[rb] || (ov == best[rb] && oi < bidx[rb])) {
+        best[rb] = ov;
+        bidx[rb] = oi;
+      }
+    }
+    const int64_t r = row0 + rb * 8 + lr;
+    if (lk == 0 && r < n) {
+      idx[r] = bidx[rb];
+      dist[r] = best[rb];
+    }
+  }
+}
+
+template <int KS>
+static void launch(cggp_ctx* ctx, const double* PX, const double* nX, int64_t n, const double* PZ, const double* nZ,
+                   int64_t m, int D, int64_t ldp, int64_t* idx, double* dist) {
+  const size_t smem = sizeof(double) * ZC * ldz_for(KS);
+  const unsigned grid = (unsigned)((n + WARPS * RBW * 8 - 1) / (WARPS * RBW * 8));
+  nearest_center_dmma_kernel<KS><<<grid, WARPS * 32, smem, ctx->stream>>>(PX, nX, n, PZ, nZ, m, D, ldp, idx, dist);
+}
+}  // namespace ncd
+
 template <typename T>
 __global__ void cluster_stats_kernel(const int64_t* __restrict__ idx, const T* __restrict__ y, int64_t n, int64_t m,
                                      T* __restrict__ counts, T* __restrict__ sums) {
@@ -201,6 +302,18 @@ template <typename T>
 static int nearest_center_impl(cggp_ctx* ctx, int kind, double variance, int distance, const void* PX, const void* nX,
                                int64_t n, const void* PZ, const void* nZ, int64_t m, int D, int64_t ldp, int64_t* idx,
                                void* dist) {
+  if (sizeof(T) == 8 && distance == CGGP_DIST_SQEUCLIDEAN && D + 1 <= 16 && m < (1LL << 31) - 512) {
+    const int ks = (D + 1 + 3) / 4;
+    const double *px = (const double*)PX, *nx = (const double*)nX, *pz = (const double*)PZ, *nz = (const double*)nZ;
+    switch (ks) {
+      case 1: ncd::launch<1>(ctx, px, nx, n, pz, nz, m, D, ldp, idx, (double*)dist); break;
+      case 2: ncd::launch<2>(ctx, px, nx, n, pz, nz, m, D, ldp, idx, (double*)dist); break;
+      case 3: ncd::launch<3>(ctx, px, nx, n, pz, nz, m, D, ldp, idx, (double*)dist); break;
+      default: ncd::launch<4>(ctx, px, nx, n, pz, nz, m, D, ldp, idx, (double*)dist); break;
+    }
+    CGGP_LAUNCH_CHECK(ctx);
+    return CGGP_OK;
+  }
   const unsigned grid = (unsigned)((n + TILE - 1) / TILE);
   const bool diff = distance == CGGP_DIST_EUCLIDEAN;
 #define NC_CALL(MODE)                                                                                       \

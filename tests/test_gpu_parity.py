@@ -138,6 +138,31 @@ def test_nearest_center_and_cluster_stats(cb, dtype_name):
     np.testing.assert_allclose(cpu(means), omeans, rtol=1e-11, atol=1e-13)
 
 
+@pytest.mark.parametrize("N,M,D", [(10_007, 700, 11), (3000, 257, 3), (513, 9, 15), (40, 1000, 7)])
+def test_sq_euclidean_assignment_dmma_vs_oracle(cb, N, M, D):
+    """optimize.py:50-67 semantics through the DMMA assignment kernel: indices bit-exact, counts, means, distances."""
+    from cggp_b200 import selection
+
+    rng = np.random.default_rng(N + M)
+    X = rng.standard_normal((N, D))
+    y = rng.standard_normal((N, 1))
+    Z = rng.standard_normal((M, D))
+    idx, dist = selection._nearest(dev(X), dev(Z), "sqeuclidean", None)
+    d2 = g.square_distance(Z, X)  # [M, N]
+    oidx = np.argmin(d2, axis=0)
+    np.testing.assert_array_equal(cpu(idx), oidx)
+    np.testing.assert_allclose(cpu(dist), d2[oidx, np.arange(N)], rtol=1e-11, atol=1e-12)
+    _, means, cnt = selection.nearest_center_update(dev(Z), (dev(X), dev(y)))
+    _, omeans, ocnt = om.oips_style_assignment(Z, X, y)
+    np.testing.assert_array_equal(cpu(cnt).astype(np.int64), ocnt)
+    np.testing.assert_allclose(cpu(means), omeans, rtol=1e-11, atol=1e-13, equal_nan=True)
+    # exact ties (integer grid, everything exact in floating point): the first minimum wins, as tf.argmin
+    Zg = np.array([[0.0, 0.0, 0.0], [2.0, 0.0, 0.0], [0.0, 0.0, 0.0], [2.0, 0.0, 0.0], [1.0, 1.0, 0.0]])
+    Xg = np.array([[1.0, 0.0, 0.0], [0.0, 0.0, 0.0], [2.0, 0.0, 0.0], [1.0, 1.0, 1.0]])
+    gi, _ = selection._nearest(dev(Xg), dev(Zg), "sqeuclidean", None)
+    np.testing.assert_array_equal(cpu(gi), np.argmin(g.square_distance(Zg, Xg), axis=0))
+
+
 def test_nearest_center_ties_pick_first(cb):
     from cggp_b200 import selection
 
