@@ -73,6 +73,8 @@ SIGNATURES = {
     "cggp_prepared_ld": (_i64, [_i]),
     "cggp_prepare_points": (_i, [_vp, _i, _vp, _i64, _i, _i64, C.POINTER(_d), _i, _vp, _i64, _vp]),
     "cggp_kernel_matrix": (_i, [_vp, _i, _i, _d, _i, _i, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i64, _d, _vp, _i64]),
+    "cggp_kernel_matrix_backward": (_i, [_vp, _i, _i, _d, _vp, _i64, _vp, _i64, _i, _i64, C.POINTER(_d), _i, _vp, _i64,
+                                          _vp, _vp]),
     "cggp_nearest_center": (_i, [_vp, _i, _i, _d, _i, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i64, _vp, _vp]),
     "cggp_cluster_stats": (_i, [_vp, _i, _vp, _vp, _i64, _i64, _vp, _vp]),
     "cggp_kuf_kfu_matvec": (_i, [_vp, _i, _i, _d, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i64, _vp, _i64, _i, _vp,

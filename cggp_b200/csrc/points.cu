@@ -117,6 +117,102 @@ nearest_center_kernel(const T* __restrict__ PX, const T* __restrict__ nX, int64_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Backward of the kernel matrix w.r.t. the hyper-parameters (what TF autodiff does behind the
+// reference's Adam loop, cggp/optimize.py:198-254): given G = dL/dK [n, m],
+//   dL/dvariance = sum_ij G_ij f(r2_ij),            K = variance * f(r2),  r2 = sum_d (a_d - b_d)^2,  a = x / l
+//   dL/dl_d      = sum_ij G_ij variance f'(r2_ij) * (-2 (a_id - b_jd)^2 / l_d)
+// Per-CTA partials [blocks][1 + D] are summed in fixed order by a second kernel (deterministic).
+// f' = df/dr2:  SE -f/2;  Matern-1/2 -exp(-r)/(2 r);  3/2 -(3/2) exp(-s);  5/2 -(5/6)(1 + s) exp(-s)   (s = sqrt(nu2) r);
+// 0 where GPflow's max(r2, 1e-36) clamps (autodiff through the max gives no gradient there).
+template <typename T, int KIND>
+__device__ __forceinline__ void kernel_f_and_dr2(T r2, T& f, T& fp) {
+  if (KIND == CGGP_SE) {
+    f = xexp(T(-0.5) * r2);
+    fp = T(-0.5) * f;
+    return;
+  }
+  const bool clamped = !(r2 > KConst<T>::clamp());
+  const T r = xsqrt(xmax(r2, KConst<T>::clamp()));
+  if (KIND == CGGP_MATERN12) {
+    f = xexp(-r);
+    fp = clamped ? T(0) : -f / (T(2) * r);
+  } else if (KIND == CGGP_MATERN32) {
+    const T s = KConst<T>::sqrt3() * r;
+    const T e = xexp(-s);
+    f = (T(1) + s) * e;
+    fp = clamped ? T(0) : T(-1.5) * e;
+  } else {
+    const T s = KConst<T>::sqrt5() * r;
+    const T e = xexp(-s);
+    f = (T(1) + s + KConst<T>::c53() * (r * r)) * e;
+    fp = clamped ? T(0) : T(-5.0 / 6.0) * (T(1) + s) * e;
+  }
+}
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(TILE_THREADS)
+kernel_matrix_backward_kernel(const T* __restrict__ PA, int64_t n, const T* __restrict__ PB, int64_t m, int D,
+                              int64_t ldp, T variance, const T* __restrict__ G, int64_t ldg,
+                              T* __restrict__ partials /* [blocks][1 + D] */) {
+  __shared__ TileSmem<T> s;
+  __shared__ T red[33];
+  const int64_t row0 = (int64_t)blockIdx.y * TILE, col0 = (int64_t)blockIdx.x * TILE;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  T acc[4][4];
+  tile_compute<T, 1>(acc, s, PA, ldp, row0, n, PB, ldp, col0, m, D);  // difference form: r2 = sum (a - b)^2
+  T w[4][4];
+  T gv = T(0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t r = row0 + ty * 4 + i, c = col0 + tx * 4 + j;
+      T g = T(0);
+      if (r < n && c < m) g = G[r * ldg + c];
+      T f, fp;
+      kernel_f_and_dr2<T, KIND>(acc[i][j], f, fp);
+      gv += g * f;
+      w[i][j] = T(-2) * g * variance * fp;
+    }
+  T* out = partials + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * (1 + D);
+  const T gvs = block_sum(gv, red);
+  if (threadIdx.x == 0) out[0] = gvs;
+  for (int d0 = 0; d0 < D; d0 += TILE_DC) {
+    __syncthreads();
+    tile_load(s.a, PA, ldp, row0, n, d0, D);
+    tile_load(s.b, PB, ldp, col0, m, d0, D);
+    __syncthreads();
+    const int dc = (D - d0) < TILE_DC ? (D - d0) : TILE_DC;
+    for (int d = 0; d < dc; ++d) {
+      T gl = T(0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const T df = s.a[d][ty * 4 + i] - s.b[d][tx * 4 + j];
+          gl = fma(w[i][j], df * df, gl);
+        }
+      const T gls = block_sum(gl, red);
+      if (threadIdx.x == 0) out[1 + d0 + d] = gls;  // still to be divided by l_d
+    }
+  }
+}
+
+template <typename T>
+__global__ void kernel_matrix_backward_reduce(const T* __restrict__ partials, int64_t blocks, int D, LsParam ls,
+                                              T* __restrict__ g_variance, T* __restrict__ g_ls) {
+  const int k = blockIdx.x;  // 0: variance, 1 + d: lengthscale d
+  __shared__ T red[33];
+  T v = T(0);
+  for (int64_t b = threadIdx.x; b < blocks; b += blockDim.x) v += partials[b * (1 + D) + k];
+  const T sum = block_sum(v, red);
+  if (threadIdx.x == 0) {
+    if (k == 0) *g_variance = sum;
+    else g_ls[k - 1] = sum / (T)ls.v[ls.count == 1 ? 0 : k - 1];
+  }
+}
+
 // float64 squared-Euclidean assignment (cggp/optimize.py:50-51, `argmin(square_distance(iv, inputs), axis=0)`) on the
 // DMMA path: the expanded distance |x|^2 + |z|^2 - 2 x.z of an 8 x 8 block comes out of mma.sync.m8n8k4.f64 (|z|^2 rides
 // in the spare feature slot, |x|^2 initialises the accumulator), 12 FMA-slots per pair instead of a DFMA each plus the
@@ -339,6 +435,50 @@ extern "C" int cggp_nearest_center(cggp_ctx* ctx, int dtype, int kind, double va
   if (dtype == CGGP_F64)
     return nearest_center_impl<double>(ctx, kind, variance, distance, PX, nX, n, PZ, nZ, m, D, ldp, idx, dist);
   return nearest_center_impl<float>(ctx, kind, variance, distance, PX, nX, n, PZ, nZ, m, D, ldp, idx, dist);
+}
+
+template <typename T>
+static int kernel_matrix_backward_impl(cggp_ctx* ctx, int kind, double variance, const void* PA, int64_t n,
+                                       const void* PB, int64_t m, int D, int64_t ldp, const double* ls, int ls_count,
+                                       const void* G, int64_t ldg, void* g_variance, void* g_ls) {
+  const dim3 grid((unsigned)((m + TILE - 1) / TILE), (unsigned)((n + TILE - 1) / TILE));
+  const int64_t blocks = (int64_t)grid.x * grid.y;
+  int rc = cggp_ws_reserve(ctx, sizeof(T) * (size_t)blocks * (1 + D));
+  if (rc) return rc;
+  T* partials = (T*)ctx->ws;
+  LsParam lp;
+  lp.count = ls_count;
+  for (int d = 0; d < ls_count; ++d) lp.v[d] = ls[d];
+#define KMB_CALL(MODE)                                                                                          \
+  kernel_matrix_backward_kernel<T, K><<<grid, TILE_THREADS, 0, ctx->stream>>>(                                  \
+      (const T*)PA, n, (const T*)PB, m, D, ldp, (T)variance, (const T*)G, ldg, partials)
+  DISPATCH_KIND(T, 0, KMB_CALL(0));
+#undef KMB_CALL
+  CGGP_LAUNCH_CHECK(ctx);
+  kernel_matrix_backward_reduce<T><<<1 + D, 256, 0, ctx->stream>>>(partials, blocks, D, lp, (T*)g_variance, (T*)g_ls);
+  CGGP_LAUNCH_CHECK(ctx);
+  return CGGP_OK;
+}
+
+extern "C" int cggp_kernel_matrix_backward(cggp_ctx* ctx, int dtype, int kind, double variance, const void* PA,
+                                           int64_t n, const void* PB, int64_t m, int D, int64_t ldp,
+                                           const double* host_lengthscales, int ls_count, const void* G, int64_t ldg,
+                                           void* g_variance, void* g_ls) {
+  if (!ctx) return CGGP_ERR_INVALID;
+  if (D < 1 || D > 128) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "D=%d outside [1,128]", D);
+  if (ls_count != 1 && ls_count != D) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "lengthscales count %d != 1 or D", ls_count);
+  if ((int64_t)((n + TILE - 1) / TILE) > 65535) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "too many rows for one call");
+  const size_t es = dtype == CGGP_F64 ? 8 : 4;
+  if (n == 0 || m == 0) {
+    CGGP_CUDA(ctx, cudaMemsetAsync(g_variance, 0, es, ctx->stream));
+    CGGP_CUDA(ctx, cudaMemsetAsync(g_ls, 0, es * D, ctx->stream));
+    return CGGP_OK;
+  }
+  if (dtype == CGGP_F64)
+    return kernel_matrix_backward_impl<double>(ctx, kind, variance, PA, n, PB, m, D, ldp, host_lengthscales, ls_count,
+                                               G, ldg, g_variance, g_ls);
+  return kernel_matrix_backward_impl<float>(ctx, kind, variance, PA, n, PB, m, D, ldp, host_lengthscales, ls_count, G,
+                                            ldg, g_variance, g_ls);
 }
 
 extern "C" int cggp_cluster_stats(cggp_ctx* ctx, int dtype, const int64_t* idx, const void* y, int64_t n, int64_t m,

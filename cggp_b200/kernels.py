@@ -103,13 +103,68 @@ def kernel_matrix(kind, variance, A: PreparedPoints, B: PreparedPoints, *, outpu
     return out
 
 
+class _KernelMatrixFn(torch.autograd.Function):
+    """``K(X, X2)`` differentiable in the hyper-parameters: forward = ``cggp_kernel_matrix``, backward =
+    ``cggp_kernel_matrix_backward`` (dL/dvariance, dL/dlengthscales from dL/dK in one fused sweep).  No gradient is
+    produced for the inputs: the reference trains kernel / likelihood parameters and moves the inducing points by
+    clustering (cggp/optimize.py:19-98), not by gradient."""
+
+    @staticmethod
+    def forward(ctx, variance_t, lengthscales_t, X, X2, kind, jitter):
+        ls = lengthscales_t.detach().reshape(-1).double().cpu()
+        A = prepare_points(X, ls)
+        B = A if X2 is None else prepare_points(X2, ls, A.P.dtype)
+        var = float(variance_t.detach())
+        ctx.save_for_backward(A.P, B.P)
+        ctx.meta = (kind, var, ls, A.D, variance_t, lengthscales_t)
+        return kernel_matrix(kind, var, A, B, jitter=jitter)
+
+    @staticmethod
+    def backward(ctx, G):
+        PA, PB = ctx.saved_tensors
+        kind, var, ls, D, variance_t, lengthscales_t = ctx.meta
+        G = _lib.row_major(G.contiguous())
+        c = _lib.context(PA.device)
+        c.use_current_stream()
+        g_var = torch.empty((1,), dtype=PA.dtype, device=PA.device)
+        g_ls = torch.empty((D,), dtype=PA.dtype, device=PA.device)
+        arr = (C.c_double * ls.numel())(*ls.tolist())
+        c.check(c.lib.cggp_kernel_matrix_backward(
+            c.handle, _lib.dtype_code(PA.dtype), int(kind), var, _lib.ptr(PA), PA.shape[0], _lib.ptr(PB), PB.shape[0],
+            D, PA.shape[1], arr, ls.numel(), _lib.ptr(G), G.stride(0), _lib.ptr(g_var), _lib.ptr(g_ls)))
+        if lengthscales_t.numel() == 1:
+            g_ls = g_ls.sum()
+        return (g_var.reshape(variance_t.shape).to(variance_t.dtype),
+                g_ls.reshape(lengthscales_t.shape).to(lengthscales_t.dtype), None, None, None, None)
+
+
 class Stationary:
+    """``variance`` / ``lengthscales`` may be numbers (fixed) or torch tensors that require grad (trainable: pass e.g.
+    ``softplus(raw)``); with trainable parameters ``K`` / ``K_diag`` are differentiable (``_KernelMatrixFn``)."""
+
     kind = None
     name = "stationary"
 
     def __init__(self, variance=1.0, lengthscales=1.0):
-        self.variance = float(variance)
-        self.lengthscales = torch.as_tensor(lengthscales, dtype=torch.float64).reshape(-1).cpu()
+        self._variance_t = variance if isinstance(variance, torch.Tensor) and variance.requires_grad else None
+        self._lengthscales_t = lengthscales if isinstance(lengthscales, torch.Tensor) and lengthscales.requires_grad \
+            else None
+        self._variance = float(variance.detach()) if isinstance(variance, torch.Tensor) else float(variance)
+        self._lengthscales = torch.as_tensor(lengthscales, dtype=torch.float64).detach().reshape(-1).cpu()
+
+    @property
+    def variance(self) -> float:
+        return float(self._variance_t.detach()) if self._variance_t is not None else self._variance
+
+    @property
+    def lengthscales(self) -> torch.Tensor:
+        if self._lengthscales_t is not None:
+            return self._lengthscales_t.detach().reshape(-1).double().cpu()
+        return self._lengthscales
+
+    @property
+    def trainable(self) -> bool:
+        return self._variance_t is not None or self._lengthscales_t is not None
 
     @property
     def ard(self) -> bool:
@@ -119,6 +174,14 @@ class Stationary:
         return X if isinstance(X, PreparedPoints) else prepare_points(X, self.lengthscales, dtype)
 
     def K(self, X, X2=None, *, jitter=0.0):
+        if self.trainable and torch.is_grad_enabled() and not isinstance(X, PreparedPoints):
+            Xt = _lib.as_device_tensor(X)
+            X2t = None if X2 is None else _lib.as_device_tensor(X2, Xt.dtype)
+            var_t = self._variance_t if self._variance_t is not None else \
+                torch.tensor(self._variance, dtype=Xt.dtype, device=Xt.device)
+            ls_t = self._lengthscales_t if self._lengthscales_t is not None else \
+                self._lengthscales.to(Xt.device)
+            return _KernelMatrixFn.apply(var_t, ls_t, Xt, X2t, self.kind, float(jitter))
         A = self.prepare(X)
         B = A if X2 is None else self.prepare(X2, A.P.dtype)
         return kernel_matrix(self.kind, self.variance, A, B, jitter=jitter)
@@ -129,6 +192,8 @@ class Stationary:
         else:
             X = _lib.as_device_tensor(X)
             n, dtype, device = X.shape[0], X.dtype, X.device
+        if self._variance_t is not None and torch.is_grad_enabled():
+            return self._variance_t.to(device=device, dtype=dtype).reshape(1).expand(n)
         return torch.full((n,), self.variance, dtype=dtype, device=device)
 
     def __call__(self, X, X2=None, *, full_cov=True):
@@ -191,13 +256,15 @@ class Gaussian:
     """GPflow ``likelihoods.Gaussian`` (variance only), the likelihood of cggp/cli_utils.py:153,164."""
 
     def __init__(self, variance=1.0):
-        self.variance = float(variance)
+        # a number (fixed) or a torch scalar that requires grad (trainable noise variance)
+        self.variance = variance if isinstance(variance, torch.Tensor) and variance.requires_grad else float(variance)
 
     def variational_expectations(self, X, Fmu, Fvar, Y):
         import math
 
         v = self.variance
-        ve = -0.5 * math.log(2.0 * math.pi) - 0.5 * math.log(v) - 0.5 * ((Y - Fmu) ** 2 + Fvar) / v
+        log_v = torch.log(v) if isinstance(v, torch.Tensor) else math.log(v)
+        ve = -0.5 * math.log(2.0 * math.pi) - 0.5 * log_v - 0.5 * ((Y - Fmu) ** 2 + Fvar) / v
         return ve.sum(-1)
 
     def predict_log_density(self, X, Fmu, Fvar, Y):

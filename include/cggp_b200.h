@@ -94,6 +94,15 @@ int cggp_kernel_matrix(cggp_ctx* ctx, int dtype, int kind, double variance, int 
                        const void* dev_PB, const void* dev_normsB, int64_t m,
                        int D, int64_t ldp, double jitter, void* dev_out, int64_t ldo);
 
+/* Backward of cggp_kernel_matrix(output = CGGP_OUT_KERNEL) w.r.t. the hyper-parameters - what TensorFlow autodiff
+ * computes behind the reference's training loop (cggp/optimize.py:198-254; gradients checked in cggp/cg_test.py:40-46):
+ * given dev_G = dL/dK [n, ldg], writes dL/dvariance (1 element) and dL/dlengthscales (D elements; the D contributions
+ * are summed by the caller for an isotropic kernel).  Deterministic (fixed-order reduction). */
+int cggp_kernel_matrix_backward(cggp_ctx* ctx, int dtype, int kind, double variance,
+                                const void* dev_PA, int64_t n, const void* dev_PB, int64_t m, int D, int64_t ldp,
+                                const double* host_lengthscales, int ls_count, const void* dev_G, int64_t ldg,
+                                void* dev_g_variance, void* dev_g_lengthscales);
+
 /* Nearest-centre assignment (cggp/selection.py:14-32, cggp/optimize.py:50-51): for every prepared data row the
  * argmin over the m centres of `distance` (first minimum wins, as tf.argmin) and that minimal distance. */
 int cggp_nearest_center(cggp_ctx* ctx, int dtype, int kind, double variance, int distance,

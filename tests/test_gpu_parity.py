@@ -703,6 +703,117 @@ def test_edge_cases_empty_tiny_and_zero_iterations(cb):
         cb.conjugate_gradient(empty, dev(rhs.astype(np.float32)), None, 1e-6)
 
 
+@pytest.mark.parametrize("name", ["se", "matern12", "matern32", "matern52"])
+@pytest.mark.parametrize("iso", [False, True])
+def test_kernel_matrix_backward_vs_oracle_finite_differences(cb, name, iso):
+    """cggp_kernel_matrix_backward: d sum(G * K(X, Z)) / d(variance, lengthscales) vs central differences of the oracle
+    kernel on a cross matrix without coincident points (so that Matern-1/2 is smooth), ARD and isotropic."""
+    rng = np.random.default_rng(12)
+    n, m, D = 301, 77, 5
+    X, Z = rng.standard_normal((n, D)), rng.standard_normal((m, D))
+    G = rng.standard_normal((n, m))
+    ls0 = np.array([1.1]) if iso else 0.8 + rng.random(D)
+    theta0 = np.concatenate([[1.7], ls0])
+
+    def f(th):
+        ok = g.KERNELS[name](variance=th[0], lengthscales=np.full(D, th[1]) if iso else th[1:])
+        return float(np.sum(G * ok.K(X, Z)))
+
+    fd = np.zeros_like(theta0)
+    for i in range(theta0.size):
+        e = np.zeros_like(theta0)
+        e[i] = 1e-6
+        fd[i] = (f(theta0 + e) - f(theta0 - e)) / 2e-6
+    var = torch.tensor(theta0[0], dtype=torch.float64, device="cuda", requires_grad=True)
+    ls = torch.tensor(theta0[1:], dtype=torch.float64, device="cuda", requires_grad=True)
+    k = cb.kernels.KERNELS[name](variance=var, lengthscales=ls)
+    K = k.K(dev(X), dev(Z))
+    np.testing.assert_allclose(cpu(K), g.KERNELS[name](variance=theta0[0], lengthscales=np.full(D, theta0[1]) if iso
+                                                       else theta0[1:]).K(X, Z), rtol=1e-12, atol=1e-14)
+    (K * dev(G)).sum().backward()
+    got = np.concatenate([[float(var.grad)], cpu(ls.grad).reshape(-1)])
+    np.testing.assert_allclose(got, fd, rtol=1e-6, atol=1e-7 * np.abs(fd).max())
+    # float32 runs the same kernel
+    var32 = torch.tensor(theta0[0], dtype=torch.float32, device="cuda", requires_grad=True)
+    ls32 = torch.tensor(theta0[1:], dtype=torch.float32, device="cuda", requires_grad=True)
+    K32 = cb.kernels.KERNELS[name](variance=var32, lengthscales=ls32).K(dev(X.astype(np.float32)), dev(Z.astype(np.float32)))
+    (K32 * dev(G.astype(np.float32))).sum().backward()
+    got32 = np.concatenate([[float(var32.grad)], cpu(ls32.grad).reshape(-1)])
+    np.testing.assert_allclose(got32, fd, rtol=2e-3, atol=2e-3 * np.abs(fd).max())
+
+
+@pytest.mark.parametrize("name", ["se", "matern32", "matern52"])  # Matern-1/2: finite differences of the ELBO are
+def test_hyperparameter_gradients_vs_oracle_finite_differences(cb, name):  # meaningless on Kuu's non-smooth diagonal
+    """dELBO / d(variance, ARD lengthscales, noise variance): kernel-matrix backward kernel + differentiable CG + custom
+    logdet gradient (models.py:21-48) vs central differences of the ORACLE's ClusterGP.elbo - the CGGP objective has
+    the same gradient (its logdet has value 0 but the true gradient), cf. cggp/cg_test.py:40-77."""
+    rng = np.random.default_rng(5)
+    N, M, D = 400, 24, 3
+    X = rng.uniform(-2, 2, (N, D))
+    y = np.sin(X.sum(-1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
+    Z = X[rng.choice(N, M, replace=False)] + 0.05
+    _, omeans, ocounts = om.oips_style_assignment(Z, X, y)
+    u, cnt = np.nan_to_num(omeans)[:, None], ocounts.astype(np.float64)[:, None]
+    theta0 = np.array([1.3, 0.9, 1.4, 1.1, 0.2])  # variance, 3 lengthscales, noise variance
+
+    def oracle_elbo(th):
+        ok = g.KERNELS[name](variance=th[0], lengthscales=th[1:4])
+        return om.ClusterGP(ok, g.Gaussian(th[4]), Z, cluster_counts=cnt, pseudo_u=u, num_data=N).elbo((X, y))
+
+    fd = np.zeros(5)
+    for i in range(5):
+        h = 1e-6 * max(1.0, abs(theta0[i]))
+        e = np.zeros(5)
+        e[i] = h
+        fd[i] = (oracle_elbo(theta0 + e) - oracle_elbo(theta0 - e)) / (2 * h)
+
+    def grads(model_cls, **kw):
+        var = torch.tensor(theta0[0], dtype=torch.float64, device="cuda", requires_grad=True)
+        ls = torch.tensor(theta0[1:4], dtype=torch.float64, device="cuda", requires_grad=True)
+        noise = torch.tensor(theta0[4], dtype=torch.float64, device="cuda", requires_grad=True)
+        k = cb.kernels.KERNELS[name](variance=var, lengthscales=ls)
+        m = model_cls(k, cb.Gaussian(noise), dev(Z), cluster_counts=dev(cnt), pseudo_u=dev(u), num_data=N, **kw)
+        elbo = m.elbo((dev(X), dev(y)))
+        elbo.backward()
+        return float(elbo.detach()), np.concatenate([[float(var.grad)], cpu(ls.grad), [float(noise.grad)]])
+
+    val, gc = grads(cb.ClusterGP)
+    # (Matern-1/2 is not smooth at r = 0: the diagonal of Kuu carries sqrt(rounding noise), see the kernel tests)
+    np.testing.assert_allclose(val, oracle_elbo(theta0), rtol=1e-8 if name == "matern12" else 1e-10)
+    np.testing.assert_allclose(gc, fd, rtol=2e-5, atol=1e-6 * np.abs(fd).max())
+    # CDGP: every solve (forward and backward) by CG, exact trace
+    _, gg = grads(lambda *a, **kw: cb.CGGP(*a[:3], cb.ConjugateGradient(1e-22, max_iterations=400), num_probes=None,
+                                           **kw))
+    np.testing.assert_allclose(gg, fd, rtol=1e-4, atol=1e-5 * np.abs(fd).max())
+
+
+def test_adam_on_the_cdgp_elbo_improves_it(cb):
+    """The reference's training loop in miniature (optimize.py:198-254): Adam on -ELBO over softplus-transformed
+    kernel / likelihood parameters, everything on the device."""
+    rng = np.random.default_rng(6)
+    N, M, D = 1500, 40, 2
+    X = rng.uniform(-3, 3, (N, D))
+    y = np.sin(2 * X[:, :1]) * np.cos(X[:, 1:]) + 0.1 * rng.standard_normal((N, 1))
+    Z = X[rng.choice(N, M, replace=False)].copy()
+    _, omeans, ocounts = om.oips_style_assignment(Z, X, y)
+    u, cnt = dev(np.nan_to_num(omeans)[:, None]), dev(ocounts.astype(np.float64)[:, None])
+    raw = torch.zeros(4, dtype=torch.float64, device="cuda", requires_grad=True)  # variance, 2 lengthscales, noise
+    opt = torch.optim.Adam([raw], lr=0.05)
+    Xd, yd, Zd = dev(X), dev(y), dev(Z)
+    values = []
+    for step in range(25):
+        p = torch.nn.functional.softplus(raw) + 1e-6
+        k = cb.Matern32(variance=p[0], lengthscales=p[1:3])
+        m = cb.CGGP(k, cb.Gaussian(p[3]), Zd, cb.ConjugateGradient(1e-10), num_probes=None, cluster_counts=cnt,
+                    pseudo_u=u, num_data=N)
+        loss = -m.elbo((Xd, yd))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        values.append(-float(loss.detach()))
+    assert np.isfinite(values).all() and values[-1] > values[0] + 10.0, values[::6]
+
+
 def test_batched_prediction_and_metrics(cb, models_golden):
     """cli_utils.batch_posterior_computation / the RMSE + NLPD of optimize.make_metrics_callback, on the device."""
     c = models_golden["matern32_probes"]
