@@ -49,8 +49,23 @@ def main():
     early = float(dh[:4].max())
     within = bool((dh <= torch.clamp(50.0 * floor, min=2e-9)).all())
     ok = same and early < 2e-9 and within and int(steps) == its
+    # float32 leg: the tcgen05 TF32 kernels on the shards + the same all-reduce, against one GPU over all rows
+    N32, M32, D32 = 60_000, 512, 40
+    g32 = torch.Generator().manual_seed(9)
+    X32 = torch.randn(N32, D32, dtype=torch.float32, generator=g32)
+    Z32 = X32[torch.randperm(N32, generator=g32)[:M32]].clone()
+    V32 = torch.randn(2, M32, dtype=torch.float32, generator=g32).to(dev)
+    k32 = cb.SquaredExponential(1.0, [D32 ** 0.5] * D32)
+    s32, e32 = shard_rows(N32, rank, world)
+    op_sh = cb.SGPROperator(k32, X32[s32:e32].to(dev), Z32.to(dev), 0.1)
+    w_sh = op_sh.kuf_kfu_matmul(V32)  # all-reduced
+    op_all = cb.SGPROperator(k32, X32.to(dev), Z32.to(dev), 0.1)
+    w_all = op_all.kuf_kfu_matmul(V32, allreduce=False)
+    dev32 = float((w_sh - w_all).abs().max() / w_all.abs().max())
+    ok = ok and op_sh.X32 is not None and dev32 < 1e-5
     if rank == 0:
-        msg = f"world={world} identical_on_ranks={same} early_dev={early:.2e} max_dev={float(dh.max()):.2e}"
+        msg = (f"world={world} identical_on_ranks={same} early_dev={early:.2e} max_dev={float(dh.max()):.2e} "
+               f"tf32_sharded_vs_single={dev32:.2e}")
         print(("MGPU_CHECK ok " if ok else "MGPU_CHECK FAIL ") + msg, flush=True)
     dist.barrier()
     dist.destroy_process_group()

@@ -1,0 +1,49 @@
+"""Small invocations of every hand-written kernel family for compute-sanitizer (development aid):
+    compute-sanitizer --tool memcheck python tools/sanitize_case.py"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import cggp_b200 as cb
+from cggp_b200 import selection
+
+
+def main():
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for (N, M, D, kern) in ((1237, 300, 11, "matern52"), (999, 130, 3, "se"), (50, 700, 7, "matern32")):
+        X = torch.randn(N, D, dtype=torch.float64, device="cuda", generator=g)
+        Z = torch.randn(M, D, dtype=torch.float64, device="cuda", generator=g)
+        V = torch.randn(3, M, dtype=torch.float64, device="cuda", generator=g)
+        y = torch.randn(N, 2, dtype=torch.float64, device="cuda", generator=g)
+        k = cb.kernels.KERNELS[kern](1.1, [1.3] * D)
+        op = cb.SGPROperator(k, X, Z, 0.1)
+        ws = [op.kuf_kfu_matmul(V, variant=v) for v in (1, 2, 3)]
+        assert float((ws[2] - ws[0]).abs().max() / ws[0].abs().max()) < 1e-10
+        op.kuf_times(y)
+        rhs = torch.randn(2, M, dtype=torch.float64, device="cuda", generator=g)
+        cb.conjugate_gradient(op, rhs, None, 0.0, None, 5, 3)
+        pc = op.nystrom_preconditioner(num_rows=2 * M)
+        cb.conjugate_gradient(op, rhs, None, 1e-8, pc, 20, 100)
+        selection.nearest_center_update(Z, (X, y[:, :1]))
+        selection.kmeans_indices_and_distances(Z, X)
+        A = cb.add_diagonal(cb.Kuu(Z, k), torch.full((M,), 0.1, dtype=torch.float64, device="cuda"))
+        for B in (1, 5, 40, 200):
+            cb.conjugate_gradient(A, torch.randn(B, M, dtype=torch.float64, device="cuda", generator=g), None, 1e-9,
+                                  None, 15, 7)
+        Xf, Zf, Vf = X.float(), Z.float(), V.float()
+        opf = cb.SGPROperator(cb.kernels.KERNELS[kern](1.1, [1.3] * D), Xf, Zf, 0.1)
+        w4, w1 = opf.kuf_kfu_matmul(Vf), opf.kuf_kfu_matmul(Vf, variant=1)
+        assert float((w4 - w1).abs().max() / w1.abs().max()) < 1e-3
+        opf.kuf_times(y.float())
+        var = torch.tensor(1.1, dtype=torch.float64, device="cuda", requires_grad=True)
+        ls = torch.full((D,), 1.3, dtype=torch.float64, device="cuda", requires_grad=True)
+        cb.kernels.KERNELS[kern](var, ls).K(X, Z).sum().backward()
+    torch.cuda.synchronize()
+    print("sanitize_case ok")
+
+
+if __name__ == "__main__":
+    main()
