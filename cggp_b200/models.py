@@ -270,6 +270,12 @@ class SGPR:
         self.conjugate_gradient = conjugate_gradient or ConjugateGradient(1e-6)
         self.operator = SGPROperator(kernel, self.X, self.inducing_variable.Z, noise_variance, jitter, variant)
         self._c = None
+        # predict_f solves Sigma S = Kus with one right-hand side per test point.  Matrix-free, every PAIR of right-hand
+        # sides costs a full sweep over the N x M Gram entries per iteration; from `dense_threshold` test points on the
+        # [M, M] matrix Sigma = Kuu + Kuf Kfu / s2 is formed once (N M^2 flop, all-reduced, cached) and the multi-RHS CG
+        # runs on it with the DMMA GEMM - GPflow's SGPR materialises the same matrix (as L B L^T).
+        self.dense_threshold = 16
+        self._sigma_dense = None
 
     def _posterior_weights(self):
         if self._c is None:
@@ -320,6 +326,11 @@ class SGPR:
         mean = Kus.t() @ c
         cg = self.conjugate_gradient
         S1 = cg(self.operator.Kuu, Kus)
-        S2 = cg(self.operator, Kus)
+        if self.dense_threshold is not None and Kus.shape[1] >= self.dense_threshold:
+            if self._sigma_dense is None:
+                self._sigma_dense = self.operator.Kuu + self.operator.gram() / self.likelihood.variance
+            S2 = cg(self._sigma_dense, Kus)
+        else:
+            S2 = cg(self.operator, Kus)
         var = self.kernel.K_diag(Xnew) - (Kus * S1).sum(0) + (Kus * S2).sum(0)
         return mean, var[:, None].repeat(1, self.Y.shape[1])

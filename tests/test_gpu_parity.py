@@ -646,9 +646,17 @@ def test_sgpr_predict_matrix_free_vs_gpflow_restatement(cb):
     ref_mean, ref_var = g.SGPR((X, Y), ok, Z, noise_variance=0.2).predict_f(Xs)
     cg = cb.ConjugateGradient(1e-22, max_iterations=4000)
     model = cb.sgpr_class((dev(X), dev(Y)), k, cb.Gaussian(0.2), dev(Z), conjugate_gradient=cg, variant=1)
+    model.dense_threshold = None  # every solve matrix-free
     mean, var = model.predict_f(dev(Xs))
     np.testing.assert_allclose(cpu(mean), ref_mean, rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(cpu(var), ref_var, rtol=1e-5, atol=1e-6)
+    # many test points: Sigma is formed once and the multi-RHS solve runs on the dense matrix
+    model2 = cb.sgpr_class((dev(X), dev(Y)), k, cb.Gaussian(0.2), dev(Z), conjugate_gradient=cg)
+    assert model2.dense_threshold <= Xs.shape[0]
+    mean2, var2 = model2.predict_f(dev(Xs))
+    assert model2._sigma_dense is not None
+    np.testing.assert_allclose(cpu(mean2), ref_mean, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(cpu(var2), ref_var, rtol=1e-5, atol=1e-6)
 
 
 @pytest.mark.parametrize("name", ["se", "matern32", "matern52"])
