@@ -157,19 +157,19 @@ __device__ __forceinline__ double kval(double q, const FastExpTable& tab) {
   }
 }
 
-template <int WARPS, int RB, int CBW, int NB, int KS>
+template <int WARPS, int RB, int CBW, int NB, int KS, int NBUF>
 struct Layout {
   static constexpr int THREADS = WARPS * 32;
   static constexpr int BM = RB * 8;
   static constexpr int WN = CBW * 8;
   static constexpr int BN = WARPS * WN;
   static constexpr int LDX = KS * 4;
-  static constexpr size_t kbuf_bytes = (size_t)2 * RB * CBW * THREADS * sizeof(double2);
+  static constexpr size_t kbuf_bytes = (size_t)NBUF * RB * CBW * THREADS * sizeof(double2);
   static constexpr size_t xt_bytes = (size_t)XS * BM * LDX * sizeof(double);
   static constexpr size_t xn_bytes = (size_t)XS * BM * sizeof(double);
-  static constexpr size_t tred_bytes = (size_t)2 * WARPS * BM * NB * sizeof(double);
-  static constexpr size_t tfull_bytes = (size_t)2 * BM * NB * sizeof(double);
-  static constexpr size_t total = kbuf_bytes + xt_bytes + xn_bytes + tred_bytes + tfull_bytes + (XS + 2) * sizeof(uint64_t);
+  static constexpr size_t tred_bytes = (size_t)NBUF * WARPS * BM * NB * sizeof(double);
+  static constexpr size_t tfull_bytes = (size_t)NBUF * BM * NB * sizeof(double);
+  static constexpr size_t total = kbuf_bytes + xt_bytes + xn_bytes + tred_bytes + tfull_bytes + (XS + NBUF) * sizeof(uint64_t);
 };
 
 // Hand-offs inside a CTA.  T (named barrier 1 + parity): "the partial t of block j is in tred[j & 1] and X stage
@@ -187,10 +187,11 @@ __device__ __forceinline__ void mbar_arrive(void* bar) {
 }
 constexpr int BAR_T = 1;  // + parity of the block
 
-template <int KIND, int KS, int WARPS, int RB, int CBW, int NB>
+template <int KIND, int KS, int WARPS, int RB, int CBW, int NB, int NBUF>
 __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args a) {
   if (cg_inactive(a.active)) return;
-  using L = Layout<WARPS, RB, CBW, NB, KS>;
+  using L = Layout<WARPS, RB, CBW, NB, KS, NBUF>;
+  constexpr int LAG = NBUF - 1;  // phase 2 of block j runs after phase 1 of block j + LAG
   constexpr int THREADS = L::THREADS, BM = L::BM, WN = L::WN, BN = L::BN, LDX = L::LDX;
   constexpr int ALL = THREADS + 32;  // compute warps + the exchange warp
   const int g = blockIdx.x / a.C, rank = blockIdx.x % a.C;
@@ -202,8 +203,8 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
   double* xt = reinterpret_cast<double*>(smem_raw + L::kbuf_bytes);
   double* xn = reinterpret_cast<double*>(smem_raw + L::kbuf_bytes + L::xt_bytes);
   double* tred = reinterpret_cast<double*>(smem_raw + L::kbuf_bytes + L::xt_bytes + L::xn_bytes);  // [2][WARPS][BM*NB]
-  double* tfull = tred + 2 * WARPS * BM * NB;                                                       // [2][BM*NB]
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(tfull + 2 * BM * NB);
+  double* tfull = tred + NBUF * WARPS * BM * NB;                                                       // [2][BM*NB]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(tfull + NBUF * BM * NB);
 
   const int64_t nit = a.nblocks > g ? (a.nblocks - g + a.G - 1) / a.G : 0;  // row blocks of this group
   auto row0_of = [&](int64_t it) { return (g + it * (int64_t)a.G) * BM; };
@@ -213,8 +214,8 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < XS; ++s) mbar_init(&mbar[s], 1);
-    mbar_init(&mbarF[0], 32);
-    mbar_init(&mbarF[1], 32);
+#pragma unroll
+    for (int s = 0; s < NBUF; ++s) mbar_init(&mbarF[s], 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
           tma_bulk_g2s(xt + s * BM * LDX, a.PX + r0 * a.ldp, xb, &mbar[s]);
           tma_bulk_g2s(xn + s * BM, a.nX + r0, nb, &mbar[s]);
         }
-      } else {  // ragged last block / unaligned caller: guarded loads, visible to the compute warps via barrier F
+      } else {  // ragged last block / unaligned caller: guarded loads, completed on the same mbarrier as a TMA tile
         for (int e = lane; e < BM * LDX; e += 32) {
           const int r = e / LDX, k = e % LDX;
           double x = 0.0;
@@ -243,6 +244,8 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
           xt[s * BM * LDX + e] = x;
         }
         for (int e = lane; e < BM; e += 32) xn[s * BM + e] = (r0 + e < a.n) ? a.nX[r0 + e] : 0.0;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mbar[s]);  // release: the tile written by the 32 lanes is visible to the waiters
       }
     };
 #pragma unroll
@@ -251,7 +254,7 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
     __syncthreads();  // (S) first tiles staged (manual ones visible)
     double* slots_g = a.part + (int64_t)g * SLOTS * a.C * (BM * NB);
     for (int64_t it = 0; it < nit; ++it) {
-      const int par = (int)(it & 1);
+      const int par = (int)(it % NBUF);
       bar_sync(BAR_T + par, ALL);  // every compute warp finished phase 1 of block it
       stage_tile(it + XS);         // X stage it % XS is free again
       const double* tr = tred + par * WARPS * BM * NB;
@@ -356,8 +359,8 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
   // phase 2 of block `jt`: w += K^T t from the K values this thread parked in shared memory.  (Interleaving these
   // steps into phase 1 of the next block was measured slower than running them back to back: 22.8-25.6 vs 20.5 ms.)
   auto phase2 = [&](int64_t jt) {
-    const int par = (int)(jt & 1);
-    mbar_wait(&mbarF[par], (unsigned)((jt >> 1) & 1));  // t of block jt is complete (normally long before)
+    const int par = (int)(jt % NBUF);
+    mbar_wait(&mbarF[par], (unsigned)((jt / NBUF) & 1));  // t of block jt is complete (normally long before)
     const double* tf = tfull + par * BM * NB;
     const double2* kb = kbuf + (size_t)par * RB * CBW * THREADS + tid;
 #pragma unroll
@@ -380,8 +383,8 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
   __syncthreads();  // (S)
   for (int64_t it = 0; it < nit; ++it) {
     // ------------------------------- phase 1 of block `it` -------------------------------
-    const int s = (int)(it % XS), par = (int)(it & 1);
-    if (!is_manual(it)) mbar_wait(&mbar[s], (unsigned)((it / XS) & 1));
+    const int s = (int)(it % XS), par = (int)(it % NBUF);
+    mbar_wait(&mbar[s], (unsigned)((it / XS) & 1));  // X tile (TMA or guarded loads) has landed
     const double* xs = xt + s * BM * LDX + lr * LDX + lk;
     const double* xns = xn + s * BM + lr;
     double2* kb = kbuf + (size_t)par * RB * CBW * THREADS + tid;
@@ -422,9 +425,10 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
     __threadfence_block();
     bar_arrive(BAR_T + par, ALL);  // hand the partials (and the X stage) to the exchange warp; do not wait
     // ------------------------------- phase 2 of block `it - 1` -------------------------------
-    if (it >= 1 && !(a.dbg & 1)) phase2(it - 1);
+    if (it >= LAG && !(a.dbg & 1)) phase2(it - LAG);
   }
-  if (nit >= 1 && !(a.dbg & 1)) phase2(nit - 1);
+  if (!(a.dbg & 1))
+    for (int64_t jt = nit > LAG ? nit - LAG : 0; jt < nit; ++jt) phase2(jt);
 
   // reduce the 8 row-lanes of every column, write this group's partial
 #pragma unroll
@@ -459,11 +463,11 @@ struct Plan {
   size_t smem;
 };
 
-template <int KIND, int KS, int WARPS, int RB, int CBW, int NB>
+template <int KIND, int KS, int WARPS, int RB, int CBW, int NB, int NBUF>
 static Plan make_plan() {
-  using L = Layout<WARPS, RB, CBW, NB, KS>;
+  using L = Layout<WARPS, RB, CBW, NB, KS, NBUF>;
   Plan p;
-  p.fn = (const void*)kfu_pipe_kernel<KIND, KS, WARPS, RB, CBW, NB>;
+  p.fn = (const void*)kfu_pipe_kernel<KIND, KS, WARPS, RB, CBW, NB, NBUF>;
   p.threads = L::THREADS + 32;  // + the exchange warp
   p.BM = L::BM;
   p.BN = L::BN;
@@ -472,30 +476,32 @@ static Plan make_plan() {
   return p;
 }
 
+// `deep`: three K buffers of 32 rows instead of two of 48, i.e. the group exchange of a block has TWO phase-1 periods
+// to complete.  Pays off when the group is large (M = 16384: 64 CTAs to wait for; 59.7 -> 52.7 ms at N = 1M, D = 2).
 template <int KIND, int KS>
-static bool plan_for_nb(int nb, Plan& p) {
+static bool plan_for_nb(int nb, bool deep, Plan& p) {
   switch (nb) {
-    case 1: p = make_plan<KIND, KS, 16, 6, 2, 1>(); return true;
-    case 2: p = make_plan<KIND, KS, 16, 5, 2, 2>(); return true;  // 40-row blocks: two tred/tfull sets must fit
+    case 1: p = deep ? make_plan<KIND, KS, 16, 4, 2, 1, 3>() : make_plan<KIND, KS, 16, 6, 2, 1, 2>(); return true;
+    case 2: p = deep ? make_plan<KIND, KS, 16, 3, 2, 2, 3>() : make_plan<KIND, KS, 16, 5, 2, 2, 2>(); return true;
     default: return false;
   }
 }
 template <int KIND>
-static bool plan_for_ks(int ks, int nb, Plan& p) {
+static bool plan_for_ks(int ks, int nb, bool deep, Plan& p) {
   switch (ks) {
-    case 1: return plan_for_nb<KIND, 1>(nb, p);
-    case 2: return plan_for_nb<KIND, 2>(nb, p);
-    case 3: return plan_for_nb<KIND, 3>(nb, p);
-    case 4: return plan_for_nb<KIND, 4>(nb, p);
+    case 1: return plan_for_nb<KIND, 1>(nb, deep, p);
+    case 2: return plan_for_nb<KIND, 2>(nb, deep, p);
+    case 3: return plan_for_nb<KIND, 3>(nb, deep, p);
+    case 4: return plan_for_nb<KIND, 4>(nb, deep, p);
     default: return false;
   }
 }
-static bool plan_for(int kind, int ks, int nb, Plan& p) {
+static bool plan_for(int kind, int ks, int nb, bool deep, Plan& p) {
   switch (kind) {
-    case CGGP_SE: return plan_for_ks<CGGP_SE>(ks, nb, p);
-    case CGGP_MATERN12: return plan_for_ks<CGGP_MATERN12>(ks, nb, p);
-    case CGGP_MATERN32: return plan_for_ks<CGGP_MATERN32>(ks, nb, p);
-    case CGGP_MATERN52: return plan_for_ks<CGGP_MATERN52>(ks, nb, p);
+    case CGGP_SE: return plan_for_ks<CGGP_SE>(ks, nb, deep, p);
+    case CGGP_MATERN12: return plan_for_ks<CGGP_MATERN12>(ks, nb, deep, p);
+    case CGGP_MATERN32: return plan_for_ks<CGGP_MATERN32>(ks, nb, deep, p);
+    case CGGP_MATERN52: return plan_for_ks<CGGP_MATERN52>(ks, nb, deep, p);
     default: return false;
   }
 }
@@ -536,7 +542,9 @@ static int pipe_launch(cggp_ctx* ctx, int kind, double variance, const double* P
   while (b0 < B) {
     const int nb = (B - b0) >= 2 ? 2 : 1;
     Plan p;
-    if (!plan_for(kind, ks, nb, p)) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "pipelined matvec: no plan for D=%d", D);
+    static const int deep_env = getenv("CGGP_PIPE_DEEP") ? atoi(getenv("CGGP_PIPE_DEEP")) : -1;  // tuning knob
+    const bool deep = deep_env >= 0 ? deep_env != 0 : (m > 8192);  // measured: wins at M = 16384, loses at M <= 4096
+    if (!plan_for(kind, ks, nb, deep, p)) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "pipelined matvec: no plan for D=%d", D);
     CGGP_CUDA(ctx, cudaFuncSetAttribute(p.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     int occ = 0;
     CGGP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p.fn, p.threads, p.smem));

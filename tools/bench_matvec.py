@@ -15,7 +15,10 @@ def timeit(fn, reps=5, warm=2):
     return min(ts), sum(ts) / len(ts)
 
 def main():
-    cfgs = [("c3", 2_000_000, 4096, 11, "matern52"), ("c2", 434_874, 2048, 3, "se"), ("c1", 10_000, 500, 2, "se")]
+    cfgs = [("c3", 2_000_000, 4096, 11, "matern52"), ("c2", 434_874, 2048, 3, "se"), ("c1", 10_000, 500, 2, "se"),
+            ("c4", 1_000_000, 16384, 2, "matern52")]  # c4: one rank's share (N = 8M over 8 GPUs) of BASELINE configs[3]
+    if len(sys.argv) == 1:
+        cfgs = cfgs[:3]
     if len(sys.argv) > 1:
         cfgs = [c for c in cfgs if c[0] in sys.argv[1:]]
     g = torch.Generator(device="cuda").manual_seed(0)
