@@ -10,9 +10,9 @@
 //   * 3xTF32:  x.z ~ xb.zb + xs.zb + xb.zs  (three accumulating MMA groups; the dropped xs.zs term is 2^-22 relative),
 //     which keeps the expanded squared distance at float32 accuracy - a single TF32 pass (NSPLIT = 1) loses ~3 digits
 //     to the cancellation in |x|^2 + |z|^2 - 2 x.z;
-//   * generic "gram contraction"  out[b, p] = sum_q k(P_p, Q_q) U[b, q]:  a CTA owns 128 P rows (= the 128 TMEM lanes,
-//     both parts resident in shared memory) and loops over 128-column Q tiles that stream through a ring of K-chunk
-//     stages.  Warp 8 is the TMA producer, warp 9 issues the tcgen05.mma chain (one elected lane each) and commits
+//   * generic "gram contraction"  out[b, p] = sum_q k(P_p, Q_q) U[b, q]:  a CTA owns 128 P rows (= the 128 TMEM lanes;
+//     both parts of the P tile live in TENSOR MEMORY as the A operand of every MMA, next to the accumulators) and
+//     loops over 128-column Q tiles that stream through a ring of K-chunk stages in shared memory.  Warp 8 is the TMA producer, warp 9 issues the tcgen05.mma chain (one elected lane each) and commits
 //     onto mbarriers, warp 10 stages the per-column scalars (|q|^2, U); warps 0-7 are the epilogue: tcgen05.ld of a finished accumulator (thread = row, registers = 64
 //     columns), r2 = |p|^2 + |q|^2 - 2 p.q, kernel value with MUFU ex2 / sqrt, dot with U.  Two TMEM accumulators
 //     (2 x 128 columns) let the MMAs of tile j+1 run under the epilogue of tile j.
@@ -70,6 +70,23 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
       "}\n" ::"r"(tmem_d),
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// same with the A operand in tensor memory (row m = lane m, feature k = column k of the given TMEM address)
+__device__ __forceinline__ void umma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
 }
 __device__ __forceinline__ void umma_commit(void* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -189,9 +206,10 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nchunk = KP >> 5;
   const int STAGES = a.stages;
-  float* sP = reinterpret_cast<float*>(smem_raw);                       // [PARTS][nchunk][4096]
-  float* sQ = sP + (size_t)PARTS * nchunk * CHUNK_FLOATS;               // [STAGES][PARTS][4096]
+  float* sQ = reinterpret_cast<float*>(smem_raw);                       // [STAGES][PARTS][4096]
   float* aux = sQ + (size_t)STAGES * PARTS * CHUNK_FLOATS;              // [2][(1 + NB) * BN]
+  // TMEM: columns [0, 256) two accumulators; [256, 256 + PARTS * KP) the P tile as the A operand (row = lane)
+  constexpr uint32_t TM_P = 256;
   __shared__ uint64_t bar_p, bar_qfull[MAX_STAGES], bar_qfree[MAX_STAGES], bar_full[2], bar_empty[2], bar_aux[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float comb[BM * NB];  // partial sums of the second column half, combined at the end
@@ -205,7 +223,7 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
   if (njt < 0) njt = 0;
 
   if (tid == 0) {
-    mbar_init(&bar_p, 1);
+    mbar_init(&bar_p, 256);
     for (int b = 0; b < MAX_STAGES; ++b) {
       mbar_init(&bar_qfull[b], 1);
       mbar_init(&bar_qfree[b], 1);
@@ -218,7 +236,7 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_s)));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
@@ -228,12 +246,6 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
 
   if (warp == 8) {
     // =============================== TMA producer warp ===============================
-    if (njt > 0 && lane == 0) {  // the P tile: both parts, all chunks (contiguous per part)
-      const unsigned pbytes = (unsigned)nchunk * CHUNK_BYTES;
-      mbar_expect_tx(&bar_p, PARTS * pbytes);
-      tma_bulk_g2s(sP, a.Pb + p0 * KP, pbytes, &bar_p);
-      if (PARTS > 1) tma_bulk_g2s(sP + (size_t)nchunk * CHUNK_FLOATS, a.Ps + p0 * KP, pbytes, &bar_p);
-    }
     if (lane == 0) {
       int64_t g = 0;  // running chunk counter over the whole loop
       for (int64_t j = 0; j < njt; ++j) {
@@ -280,7 +292,8 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
       const unsigned lbo = 128, sbo = 1024;
       const uint32_t idesc =
           (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      mbar_wait(&bar_p, 0);
+      mbar_wait(&bar_p, 0);  // the epilogue warps have stored the P tile into tensor memory
+      asm volatile("tcgen05.fence::after_thread_sync;");
       int64_t g = 0;
       for (int64_t j = 0; j < njt; ++j) {
         const int buf = (int)(j & 1);
@@ -291,20 +304,20 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
           const int s = (int)(g % STAGES);
           mbar_wait(&bar_qfull[s], (unsigned)((g / STAGES) & 1));
           asm volatile("tcgen05.fence::after_thread_sync;");
-          const unsigned pb = smem_u32(sP) + (unsigned)c * CHUNK_BYTES, ps = pb + (unsigned)nchunk * CHUNK_BYTES;
+          const uint32_t pb = tmem_base + TM_P + (uint32_t)c * 32, ps = pb + (uint32_t)KP;  // A operand: TMEM columns
           const unsigned qb = smem_u32(sQ) + (unsigned)s * PARTS * CHUNK_BYTES, qs = qb + CHUNK_BYTES;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // D (+)= Pb Qb^T
-            umma_tf32(d, smem_desc(pb + k * 256, lbo, sbo), smem_desc(qb + k * 256, lbo, sbo), idesc, acc);
+            umma_tf32_ta(d, pb + k * 8, smem_desc(qb + k * 256, lbo, sbo), idesc, acc);
             acc = 1;
           }
           if (PARTS > 1) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)  // + Ps Qb^T
-              umma_tf32(d, smem_desc(ps + k * 256, lbo, sbo), smem_desc(qb + k * 256, lbo, sbo), idesc, 1);
+              umma_tf32_ta(d, ps + k * 8, smem_desc(qb + k * 256, lbo, sbo), idesc, 1);
 #pragma unroll
             for (int k = 0; k < 4; ++k)  // + Pb Qs^T
-              umma_tf32(d, smem_desc(pb + k * 256, lbo, sbo), smem_desc(qs + k * 256, lbo, sbo), idesc, 1);
+              umma_tf32_ta(d, pb + k * 8, smem_desc(qs + k * 256, lbo, sbo), idesc, 1);
           }
           umma_commit(&bar_qfree[s]);  // the stage may be refilled once these MMAs are done
         }
@@ -320,6 +333,26 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
     const int64_t p = p0 + row;
     const float pn = a.pn[p];  // padded array
     const float cp = -HALF_LOG2E * pn;
+    if (njt > 0) {
+      // P tile -> tensor memory (A operand of every MMA of this CTA): thread = row = TMEM lane; the two column halves
+      // of the epilogue split the features.  Halves the shared-memory operand traffic of the MMAs (only Q is read
+      // from shared memory) and frees 96 KB for a deeper Q ring.
+      const int kper = KP / 2;  // KP is a multiple of 32
+      for (int part = 0; part < PARTS; ++part) {
+        const float* src = part == 0 ? a.Pb : a.Ps;
+        for (int k0 = half * kper; k0 < (half + 1) * kper; k0 += 8) {
+          const float4 x0 = *reinterpret_cast<const float4*>(src + canon_off(p, k0, KP));
+          const float4 x1 = *reinterpret_cast<const float4*>(src + canon_off(p, k0 + 4, KP));
+          const uint32_t v[8] = {__float_as_uint(x0.x), __float_as_uint(x0.y), __float_as_uint(x0.z),
+                                 __float_as_uint(x0.w), __float_as_uint(x1.x), __float_as_uint(x1.y),
+                                 __float_as_uint(x1.z), __float_as_uint(x1.w)};
+          tmem_st8(tmem_base + ((uint32_t)(quarter * 32) << 16) + TM_P + (uint32_t)(part * KP + k0), v);
+        }
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      mbar_arrive(&bar_p);
+    }
     float acc[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) acc[b] = 0.f;
@@ -384,7 +417,7 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
 }
 
 __global__ void reduce_splits_kernel(const float* __restrict__ part, int splits, int NB, int64_t ld, int64_t n,
@@ -420,7 +453,8 @@ constexpr size_t SMEM_BUDGET = 227 * 1024 - 1024;  // leave room for the static 
 // ring depth that fits next to the resident P tile (0 = does not fit)
 static int stages_for(int KP, int nsplit, int nb) {
   const size_t parts = nsplit > 1 ? 2 : 1;
-  const size_t fixed = parts * (size_t)(KP / 32) * CHUNK_BYTES + (size_t)2 * (1 + nb) * 128 * sizeof(float) + 128;
+  if (parts * (size_t)KP > 256) return 0;  // the P tile must fit in the 256 tensor-memory columns next to the accumulators
+  const size_t fixed = (size_t)2 * (1 + nb) * 128 * sizeof(float) + 128;
   if (fixed >= SMEM_BUDGET) return 0;
   size_t st = (SMEM_BUDGET - fixed) / (parts * CHUNK_BYTES);
   if (st > MAX_STAGES) st = MAX_STAGES;
@@ -428,7 +462,7 @@ static int stages_for(int KP, int nsplit, int nb) {
 }
 static size_t smem_bytes(int KP, int nsplit, int nb, int stages) {
   const size_t parts = nsplit > 1 ? 2 : 1;
-  return parts * (size_t)(KP / 32 + stages) * CHUNK_BYTES + (size_t)2 * (1 + nb) * 128 * sizeof(float) + 128;
+  return parts * (size_t)stages * CHUNK_BYTES + (size_t)2 * (1 + nb) * 128 * sizeof(float) + 128;
 }
 }  // namespace tf32
 

@@ -84,7 +84,7 @@ class SGPROperator(LinearOperator):
             if ctx.lib.cggp_tf32_supported(ctx.handle, self.PZ.D, self.tf32_nsplit):
                 self.X32, self.Z32 = prepare_tf32(self.PX), prepare_tf32(self.PZ)
             elif self.variant == 4:
-                raise _lib.CggpError("the tcgen05 TF32 path needs sm_100 and D <= 160 (3xTF32) / 320 (1xTF32)")
+                raise _lib.CggpError("the tcgen05 TF32 path needs sm_100 and D <= 128 (3xTF32) / 256 (1xTF32)")
 
     def c_struct(self):
         op = _lib.Operator()

@@ -137,8 +137,8 @@ int cggp_kuf_kfu_matvec(cggp_ctx* ctx, int dtype, int kind, double variance,
  * distances), nsplit = 1 -> single TF32 pass (3x fewer tensor-core flops, ~1e-3 relative on the distances). */
 int cggp_tf32_kp(int D);
 int64_t cggp_tf32_rows(int64_t n);
-/* 1 if the device is sm_100+ and the resident row tile plus a ring of K-chunk stages fit in shared memory
- * (D <= 160 for nsplit = 3, D <= 320 for nsplit = 1), else 0 */
+/* 1 if the device is sm_100+ and the row tile fits in tensor memory next to the two accumulators
+ * (D <= 128 for nsplit = 3, D <= 256 for nsplit = 1), else 0 */
 int cggp_tf32_supported(cggp_ctx* ctx, int D, int nsplit);
 int cggp_tf32_prepare(cggp_ctx* ctx, const void* dev_P, const void* dev_norms, int64_t n, int D, int64_t ldp,
                       void* dev_big, void* dev_small, void* dev_norms_pad);

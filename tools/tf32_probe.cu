@@ -25,7 +25,7 @@ __device__ __forceinline__ uint64_t make_desc(unsigned saddr, unsigned lbo, unsi
          (1ull << 46);
 }
 
-template <int KP>
+template <int KP, bool A_TMEM>
 __global__ void __launch_bounds__(128) probe_kernel(const float* A, const float* B, float* D) {
   extern __shared__ __align__(128) float smem[];
   float* sA = smem;
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* A, const float*
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&tmem_base)));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // generic-proxy writes of the operands -> visible to the async proxy (tensor core reads)
@@ -49,6 +49,23 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* A, const float*
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tb = tmem_base;
+  if (A_TMEM) {
+    // A operand in tensor memory: row m -> lane m, feature k -> column 128 + k (one 32-bit column per TF32 element);
+    // every thread stores its own row with tcgen05.st (thread = lane), 8 columns at a time
+    const int row = warp * 32 + lane;
+    for (int k0 = 0; k0 < KP; k0 += 8) {
+      uint32_t v[8];
+      for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(A[row * KP + k0 + i]);
+      const uint32_t taddr = tb + ((uint32_t)(warp * 32) << 16) + 128 + k0;
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]),
+                   "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                   : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+  }
   if (tid == 0) {
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
     const unsigned lbo = 128, sbo = (KP / 4) * 128;
@@ -56,10 +73,18 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* A, const float*
       const uint64_t da = make_desc(smem_u32(sA) + j * 256, lbo, sbo);
       const uint64_t db = make_desc(smem_u32(sB) + j * 256, lbo, sbo);
       const uint32_t acc = j > 0;
-      asm volatile(
-          "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-          "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tb), "l"(da), "l"(db), "r"(idesc), "r"(acc)
-          : "memory");
+      if (A_TMEM) {
+        const uint32_t ta = tb + 128 + j * 8;
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tb), "r"(ta), "l"(db), "r"(idesc), "r"(acc)
+            : "memory");
+      } else {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tb), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+            : "memory");
+      }
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
   }
@@ -86,12 +111,12 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* A, const float*
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tb));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tb));
 }
 
 static float tf32_trunc(float x) { unsigned u; memcpy(&u, &x, 4); u &= 0xffffe000u; float y; memcpy(&y, &u, 4); return y; }
 
-template <int KP>
+template <int KP, bool A_TMEM>
 int run() {
   std::vector<float> A(M * KP), B(N * KP), D(M * N), R(M * N), Rt(M * N);
   srand(1);
@@ -109,21 +134,24 @@ int run() {
   CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dD, 0, D.size() * 4));
   const size_t smem = (size_t)(M + N) * KP * 4;
-  CK(cudaFuncSetAttribute(probe_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  probe_kernel<KP><<<1, 128, smem>>>(dA, dB, dD);
+  CK(cudaFuncSetAttribute(probe_kernel<KP, A_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_kernel<KP, A_TMEM><<<1, 128, smem>>>(dA, dB, dD);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
   double e_full = 0, e_trunc = 0, scale = 0;
   for (int i = 0; i < M * N; ++i) { e_full = fmax(e_full, fabs(D[i] - R[i])); e_trunc = fmax(e_trunc, fabs(D[i] - Rt[i])); scale = fmax(scale, fabs(R[i])); }
-  printf("K=%3d: max|D - fp32 ref| = %.3e   max|D - tf32-truncated ref| = %.3e   (scale %.3f)  D[0..3] = %f %f %f %f  ref %f %f %f %f\n", KP, e_full,
+  printf("%s K=%3d: max|D - fp32 ref| = %.3e   max|D - tf32-truncated ref| = %.3e   (scale %.3f)  D[0..3] = %f %f %f %f  ref %f %f %f %f\n", A_TMEM ? "A in TMEM:" : "A in smem:", KP, e_full,
          e_trunc, scale, D[0], D[1], D[2], D[3], R[0], R[1], R[2], R[3]);
   return (e_full < 5e-3 * scale) ? 0 : 1;
 }
 
 int main() {
-  int bad = run<8>();
-  bad += run<32>();
-  bad += run<96>();
+  int bad = run<8, false>();
+  bad += run<32, false>();
+  bad += run<96, false>();
+  bad += run<8, true>();
+  bad += run<32, true>();
+  bad += run<96, true>();
   printf(bad ? "PROBE FAIL\n" : "PROBE OK\n");
   return bad;
 }
