@@ -138,6 +138,79 @@ class _KernelMatrixFn(torch.autograd.Function):
                 g_ls.reshape(lengthscales_t.shape).to(lengthscales_t.dtype), None, None, None, None)
 
 
+class _SGPRTermsFn(torch.autograd.Function):
+    """``(K(Z, Z), Kuf Kfu, Kuf Y)`` over this rank's shard, differentiable in the kernel hyper-parameters: the three
+    kernel-dependent terms of GPflow's ``SGPR.elbo``.  Forward forms ``Kuf`` in row chunks (``cggp_kernel_matrix``) and
+    accumulates the rank-k updates; backward re-forms each chunk, builds ``dL/dKuf = (dG + dG^T) Kuf + dW Y^T`` and
+    hands it to ``cggp_kernel_matrix_backward``.  The shard terms (forward values and parameter gradients) are
+    all-reduced over the communicator of the context, so every rank sees the full gradient."""
+
+    @staticmethod
+    def forward(ctx, variance_t, lengthscales_t, X, Z, Y, kind):
+        ls = lengthscales_t.detach().reshape(-1).double().cpu()
+        var = float(variance_t.detach())
+        PZ = prepare_points(Z, ls)
+        PX = prepare_points(X, ls, PZ.P.dtype)
+        M = PZ.n
+        Kzz = kernel_matrix(kind, var, PZ, PZ)
+        G = torch.zeros((M, M), dtype=PZ.P.dtype, device=PZ.P.device)
+        W = torch.zeros((M, Y.shape[1]), dtype=PZ.P.dtype, device=PZ.P.device)
+        step = max(1, (1 << 27) // max(M, 1))
+        for s in range(0, PX.n, step):
+            e = min(PX.n, s + step)
+            Kzx = kernel_matrix(kind, var, PZ, PX.rows(s, e))
+            G.addmm_(Kzx, Kzx.t())
+            W.addmm_(Kzx, Y[s:e])
+        c = _lib.context(PZ.P.device)
+        if c.world > 1:
+            c.allreduce_sum_(G)
+            c.allreduce_sum_(W)
+        ctx.save_for_backward(PZ.P, PZ.norms, PX.P, PX.norms, Y)
+        ctx.meta = (kind, var, ls, PZ.D, variance_t, lengthscales_t, step)
+        return Kzz, G, W
+
+    @staticmethod
+    def backward(ctx, dKzz, dG, dW):
+        PZp, PZn, PXp, PXn, Y = ctx.saved_tensors
+        kind, var, ls, D, variance_t, lengthscales_t, step = ctx.meta
+        c = _lib.context(PZp.device)
+        c.use_current_stream()
+        arr = (C.c_double * ls.numel())(*ls.tolist())
+        PZ = PreparedPoints(PZp, PZn, D)
+        PX = PreparedPoints(PXp, PXn, D)
+
+        def kmb(PA, PB, Gm):
+            Gm = _lib.row_major(Gm.contiguous())
+            g_var = torch.empty((1,), dtype=PZp.dtype, device=PZp.device)
+            g_ls = torch.empty((D,), dtype=PZp.dtype, device=PZp.device)
+            c.check(c.lib.cggp_kernel_matrix_backward(
+                c.handle, _lib.dtype_code(PZp.dtype), int(kind), var, _lib.ptr(PA.P), PA.n, _lib.ptr(PB.P), PB.n, D,
+                PA.P.shape[1], arr, ls.numel(), _lib.ptr(Gm), Gm.stride(0), _lib.ptr(g_var), _lib.ptr(g_ls)))
+            return torch.cat([g_var, g_ls])
+
+        shard = torch.zeros((1 + D,), dtype=PZp.dtype, device=PZp.device)
+        sym = None if dG is None else dG + dG.t()
+        for s in range(0, PX.n, step):
+            e = min(PX.n, s + step)
+            rows = PX.rows(s, e)
+            dK = torch.zeros((PZ.n, e - s), dtype=PZp.dtype, device=PZp.device)
+            if sym is not None:
+                dK.addmm_(sym, kernel_matrix(kind, var, PZ, rows))
+            if dW is not None:
+                dK.addmm_(dW, Y[s:e].t())
+            shard += kmb(PZ, rows, dK)
+        if c.world > 1:
+            c.allreduce_sum_(shard)
+        g = shard
+        if dKzz is not None:
+            g = g + kmb(PZ, PZ, dKzz)  # replicated term: identical on every rank, not reduced
+        g_var, g_ls = g[:1], g[1:]
+        if lengthscales_t.numel() == 1:
+            g_ls = g_ls.sum()
+        return (g_var.reshape(variance_t.shape).to(variance_t.dtype),
+                g_ls.reshape(lengthscales_t.shape).to(lengthscales_t.dtype), None, None, None, None)
+
+
 class Stationary:
     """``variance`` / ``lengthscales`` may be numbers (fixed) or torch tensors that require grad (trainable: pass e.g.
     ``softplus(raw)``); with trainable parameters ``K`` / ``K_diag`` are differentiable (``_KernelMatrixFn``)."""
@@ -185,6 +258,13 @@ class Stationary:
         A = self.prepare(X)
         B = A if X2 is None else self.prepare(X2, A.P.dtype)
         return kernel_matrix(self.kind, self.variance, A, B, jitter=jitter)
+
+    def param_tensors(self, dtype, device):
+        """(variance, lengthscales) as tensors on `device` (the trainable ones where present)."""
+        var_t = self._variance_t if self._variance_t is not None else \
+            torch.tensor(self._variance, dtype=dtype, device=device)
+        ls_t = self._lengthscales_t if self._lengthscales_t is not None else self._lengthscales.to(device)
+        return var_t, ls_t
 
     def K_diag(self, X):
         if isinstance(X, PreparedPoints):

@@ -268,7 +268,8 @@ class SGPR:
         self.likelihood = Gaussian(noise_variance)
         self.jitter = jitter
         self.conjugate_gradient = conjugate_gradient or ConjugateGradient(1e-6)
-        self.operator = SGPROperator(kernel, self.X, self.inducing_variable.Z, noise_variance, jitter, variant)
+        nv = float(noise_variance.detach()) if isinstance(noise_variance, torch.Tensor) else float(noise_variance)
+        self.operator = SGPROperator(kernel, self.X, self.inducing_variable.Z, nv, jitter, variant)
         self._c = None
         # predict_f solves Sigma S = Kus with one right-hand side per test point.  Matrix-free, every PAIR of right-hand
         # sides costs a full sweep over the N x M Gram entries per iteration; from `dense_threshold` test points on the
@@ -293,14 +294,27 @@ class SGPR:
         op, ctx = self.operator, _lib.context(self.operator.device)
         s2 = self.likelihood.variance
         P = self.Y.shape[1]
-        G = op.gram()
-        KufY = op.kuf_times(self.Y)  # [M, P], all-reduced
+        trainable = torch.is_grad_enabled() and (self.kernel.trainable or isinstance(s2, torch.Tensor))
+        if trainable:
+            # differentiable in (variance, lengthscales, noise variance): the kernel terms come from _SGPRTermsFn with
+            # the CURRENT hyper-parameters (self.operator was prepared with the values at construction time)
+            from .kernels import _SGPRTermsFn
+
+            var_t, ls_t = self.kernel.param_tensors(self.X.dtype, self.X.device)
+            Kzz, G, KufY = _SGPRTermsFn.apply(var_t, ls_t, self.X, self.inducing_variable.Z, self.Y, self.kernel.kind)
+            Kuu_j = Kzz + self.jitter * torch.eye(op.n, dtype=Kzz.dtype, device=Kzz.device)
+            kvar = var_t
+            log_s2 = torch.log(s2) if isinstance(s2, torch.Tensor) else math.log(s2)
+        else:
+            G = op.gram()
+            KufY = op.kuf_times(self.Y)  # [M, P], all-reduced
+            Kuu_j, kvar, log_s2 = op.Kuu, self.kernel.variance, math.log(s2)
         stats = torch.stack([torch.tensor(float(self.X.shape[0]), dtype=self.Y.dtype, device=self.Y.device),
                              (self.Y * self.Y).sum()])
         if ctx.world > 1:
             ctx.allreduce_sum_(stats)
         n_total, sum_y2 = float(stats[0]), stats[1]
-        L = torch.linalg.cholesky(op.Kuu)
+        L = torch.linalg.cholesky(Kuu_j)
         AAT = torch.linalg.solve_triangular(L, torch.linalg.solve_triangular(L, G, upper=False).t(), upper=False) / s2
         AAT = 0.5 * (AAT + AAT.t())
         B = AAT + torch.eye(op.n, dtype=AAT.dtype, device=AAT.device)
@@ -309,9 +323,9 @@ class SGPR:
         c = torch.linalg.solve_triangular(LB, Aerr, upper=False)
         const = -0.5 * n_total * P * math.log(2.0 * math.pi)
         half_logdet_B = torch.log(torch.diagonal(LB)).sum()
-        trace_k = n_total * self.kernel.variance / s2
+        trace_k = n_total * kvar / s2
         trace_q = torch.trace(AAT)
-        logdet = -P * (half_logdet_B + 0.5 * n_total * math.log(s2) + 0.5 * (trace_k - trace_q))
+        logdet = -P * (half_logdet_B + 0.5 * n_total * log_s2 + 0.5 * (trace_k - trace_q))
         quad = -0.5 * (sum_y2 / s2 - (c * c).sum())
         return const + logdet + quad
 

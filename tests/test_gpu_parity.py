@@ -796,6 +796,37 @@ def test_hyperparameter_gradients_vs_oracle_finite_differences(cb, name):  # mea
     np.testing.assert_allclose(gg, fd, rtol=1e-4, atol=1e-5 * np.abs(fd).max())
 
 
+@pytest.mark.parametrize("name", ["se", "matern32", "matern52"])
+def test_sgpr_elbo_gradients_vs_oracle_finite_differences(cb, name):
+    """d SGPR.elbo / d(variance, ARD lengthscales, noise variance) through the chunked Gram backward vs central
+    differences of the oracle's GPflow restatement."""
+    rng = np.random.default_rng(15)
+    N, M, D = 700, 20, 2
+    X = rng.uniform(-2, 2, (N, D))
+    Y = np.sin(2 * X[:, :1]) + 0.1 * rng.standard_normal((N, 2))
+    Z = rng.uniform(-2, 2, (M, D))
+    theta0 = np.array([1.2, 0.9, 1.4, 0.2])
+
+    def oracle(th):
+        return g.SGPR((X, Y), g.KERNELS[name](variance=th[0], lengthscales=th[1:3]), Z, noise_variance=th[3]).elbo()
+
+    fd = np.zeros(4)
+    for i in range(4):
+        e = np.zeros(4)
+        e[i] = 1e-6
+        fd[i] = (oracle(theta0 + e) - oracle(theta0 - e)) / 2e-6
+    var = torch.tensor(theta0[0], dtype=torch.float64, device="cuda", requires_grad=True)
+    ls = torch.tensor(theta0[1:3], dtype=torch.float64, device="cuda", requires_grad=True)
+    noise = torch.tensor(theta0[3], dtype=torch.float64, device="cuda", requires_grad=True)
+    model = cb.SGPR((dev(X), dev(Y)), cb.kernels.KERNELS[name](variance=var, lengthscales=ls), dev(Z),
+                    noise_variance=noise)
+    elbo = model.elbo()
+    np.testing.assert_allclose(float(elbo.detach()), oracle(theta0), rtol=1e-9)
+    elbo.backward()
+    got = np.concatenate([[float(var.grad)], cpu(ls.grad), [float(noise.grad)]])
+    np.testing.assert_allclose(got, fd, rtol=2e-5, atol=1e-6 * np.abs(fd).max())
+
+
 def test_adam_on_the_cdgp_elbo_improves_it(cb):
     """The reference's training loop in miniature (optimize.py:198-254): Adam on -ELBO over softplus-transformed
     kernel / likelihood parameters, everything on the device."""
