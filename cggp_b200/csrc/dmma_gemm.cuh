@@ -90,9 +90,21 @@ template <int WMB>  // m8-blocks per warp along rows: 8 (BM = 128) or 4 (BM = 64
 __global__ void __launch_bounds__(256)
 dmma_gemm_nt_kernel(const double* __restrict__ A, int64_t lda, int64_t M, const double* __restrict__ Bm, int64_t ldb,
                     int64_t N, int64_t K, double* __restrict__ C, int64_t ldc, const double* __restrict__ addend,
-                    int64_t ldadd, double scale, const int* __restrict__ active, const int vec16) {
+                    int64_t ldadd, double scale, const int* __restrict__ active, const int vec16, const int64_t k_chunk,
+                    double* __restrict__ partial) {
   if (cg_inactive(active)) return;
   constexpr int BM = WMB * 16;
+  if (gridDim.z > 1) {
+    // split-K: this CTA contracts k in [z * k_chunk, min(K, (z + 1) * k_chunk)) and writes its partial [M, N] tile
+    // set; a fixed-order reduction adds the partials (and the addend) afterwards
+    const int64_t kb = (int64_t)blockIdx.z * k_chunk;
+    A += kb;
+    Bm += kb;
+    K = (K - kb) < k_chunk ? (K - kb) : k_chunk;
+    C = partial + (int64_t)blockIdx.z * M * N;
+    ldc = N;
+    addend = nullptr;
+  }
   extern __shared__ __align__(16) double smem[];
   double* sA = smem;                        // [STAGES][BM][LDS]
   double* sB = smem + STAGES * BM * LDS;    // [STAGES][BN][LDS]
@@ -203,6 +215,19 @@ tile_gemm_nt_kernel(const T* __restrict__ A, int64_t lda, int64_t M, const T* __
   }
 }
 
+__global__ void splitk_reduce_kernel(const double* __restrict__ partial, int splits, int64_t M, int64_t N,
+                                     double* __restrict__ C, int64_t ldc, const double* __restrict__ addend,
+                                     int64_t ldadd, double scale, const int* __restrict__ active) {
+  if (cg_inactive(active)) return;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= M * N) return;
+  const int64_t r = e / N, c = e % N;
+  double v = 0.0;
+  for (int s = 0; s < splits; ++s) v += partial[(int64_t)s * M * N + e];
+  if (addend) v += scale * addend[r * ldadd + c];
+  C[r * ldc + c] = v;
+}
+
 template <typename T>
 int dmma_gemm_nt(cggp_ctx* ctx, const T* A, int64_t lda, int64_t M, const T* Bm, int64_t ldb, int64_t N, int64_t K,
                  T* C, int64_t ldc, const T* addend, int64_t ldadd, T scale, const int* active);
@@ -232,6 +257,24 @@ inline int dmma_gemm_nt<double>(cggp_ctx* ctx, const double* A, int64_t lda, int
   const int BM = small ? 64 : 128;
   const size_t smem = (size_t)STAGES * (BM + BN) * LDS * sizeof(double);
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
+  // split-K when the output tiles alone leave most SMs idle (9..~256 right-hand sides): k chunks of >= 256
+  int64_t k_chunk = K;
+  double* partial = nullptr;
+  {
+    const int64_t tiles = (int64_t)grid.x * grid.y;
+    int64_t splits = tiles * 2 <= ctx->sm_count ? ctx->sm_count / tiles : 1;
+    if (splits > K / 256) splits = K / 256;
+    if (splits > 1) {
+      k_chunk = ((K + splits - 1) / splits + BK - 1) / BK * BK;
+      splits = (K + k_chunk - 1) / k_chunk;
+    }
+    if (splits > 1) {
+      int rc = cggp_ws_reserve(ctx, sizeof(double) * (size_t)splits * (size_t)M * (size_t)N);
+      if (rc) return rc;
+      partial = (double*)ctx->ws;
+      grid.z = (unsigned)splits;
+    }
+  }
   if (small) {
     static bool attr = false;
     if (!attr) {
@@ -240,7 +283,7 @@ inline int dmma_gemm_nt<double>(cggp_ctx* ctx, const double* A, int64_t lda, int
       attr = true;
     }
     dmma_gemm_nt_kernel<4><<<grid, 256, smem, ctx->stream>>>(A, lda, M, Bm, ldb, N, K, C, ldc, addend, ldadd, scale,
-                                                             active, vec16);
+                                                             active, vec16, k_chunk, partial);
   } else {
     static bool attr = false;
     if (!attr) {
@@ -249,8 +292,14 @@ inline int dmma_gemm_nt<double>(cggp_ctx* ctx, const double* A, int64_t lda, int
       attr = true;
     }
     dmma_gemm_nt_kernel<8><<<grid, 256, smem, ctx->stream>>>(A, lda, M, Bm, ldb, N, K, C, ldc, addend, ldadd, scale,
-                                                             active, vec16);
+                                                             active, vec16, k_chunk, partial);
   }
   CGGP_LAUNCH_CHECK(ctx);
+  if (grid.z > 1) {
+    const int64_t total = M * N;
+    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(partial, (int)grid.z, M, N, C, ldc,
+                                                                                  addend, ldadd, scale, active);
+    CGGP_LAUNCH_CHECK(ctx);
+  }
   return CGGP_OK;
 }
