@@ -76,6 +76,7 @@ extern "C" int cggp_ctx_destroy(cggp_ctx* ctx) {
   if (ctx->ws) cudaFree(ctx->ws);
   Ws2& w = ws2_of(ctx);
   if (w.p) { cudaFree(w.p); w.p = nullptr; w.bytes = 0; }
+  if (ctx->exp_tab) cudaFree(ctx->exp_tab);
   if (ctx->cg_state) cudaFree(ctx->cg_state);
   if (ctx->cg_state_host) cudaFreeHost(ctx->cg_state_host);
   for (int s = 0; s < CGGP_PROF_SECTIONS; ++s)
@@ -295,7 +296,8 @@ extern "C" int cggp_kuf_kfu_matvec_tf32(cggp_ctx* ctx, int kind, double variance
   if (!ctx) return CGGP_ERR_INVALID;
   if (B <= 0 || m <= 0) return CGGP_OK;
   if (kind < CGGP_SE || kind > CGGP_MATERN52) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "unknown kernel kind %d", kind);
-  if (nsplit != 1 && nsplit != 3) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "nsplit must be 1 or 3");
+  if (nsplit != 1 && nsplit != 3 && nsplit != 16)
+    CGGP_FAIL(ctx, CGGP_ERR_INVALID, "nsplit must be 1, 3 (TF32) or 16 (3xFP16)");
   ProfScope prof(ctx, 0);
   return cggp_matvec_tf32(ctx, kind, variance, (const float*)Xb, (const float*)Xs, (const float*)xn, n,
                           (const float*)Zb, (const float*)Zs, (const float*)zn, m, D, (const float*)V, ldv, B,

@@ -394,7 +394,7 @@ static int apply_operator(cggp_ctx* ctx, const cggp_operator* op, const void* V,
     rc = cggp_matvec_tf32(ctx, op->kind, op->variance, (const float*)op->dev_X32_big, (const float*)op->dev_X32_small,
                           (const float*)op->dev_x32_norms, op->n_local, (const float*)op->dev_Z32_big,
                           (const float*)op->dev_Z32_small, (const float*)op->dev_z32_norms, n, op->D, (const float*)V,
-                          n, B, (float*)wbuf, n, op->tf32_nsplit == 1 ? 1 : 3, active);
+                          n, B, (float*)wbuf, n, (op->tf32_nsplit == 1 || op->tf32_nsplit == 16) ? op->tf32_nsplit : 3, active);
   } else
     rc = cggp_matvec_dispatch(ctx, op->dtype, op->kind, op->variance, op->dev_PX, op->dev_normsX, op->n_local,
                                 op->dev_PZ, op->dev_normsZ, n, op->D, op->ldp, V, n, B, wbuf, n, op->variant, active);

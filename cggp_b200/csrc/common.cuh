@@ -22,6 +22,7 @@ struct cggp_ctx {
   // device-side CG loop state: [0]=active, [1]=iteration, [2]=ticket
   int* cg_state = nullptr;
   int* cg_state_host = nullptr;  // pinned
+  void* exp_tab = nullptr;  // exp tables of the pipelined matvec (built on first use)
   // NCCL (dlopen'ed)
   void* comm = nullptr;
   int rank = 0, world = 1;

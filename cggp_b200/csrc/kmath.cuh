@@ -96,6 +96,31 @@ __device__ __forceinline__ double fast_sqrt_pos_lean(double u) {
   return g;
 }
 
+// sqrt(u) by ONE third-order step from the MUFU.RSQ64H seed y (relative error 2^-22.9):
+//   g = u y,  r = 1 - g y,  sqrt(u) = g (1 - r)^(-1/2) = g (1 + r/2 + 3 r^2/8 + O(r^3)),  |r|^3 < 2^-65.
+// 2 DMUL + 3 DFMA like the two Newton steps above, but no y/2 is needed (one integer add and one register move
+// less per value on the issue-bound matvec) and the dependency chain is one FP64 instruction shorter.  r is exact
+// for the rounded g (FMA), so the result carries the rounding of g (2^-54 relative after the square root) plus the
+// final rounding: < 1 ulp.  The low word of the seed is left undefined as in fast_sqrt_pos_lean.
+__device__ __forceinline__ double fast_sqrt_pos_cubic(double u) {
+  double y;
+  asm("{\n"
+      ".reg .b32 ulo, uhi, yhi;\n"
+      ".reg .f64 yy;\n"
+      "rsqrt.approx.ftz.f64 yy, %1;\n"
+      "mov.b64 {ulo, yhi}, yy;\n"
+      "mov.b64 {ulo, uhi}, %1;\n"
+      "mov.b64 %0, {ulo, yhi};\n"
+      "}\n"
+      : "=d"(y)
+      : "d"(u));
+  const double g = u * y;
+  const double r = fma(-g, y, 1.0);
+  const double p = fma(r, 0.375, 0.5);
+  const double gr = g * r;
+  return fma(gr, p, g);
+}
+
 // exp(x) for x <= ~0 (any x in [-745, 700] works).  x*32/ln2 = n + f, n = 32 k + j:
 //   exp(x) = 2^k * 2^(j/32) * exp(d),  d = x - n ln2/32,  |d| <= ln2/64
 // 2^(j/32) comes from a 32-entry table held one entry per lane (two SHFLs, no shared memory), exp(d) from a
@@ -214,6 +239,49 @@ __device__ __forceinline__ double fast_exp_neg_core(double a, const FastExpTable
   int lo = __shfl_sync(0xffffffffu, tab.lo, n);
   hi += n << 15;
   return __hiloint2double(hi, lo) * q;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Shared-memory table variant of the clamp-free cores: 2^(j / 2^TBITS) from a table of 2^TBITS entries in shared
+// memory (one LDS.64 instead of two SHFLs), which shortens the polynomial: TBITS = 10 -> degree 3 (2 DFMA less per
+// value than the 32-entry / degree-5 scheme).  Entries are (lo, hi - (j << (20 - TBITS))), so that the 2^k scaling is
+// one integer multiply-add on n = 2^TBITS k + j; the table is built on the host (correctly rounded from long
+// double, matvec_pipe.cu).  Max relative error of the polynomial in exact arithmetic with the double coefficients:
+// 1.37e-16 (the degree-5 / 32-entry scheme: 1.41e-16); tools/fit_exp_poly.py.
+// ---------------------------------------------------------------------------------------------------------
+template <int TBITS>
+struct ExpSmemConst;
+template <>
+struct ExpSmemConst<10> {
+  static constexpr double SCALE = 1477.319721870298529136562873346117549;   // 1024 / ln 2
+  static constexpr double STEP = 6.769015435155715912277655808101410987e-4;  // ln 2 / 1024
+  static __device__ __forceinline__ double poly(double d) {
+    double q = fma(d, 1.66666667859884626e-01, 5.00000003579653907e-01);
+    q = fma(q, d, 1.0);
+    return fma(q, d, 1.0);
+  }
+};
+template <int TBITS>
+__device__ __forceinline__ double fast_exp_core_smem(double x, const int2* tab) {
+  const double MAGIC = 6755399441055744.0;
+  double t = fma(x, ExpSmemConst<TBITS>::SCALE, MAGIC);
+  int n = __double2loint(t);
+  double nf = t - MAGIC;
+  double d = fma(nf, -ExpSmemConst<TBITS>::STEP, x);
+  double q = ExpSmemConst<TBITS>::poly(d);
+  const int2 e = tab[n & ((1 << TBITS) - 1)];
+  return __hiloint2double(e.y + (n << (20 - TBITS)), e.x) * q;
+}
+template <int TBITS>
+__device__ __forceinline__ double fast_exp_neg_core_smem(double a, const int2* tab) {
+  const double MAGIC = 6755399441055744.0;
+  double t = fma(a, -ExpSmemConst<TBITS>::SCALE, MAGIC);
+  int n = __double2loint(t);
+  double nf = t - MAGIC;
+  double d = fma(nf, -ExpSmemConst<TBITS>::STEP, -a);
+  double q = ExpSmemConst<TBITS>::poly(d);
+  const int2 e = tab[n & ((1 << TBITS) - 1)];
+  return __hiloint2double(e.y + (n << (20 - TBITS)), e.x) * q;
 }
 
 // Fast kernel value on r2 (variance is applied by the caller once per row, not per entry).

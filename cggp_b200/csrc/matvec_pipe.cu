@@ -23,7 +23,9 @@
 // in the same order, so all ranks hold bit-identical t.
 #include <cooperative_groups.h>
 
+#include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "kmath.cuh"
@@ -56,6 +58,7 @@ struct Args {
   int dbg;        // timing experiments only (env CGGP_PIPE_DBG; results are WRONG when set): 1 = skip phase 2,
                   // 2 = skip the L2 exchange
   const int* active;
+  const int2* etab;  // exp table of the shared-memory variant (ET = 10: 1024 entries)
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -128,11 +131,13 @@ struct Fam<CGGP_MATERN52> {  // a = sqrt(5) r
 //           q below GPflow's max(r2, 1e-36) land on the lower clamp, q beyond (708 lengthscales)^2 on the upper one
 //           (exp(-708) = 3e-308 instead of an underflowed 0: absolute error 3e-308);
 //   SE:     hi(q) -> min with hi(-708) as UNSIGNED ints (more negative = larger).
-template <int KIND>
-__device__ __forceinline__ double kval(double q, const FastExpTable& tab) {
+template <int KIND, int ET, int SQ = 0>
+__device__ __forceinline__ double kval(double q, const FastExpTable& tab, const int2* etab) {
   if constexpr (KIND == CGGP_SE) {
     const unsigned h = min((unsigned)__double2hiint(q), 0xC0862000u);
-    return fast_exp_core(__hiloint2double((int)h, __double2loint(q)), tab);
+    const double x = __hiloint2double((int)h, __double2loint(q));
+    if constexpr (ET == 0) return fast_exp_core(x, tab);
+    else return fast_exp_core_smem<ET>(x, etab);
   } else {
     // in place on the register pair (the compiler otherwise copies the low word to a fresh pair)
     double qc = q;
@@ -145,8 +150,10 @@ __device__ __forceinline__ double kval(double q, const FastExpTable& tab) {
         "}\n"
         : "+d"(qc)
         : "n"(Fam<KIND>::clamp_hi));
-    const double a = fast_sqrt_pos_lean(qc);
-    const double e = fast_exp_neg_core(a, tab);
+    const double a = SQ == 1 ? fast_sqrt_pos_cubic(qc) : fast_sqrt_pos_lean(qc);
+    double e;
+    if constexpr (ET == 0) e = fast_exp_neg_core(a, tab);
+    else e = fast_exp_neg_core_smem<ET>(a, etab);
     if constexpr (KIND == CGGP_MATERN12) {
       return e;
     } else if constexpr (KIND == CGGP_MATERN32) {
@@ -157,7 +164,7 @@ __device__ __forceinline__ double kval(double q, const FastExpTable& tab) {
   }
 }
 
-template <int WARPS, int RB, int CBW, int NB, int KS, int NBUF>
+template <int WARPS, int RB, int CBW, int NB, int KS, int NBUF, int ET>
 struct Layout {
   static constexpr int THREADS = WARPS * 32;
   static constexpr int BM = RB * 8;
@@ -169,7 +176,9 @@ struct Layout {
   static constexpr size_t xn_bytes = (size_t)XS * BM * sizeof(double);
   static constexpr size_t tred_bytes = (size_t)NBUF * WARPS * BM * NB * sizeof(double);
   static constexpr size_t tfull_bytes = (size_t)NBUF * BM * NB * sizeof(double);
-  static constexpr size_t total = kbuf_bytes + xt_bytes + xn_bytes + tred_bytes + tfull_bytes + (XS + NBUF) * sizeof(uint64_t);
+  static constexpr size_t etab_bytes = ET ? ((size_t)sizeof(int2) << ET) : 0;
+  static constexpr size_t bar_bytes = (XS + NBUF + 1) / 2 * 2 * sizeof(uint64_t);  // keeps the table 16-byte aligned
+  static constexpr size_t total = kbuf_bytes + xt_bytes + xn_bytes + tred_bytes + tfull_bytes + bar_bytes + etab_bytes;
 };
 
 // Hand-offs inside a CTA.  T (named barrier 1 + parity): "the partial t of block j is in tred[j & 1] and X stage
@@ -187,10 +196,10 @@ __device__ __forceinline__ void mbar_arrive(void* bar) {
 }
 constexpr int BAR_T = 1;  // + parity of the block
 
-template <int KIND, int KS, int WARPS, int RB, int CBW, int NB, int NBUF>
+template <int KIND, int KS, int WARPS, int RB, int CBW, int NB, int NBUF, int ET, int SQ>
 __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args a) {
   if (cg_inactive(a.active)) return;
-  using L = Layout<WARPS, RB, CBW, NB, KS, NBUF>;
+  using L = Layout<WARPS, RB, CBW, NB, KS, NBUF, ET>;
   constexpr int LAG = NBUF - 1;  // phase 2 of block j runs after phase 1 of block j + LAG
   constexpr int THREADS = L::THREADS, BM = L::BM, WN = L::WN, BN = L::BN, LDX = L::LDX;
   constexpr int ALL = THREADS + 32;  // compute warps + the exchange warp
@@ -205,6 +214,11 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
   double* tred = reinterpret_cast<double*>(smem_raw + L::kbuf_bytes + L::xt_bytes + L::xn_bytes);  // [2][WARPS][BM*NB]
   double* tfull = tred + NBUF * WARPS * BM * NB;                                                       // [2][BM*NB]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(tfull + NBUF * BM * NB);
+  const int2* etab = reinterpret_cast<const int2*>(reinterpret_cast<unsigned char*>(mbar) + L::bar_bytes);
+  if constexpr (ET != 0) {
+    int2* et = const_cast<int2*>(etab);
+    for (int j = tid; j < (1 << ET); j += ALL) et[j] = a.etab[j];
+  }
 
   const int64_t nit = a.nblocks > g ? (a.nblocks - g + a.G - 1) / a.G : 0;  // row blocks of this group
   auto row0_of = [&](int64_t it) { return (g + it * (int64_t)a.G) * BM; };
@@ -407,8 +421,8 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
       for (int b = 0; b < NB; ++b) tp[b] = 0.0;
 #pragma unroll
       for (int cb = 0; cb < CBW; ++cb) {
-        const double k0 = kval<KIND>(c[cb][0], tab);
-        const double k1 = kval<KIND>(c[cb][1], tab);
+        const double k0 = kval<KIND, ET, SQ>(c[cb][0], tab, etab);
+        const double k1 = kval<KIND, ET, SQ>(c[cb][1], tab, etab);
         kb[(rb * CBW + cb) * THREADS] = make_double2(k0, k1);
 #pragma unroll
         for (int b = 0; b < NB; ++b) tp[b] = fma(k0, vv[cb][b].x, fma(k1, vv[cb][b].y, tp[b]));
@@ -463,11 +477,11 @@ struct Plan {
   size_t smem;
 };
 
-template <int KIND, int KS, int WARPS, int RB, int CBW, int NB, int NBUF>
+template <int KIND, int KS, int WARPS, int RB, int CBW, int NB, int NBUF, int ET = 0, int SQ = 0>
 static Plan make_plan() {
-  using L = Layout<WARPS, RB, CBW, NB, KS, NBUF>;
+  using L = Layout<WARPS, RB, CBW, NB, KS, NBUF, ET>;
   Plan p;
-  p.fn = (const void*)kfu_pipe_kernel<KIND, KS, WARPS, RB, CBW, NB, NBUF>;
+  p.fn = (const void*)kfu_pipe_kernel<KIND, KS, WARPS, RB, CBW, NB, NBUF, ET, SQ>;
   p.threads = L::THREADS + 32;  // + the exchange warp
   p.BM = L::BM;
   p.BN = L::BN;
@@ -479,29 +493,34 @@ static Plan make_plan() {
 // `deep`: three K buffers of 32 rows instead of two of 48, i.e. the group exchange of a block has TWO phase-1 periods
 // to complete.  Pays off when the group is large (M = 16384: 64 CTAs to wait for; 59.7 -> 52.7 ms at N = 1M, D = 2).
 template <int KIND, int KS>
-static bool plan_for_nb(int nb, bool deep, Plan& p) {
+static bool plan_for_nb(int nb, bool deep, int et, Plan& p) {
+  // et = 10 (default for one right-hand side): 1024-entry shared-memory exp table (degree-3 polynomial) + third-order
+  // sqrt step; et = 0: 32-entry shuffle table (degree 5) + two Newton steps.  Measured at c3: 20.58 vs 21.14 ms.
   switch (nb) {
-    case 1: p = deep ? make_plan<KIND, KS, 16, 4, 2, 1, 3>() : make_plan<KIND, KS, 16, 6, 2, 1, 2>(); return true;
+    case 1:
+      if (et == 10) p = deep ? make_plan<KIND, KS, 16, 4, 2, 1, 3, 10, 1>() : make_plan<KIND, KS, 16, 6, 2, 1, 2, 10, 1>();
+      else p = deep ? make_plan<KIND, KS, 16, 4, 2, 1, 3>() : make_plan<KIND, KS, 16, 6, 2, 1, 2>();
+      return true;
     case 2: p = deep ? make_plan<KIND, KS, 16, 3, 2, 2, 3>() : make_plan<KIND, KS, 16, 5, 2, 2, 2>(); return true;
     default: return false;
   }
 }
 template <int KIND>
-static bool plan_for_ks(int ks, int nb, bool deep, Plan& p) {
+static bool plan_for_ks(int ks, int nb, bool deep, int et, Plan& p) {
   switch (ks) {
-    case 1: return plan_for_nb<KIND, 1>(nb, deep, p);
-    case 2: return plan_for_nb<KIND, 2>(nb, deep, p);
-    case 3: return plan_for_nb<KIND, 3>(nb, deep, p);
-    case 4: return plan_for_nb<KIND, 4>(nb, deep, p);
+    case 1: return plan_for_nb<KIND, 1>(nb, deep, et, p);
+    case 2: return plan_for_nb<KIND, 2>(nb, deep, et, p);
+    case 3: return plan_for_nb<KIND, 3>(nb, deep, et, p);
+    case 4: return plan_for_nb<KIND, 4>(nb, deep, et, p);
     default: return false;
   }
 }
-static bool plan_for(int kind, int ks, int nb, bool deep, Plan& p) {
+static bool plan_for(int kind, int ks, int nb, bool deep, int et, Plan& p) {
   switch (kind) {
-    case CGGP_SE: return plan_for_ks<CGGP_SE>(ks, nb, deep, p);
-    case CGGP_MATERN12: return plan_for_ks<CGGP_MATERN12>(ks, nb, deep, p);
-    case CGGP_MATERN32: return plan_for_ks<CGGP_MATERN32>(ks, nb, deep, p);
-    case CGGP_MATERN52: return plan_for_ks<CGGP_MATERN52>(ks, nb, deep, p);
+    case CGGP_SE: return plan_for_ks<CGGP_SE>(ks, nb, deep, et, p);
+    case CGGP_MATERN12: return plan_for_ks<CGGP_MATERN12>(ks, nb, deep, et, p);
+    case CGGP_MATERN32: return plan_for_ks<CGGP_MATERN32>(ks, nb, deep, et, p);
+    case CGGP_MATERN52: return plan_for_ks<CGGP_MATERN52>(ks, nb, deep, et, p);
     default: return false;
   }
 }
@@ -533,6 +552,27 @@ int cggp_kuf_times_pipe(cggp_ctx* ctx, int kind, double variance, const double* 
   return pipe_launch(ctx, kind, variance, PX, nX, n, PZ, nZ, m, D, ldp, nullptr, 0, P, W, ldw, nullptr, Y, ldy);
 }
 
+// 2^(j / 1024), j < 1024, correctly rounded from long double on the host; the high word of entry j is pre-decremented
+// by j << (20 - TBITS) (kmath.cuh).  Built once per ctx.
+static int cggp_exp_tables(cggp_ctx* ctx, const int2** out) {
+  if (!ctx->exp_tab) {
+    std::vector<int2> h(1024);
+    auto fill = [&](int off, int bits) {
+      for (int j = 0; j < (1 << bits); ++j) {
+        const double t = (double)exp2l((long double)j / (long double)(1 << bits));
+        int64_t u;
+        memcpy(&u, &t, 8);
+        h[off + j] = make_int2((int)(u & 0xffffffff), (int)(u >> 32) - (j << (20 - bits)));
+      }
+    };
+    fill(0, 10);
+    CGGP_CUDA(ctx, cudaMalloc(&ctx->exp_tab, h.size() * sizeof(int2)));
+    CGGP_CUDA(ctx, cudaMemcpy(ctx->exp_tab, h.data(), h.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  }
+  *out = (const int2*)ctx->exp_tab;
+  return CGGP_OK;
+}
+
 static int pipe_launch(cggp_ctx* ctx, int kind, double variance, const double* PX, const double* nX, int64_t n,
                        const double* PZ, const double* nZ, int64_t m, int D, int64_t ldp, const double* V, int64_t ldv,
                        int B, double* W, int64_t ldw, const int* active, const double* Tin, int64_t ldt) {
@@ -544,7 +584,9 @@ static int pipe_launch(cggp_ctx* ctx, int kind, double variance, const double* P
     Plan p;
     static const int deep_env = getenv("CGGP_PIPE_DEEP") ? atoi(getenv("CGGP_PIPE_DEEP")) : -1;  // tuning knob
     const bool deep = deep_env >= 0 ? deep_env != 0 : (m > 8192);  // measured: wins at M = 16384, loses at M <= 4096
-    if (!plan_for(kind, ks, nb, deep, p)) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "pipelined matvec: no plan for D=%d", D);
+    static const int et_env = getenv("CGGP_PIPE_ET") ? atoi(getenv("CGGP_PIPE_ET")) : 10;  // tuning knob
+    const int et = (nb == 1 && et_env == 10) ? 10 : 0;
+    if (!plan_for(kind, ks, nb, deep, et, p)) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "pipelined matvec: no plan for D=%d", D);
     CGGP_CUDA(ctx, cudaFuncSetAttribute(p.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     int occ = 0;
     CGGP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p.fn, p.threads, p.smem));
@@ -572,6 +614,11 @@ static int pipe_launch(cggp_ctx* ctx, int kind, double variance, const double* P
     a.counters = (int*)(base + wp_bytes + part_bytes);
     a.C = C; a.G = G; a.nblocks = nblocks; a.active = active;
     a.dbg = getenv("CGGP_PIPE_DBG") ? atoi(getenv("CGGP_PIPE_DBG")) : 0;
+    a.etab = nullptr;
+    if (et == 10) {
+      rc = cggp_exp_tables(ctx, &a.etab);
+      if (rc) return rc;
+    }
     a.tma_ok = (ldp == ks * 4) && (((uintptr_t)PX | (uintptr_t)nX) % 16 == 0) ? 1 : 0;
     CGGP_CUDA(ctx, cudaMemsetAsync(a.counters, 0, cnt_bytes, ctx->stream));
     void* kargs[] = {(void*)&a};

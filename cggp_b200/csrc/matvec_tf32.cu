@@ -19,6 +19,9 @@
 //   The product is two such sweeps:  T = gram(X, Z, V)  then  W = gram(Z, X, T)  (roles swapped, X split over
 //   grid.y with a fixed-order reduction), i.e. every Gram entry is evaluated twice - parking a 128 x 128 FP32 tile per
 //   block would be the next step, as matvec_pipe.cu does for float64.
+#include <cuda_fp16.h>
+
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -83,6 +86,18 @@ __device__ __forceinline__ void umma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, u
       "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16 (FP16 inputs, FP32 accumulate) with the A operand in tensor memory: two halfs per 32-bit TMEM column
+__device__ __forceinline__ void umma_f16_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]),
                "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
@@ -122,9 +137,17 @@ __host__ __device__ inline int64_t canon_off(int64_t r, int k, int KP) {
   const int64_t chunk = (r >> 7) * (KP >> 5) + (k >> 5);
   return chunk * 4096 + ((((r & 127) >> 3) * 8 + ((k & 31) >> 2)) * 32) + (r & 7) * 4 + (k & 3);
 }
+// same for the FP16 arrays (offset in halfs): core matrices are 8 rows x 8 halfs (16 bytes per row), a 128-row x
+// 32-feature chunk is 8 KB: [(r % 128) / 8][(k % 32) / 8][r % 8][k % 8] (LBO = 128 B, SBO = 512 B)
+__host__ __device__ inline int64_t canon_off_h(int64_t r, int k, int KP) {
+  const int64_t chunk = (r >> 7) * (KP >> 5) + (k >> 5);
+  return chunk * 4096 + ((((r & 127) >> 3) * 4 + ((k & 31) >> 3)) * 64) + (r & 7) * 8 + (k & 7);
+}
 constexpr int CHUNK_FLOATS = 4096;                      // 128 rows x 32 features
 constexpr unsigned CHUNK_BYTES = CHUNK_FLOATS * 4;      // 16 KB
+constexpr unsigned CHUNK_BYTES_H = 4096 * 2;            // the same chunk in FP16: 8 KB
 constexpr int MAX_STAGES = 8;
+constexpr int F16X3 = 16;                               // `nsplit` code of the 3xFP16 mode
 
 // ---------------------------------------------------------------------------------------------------------
 // one-time conversion of prepared points into the canonical TF32 big / small arrays (rows padded to 128)
@@ -148,6 +171,52 @@ __global__ void prepare_kernel(const float* __restrict__ P, const float* __restr
   const int64_t o = canon_off(r, k, KP);
   big[o] = b;
   small[o] = s;
+}
+
+// 3xFP16 mode: the tensor cores run FP16 inputs (FP32 accumulate) at twice the TF32 rate, and FP16 carries the same
+// 11 significant bits as TF32 - what it lacks is exponent range, which a per-row power-of-two scale restores:
+//   xs = x 2^s (row maximum in [2^14, 2^15)),  H = fp16(xs),  rem = xs - H  (exact, |rem| <= 2^-11 |xs|)
+//   row role (tile resident in tensor memory):  H, L' = fp16(rem), H' = fp16(H 2^-11)
+//   column role (streamed through shared memory): H, L = fp16(rem 2^11)      - only TWO arrays travel per tile
+//   x.z 2^(sx + sz) = sum H_x H_z + L'_x H_z + H'_x L_z   (+ the dropped rem_x rem_z term, 2^-22, as in 3xTF32)
+// (values 2^-17 below their row maximum lose bits of L' / H' to FP16 subnormals: an absolute error of 2^-40 of the
+// row-norm product).  One warp per row: row maximum -> scale, then the four arrays in the canonical FP16 order;
+// 1 / 2^s goes to `rinv`.
+__global__ void prepare_f16_kernel(const float* __restrict__ P, const float* __restrict__ norms, int64_t n, int D,
+                                   int64_t ldp, int KP, int64_t n_pad, __half* __restrict__ H, __half* __restrict__ L,
+                                   __half* __restrict__ Lp, __half* __restrict__ Hp, float* __restrict__ rinv,
+                                   float* __restrict__ norms_pad) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n_pad) return;
+  float mx = 0.f;
+  if (r < n)
+    for (int k = lane; k < D; k += 32) mx = fmaxf(mx, fabsf(P[r * ldp + k]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  int s = 0;
+  if (mx > 0.f && mx < 3.0e38f) {
+    int e;
+    frexpf(mx, &e);  // mx = f 2^e, f in [0.5, 1)  ->  mx 2^(15 - e) in [2^14, 2^15)
+    s = 15 - e;
+    s = s > 100 ? 100 : (s < -100 ? -100 : s);
+  }
+  const float up = exp2f((float)s);
+  if (lane == 0) {
+    rinv[r] = exp2f((float)-s);
+    norms_pad[r] = r < n ? norms[r] : 0.f;
+  }
+  for (int k = lane; k < KP; k += 32) {
+    float x = 0.f;
+    if (r < n && k < D) x = P[r * ldp + k] * up;
+    const __half h = __float2half_rn(x);
+    const float rem = x - __half2float(h);
+    const int64_t o = canon_off_h(r, k, KP);
+    H[o] = h;
+    L[o] = __float2half_rn(rem * 2048.f);
+    Lp[o] = __float2half_rn(rem);
+    Hp[o] = __float2half_rn(__half2float(h) * (1.f / 2048.f));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -194,20 +263,27 @@ struct Args {
   int64_t ldo;
   int64_t q_tiles_per_split;
   float variance;
+  int64_t np_pad, nq_pad;  // rows padded to 128 (3xFP16: offsets of the L array and of the row scales)
   int stages;        // Q chunk ring depth (what fits next to the resident P tile)
+  int dbg;           // timing experiments only (env CGGP_TF32_DBG; results are WRONG when set): 1 = no epilogue math,
+                     // 2 = no MMAs, 4 = no TMA copies, 8 = no global loads of the column scalars, 16 = no tcgen05.ld
+  long long* stamps;  // timing experiments: [4 roles][128] clock64 stamps of CTA (0, 0) at tile boundaries, or NULL
   const int* active;
 };
 
 template <int KIND, int NSPLIT, int NB>
 __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, const int KP) {
   if (cg_inactive(a.active)) return;
-  constexpr int PARTS = NSPLIT > 1 ? 2 : 1;
+  constexpr bool F16 = NSPLIT == F16X3;
+  constexpr int PARTS = NSPLIT > 1 ? 2 : 1;  // arrays of the column set that travel through shared memory
+  constexpr unsigned CHB = F16 ? CHUNK_BYTES_H : CHUNK_BYTES;  // bytes of one part of one K chunk
+  constexpr int AUXR = (F16 ? 2 : 1) + NB;                     // per-column scalars: |q|^2 term, (scale,) weights
   constexpr int BN = 128;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nchunk = KP >> 5;
   const int STAGES = a.stages;
-  float* sQ = reinterpret_cast<float*>(smem_raw);                       // [STAGES][PARTS][4096]
-  float* aux = sQ + (size_t)STAGES * PARTS * CHUNK_FLOATS;              // [2][(1 + NB) * BN]
+  unsigned char* sQ = smem_raw;                                          // [STAGES][PARTS][CHB bytes]
+  float* aux = reinterpret_cast<float*>(sQ + (size_t)STAGES * PARTS * CHB);  // [2][AUXR * BN]
   // TMEM: columns [0, 256) two accumulators; [256, 256 + PARTS * KP) the P tile as the A operand (row = lane)
   constexpr uint32_t TM_P = 256;
   __shared__ uint64_t bar_p, bar_qfull[MAX_STAGES], bar_qfree[MAX_STAGES], bar_full[2], bar_empty[2], bar_aux[2];
@@ -223,14 +299,14 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
   if (njt < 0) njt = 0;
 
   if (tid == 0) {
-    mbar_init(&bar_p, 256);
+    mbar_init(&bar_p, 8);  // one elected lane per epilogue warp arrives (256 arrivals on one mbarrier serialise)
     for (int b = 0; b < MAX_STAGES; ++b) {
       mbar_init(&bar_qfull[b], 1);
       mbar_init(&bar_qfree[b], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bar_full[b], 1);
-      mbar_init(&bar_empty[b], 256);
+      mbar_init(&bar_empty[b], 8);
       mbar_init(&bar_aux[b], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -253,12 +329,24 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
         for (int c = 0; c < nchunk; ++c, ++g) {
           const int s = (int)(g % STAGES);
           if (g >= STAGES) mbar_wait(&bar_qfree[s], (unsigned)(((g / STAGES) - 1) & 1));  // MMAs done with this stage
-          float* dst = sQ + (size_t)s * PARTS * CHUNK_FLOATS;
-          const int64_t src = (q0 >> 7) * (int64_t)nchunk * CHUNK_FLOATS + (int64_t)c * CHUNK_FLOATS;
-          mbar_expect_tx(&bar_qfull[s], PARTS * CHUNK_BYTES);
-          tma_bulk_g2s(dst, a.Qb + src, CHUNK_BYTES, &bar_qfull[s]);
-          if (PARTS > 1) tma_bulk_g2s(dst + CHUNK_FLOATS, a.Qs + src, CHUNK_BYTES, &bar_qfull[s]);
+          unsigned char* dst = sQ + (size_t)s * PARTS * CHB;
+          const int64_t src = (q0 >> 7) * (int64_t)nchunk * CHUNK_FLOATS + (int64_t)c * CHUNK_FLOATS;  // elements
+          if (a.dbg & 4) {
+            mbar_arrive(&bar_qfull[s]);
+            continue;
+          }
+          mbar_expect_tx(&bar_qfull[s], PARTS * CHB);
+          if constexpr (F16) {
+            const __half* QH = reinterpret_cast<const __half*>(a.Qb);
+            const __half* QL = QH + a.nq_pad * KP;
+            tma_bulk_g2s(dst, QH + src, CHB, &bar_qfull[s]);
+            tma_bulk_g2s(dst + CHB, QL + src, CHB, &bar_qfull[s]);
+          } else {
+            tma_bulk_g2s(dst, a.Qb + src, CHB, &bar_qfull[s]);
+            if (PARTS > 1) tma_bulk_g2s(dst + CHB, a.Qs + src, CHB, &bar_qfull[s]);
+          }
         }
+        if (a.stamps && blockIdx.x == 0 && blockIdx.y == 0 && j < 128) a.stamps[j] = clock64();
       }
     }
     __syncwarp();
@@ -269,29 +357,42 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
     for (int64_t j = 0; j < njt; ++j) {
       const int buf = (int)(j & 1);
       const int64_t q0 = (jt0 + j) * BN;
-      float vals[BN / 32][1 + NB];
+      float vals[BN / 32][AUXR];
+      constexpr int UO = AUXR - NB;  // first weight row
 #pragma unroll
       for (int i = 0; i < BN / 32; ++i) {
         const int64_t q = q0 + i * 32 + lane;
-        vals[i][0] = KIND == CGGP_SE ? -HALF_LOG2E * a.qn[q] : a.qn[q];  // padded array
+        if (a.dbg & 8) {
 #pragma unroll
-        for (int b = 0; b < NB; ++b) vals[i][1 + b] = q < a.nq ? a.U[(int64_t)b * a.ldu + q] : 0.f;
+          for (int b = 0; b < AUXR; ++b) vals[i][b] = 0.f;
+          continue;
+        }
+        vals[i][0] = KIND == CGGP_SE ? -HALF_LOG2E * a.qn[q] : a.qn[q];  // padded array
+        if constexpr (F16) {
+          // the column's share of the accumulator scale, folded with the constant the kernel family multiplies by
+          const float rq = (a.Qs + a.nq_pad * KP)[q];
+          vals[i][1] = (KIND == CGGP_SE ? 2.f * HALF_LOG2E : -2.f) * rq;
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) vals[i][UO + b] = q < a.nq ? a.U[(int64_t)b * a.ldu + q] : 0.f;
       }
       if (j >= 2) mbar_wait(&bar_empty[buf], (unsigned)(((j >> 1) - 1) & 1));  // epilogue of tile j-2 left aux[buf]
-      float* ax = aux + buf * (1 + NB) * BN;
+      float* ax = aux + buf * AUXR * BN;
 #pragma unroll
       for (int i = 0; i < BN / 32; ++i)
 #pragma unroll
-        for (int b = 0; b < 1 + NB; ++b) ax[b * BN + i * 32 + lane] = vals[i][b];
+        for (int b = 0; b < AUXR; ++b) ax[b * BN + i * 32 + lane] = vals[i][b];
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_aux[buf]);
+      if (a.stamps && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && j < 128) a.stamps[128 + j] = clock64();
     }
   } else if (warp == 9) {
     // =============================== MMA issuer warp ===============================
     if (lane == 0 && njt > 0) {
-      const unsigned lbo = 128, sbo = 1024;
-      const uint32_t idesc =
-          (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const unsigned lbo = 128, sbo = F16 ? 512 : 1024;
+      // instruction descriptor: FP32 accumulate, A / B format TF32 (2) resp. F16 (0), K-major, N, M
+      const uint32_t idesc = (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       mbar_wait(&bar_p, 0);  // the epilogue warps have stored the P tile into tensor memory
       asm volatile("tcgen05.fence::after_thread_sync;");
       int64_t g = 0;
@@ -304,8 +405,31 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
           const int s = (int)(g % STAGES);
           mbar_wait(&bar_qfull[s], (unsigned)((g / STAGES) & 1));
           asm volatile("tcgen05.fence::after_thread_sync;");
+          const unsigned qb = smem_u32(sQ) + (unsigned)s * PARTS * CHB, qs = qb + CHB;
+          if (a.dbg & 2) {
+            umma_commit(&bar_qfree[s]);
+            continue;
+          }
+          if constexpr (F16) {
+            // A operand: H at TMEM columns [TM_P, + KP / 2), L' and H' behind it (two features per column); a K = 16
+            // step is 8 columns of A and two 128-byte core matrices of B; stage order: H | L
+            const uint32_t ph = tmem_base + TM_P + (uint32_t)c * 16, pl = ph + (uint32_t)(KP / 2),
+                           php = pl + (uint32_t)(KP / 2);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {  // D (+)= H_p H_q^T
+              umma_f16_ta(d, ph + k * 8, smem_desc(qb + k * 256, lbo, sbo), idesc, acc);
+              acc = 1;
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k)  // + L'_p H_q^T
+              umma_f16_ta(d, pl + k * 8, smem_desc(qb + k * 256, lbo, sbo), idesc, 1);
+#pragma unroll
+            for (int k = 0; k < 2; ++k)  // + H'_p L_q^T
+              umma_f16_ta(d, php + k * 8, smem_desc(qs + k * 256, lbo, sbo), idesc, 1);
+            umma_commit(&bar_qfree[s]);
+            continue;
+          }
           const uint32_t pb = tmem_base + TM_P + (uint32_t)c * 32, ps = pb + (uint32_t)KP;  // A operand: TMEM columns
-          const unsigned qb = smem_u32(sQ) + (unsigned)s * PARTS * CHUNK_BYTES, qs = qb + CHUNK_BYTES;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // D (+)= Pb Qb^T
             umma_tf32_ta(d, pb + k * 8, smem_desc(qb + k * 256, lbo, sbo), idesc, acc);
@@ -322,6 +446,7 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
           umma_commit(&bar_qfree[s]);  // the stage may be refilled once these MMAs are done
         }
         umma_commit(&bar_full[buf]);  // accumulator ready for the epilogue
+        if (a.stamps && blockIdx.x == 0 && blockIdx.y == 0 && j < 128) a.stamps[256 + j] = clock64();
       }
     }
     __syncwarp();
@@ -333,11 +458,26 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
     const int64_t p = p0 + row;
     const float pn = a.pn[p];  // padded array
     const float cp = -HALF_LOG2E * pn;
+    float rp = 1.f;            // 3xFP16: this row's share of the accumulator scale
+    if constexpr (F16) rp = (a.Ps + a.np_pad * KP)[p];
     if (njt > 0) {
       // P tile -> tensor memory (A operand of every MMA of this CTA): thread = row = TMEM lane; the two column halves
       // of the epilogue split the features.  Halves the shared-memory operand traffic of the MMAs (only Q is read
       // from shared memory) and frees 96 KB for a deeper Q ring.
       const int kper = KP / 2;  // KP is a multiple of 32
+      if constexpr (F16) {
+        const __half* PH = reinterpret_cast<const __half*>(a.Pb);
+        const __half* PLp = reinterpret_cast<const __half*>(a.Ps);
+        for (int part = 0; part < 3; ++part) {
+          const __half* src = part == 0 ? PH : (part == 1 ? PLp : PLp + a.np_pad * KP);
+          for (int k0 = half * kper; k0 < (half + 1) * kper; k0 += 16) {
+            const uint4 x0 = *reinterpret_cast<const uint4*>(src + canon_off_h(p, k0, KP));
+            const uint4 x1 = *reinterpret_cast<const uint4*>(src + canon_off_h(p, k0 + 8, KP));
+            const uint32_t v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            tmem_st8(tmem_base + ((uint32_t)(quarter * 32) << 16) + TM_P + (uint32_t)(part * (KP / 2) + k0 / 2), v);
+          }
+        }
+      } else
       for (int part = 0; part < PARTS; ++part) {
         const float* src = part == 0 ? a.Pb : a.Ps;
         for (int k0 = half * kper; k0 < (half + 1) * kper; k0 += 8) {
@@ -351,7 +491,8 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;");
-      mbar_arrive(&bar_p);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p);
     }
     float acc[NB];
 #pragma unroll
@@ -361,17 +502,25 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
       mbar_wait(&bar_aux[buf], (unsigned)((j >> 1) & 1));
       mbar_wait(&bar_full[buf], (unsigned)((j >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;");
-      const float* ax = aux + buf * (1 + NB) * BN + half * 64;
+      const float* ax = aux + buf * AUXR * BN + half * 64;
+      constexpr int UO = AUXR - NB;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + half * 64);
       uint32_t v[2][32];
-      tmem_ld32_nowait(taddr, v[0]);
-      tmem_ld32_nowait(taddr + 32, v[1]);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (!(a.dbg & 16)) {
+        tmem_ld32_nowait(taddr, v[0]);
+        tmem_ld32_nowait(taddr + 32, v[1]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+        v[0][0] = v[1][31] = 0;
+      }
       // the accumulator is in registers: hand the TMEM buffer back before the math
       asm volatile("tcgen05.fence::before_thread_sync;");
       float part[NB];
 #pragma unroll
       for (int b = 0; b < NB; ++b) part[b] = 0.f;
+      if (a.dbg & 1) {
+        part[0] = __uint_as_float(v[0][0] ^ v[1][31]);
+      } else
 #pragma unroll
       for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -379,13 +528,22 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
           const float4 qv = *reinterpret_cast<const float4*>(ax + h * 32 + c4);
           float4 uv[NB];
 #pragma unroll
-          for (int b = 0; b < NB; ++b) uv[b] = *reinterpret_cast<const float4*>(ax + (1 + b) * BN + h * 32 + c4);
+          for (int b = 0; b < NB; ++b) uv[b] = *reinterpret_cast<const float4*>(ax + (UO + b) * BN + h * 32 + c4);
           const float qs[4] = {qv.x, qv.y, qv.z, qv.w};
+          float aq[4] = {0.f, 0.f, 0.f, 0.f};
+          if constexpr (F16) {
+            const float4 av = *reinterpret_cast<const float4*>(ax + BN + h * 32 + c4);
+            aq[0] = av.x; aq[1] = av.y; aq[2] = av.z; aq[3] = av.w;
+          }
           float kv[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float d = __uint_as_float(v[h][c4 + i]);
-            if constexpr (KIND == CGGP_SE) {
+            if constexpr (F16) {
+              // accumulator = 2^(sp + sq) p.q; aq carries 2^-sq and the family's factor on the cross term
+              if constexpr (KIND == CGGP_SE) kv[i] = ex2_approx(fmaf(d * aq[i], rp, cp + qs[i]));
+              else kv[i] = kval32<KIND>(fmaf(d * aq[i], rp, pn + qs[i]));
+            } else if constexpr (KIND == CGGP_SE) {
               // exp(-r2 / 2) with r2 = |p|^2 + |q|^2 - 2 p.q: one FADD + one FFMA + MUFU.EX2
               kv[i] = ex2_approx(fmaf(2.f * HALF_LOG2E, d, cp + qs[i]));
             } else {
@@ -400,7 +558,9 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
             part[b] = fmaf(kv[3], uv[b].w, part[b]);
           }
         }
-      mbar_arrive(&bar_empty[buf]);  // (aux[buf] has been read as well)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_empty[buf]);  // the warp has read its accumulator slice and aux[buf]
+      if (a.stamps && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && j < 128) a.stamps[384 + j] = clock64();
 #pragma unroll
       for (int b = 0; b < NB; ++b) acc[b] += part[b];
     }
@@ -438,7 +598,7 @@ static KernelFn pick_nb(int nb) {
 }
 template <int KIND>
 static KernelFn pick_split(int nsplit, int nb) {
-  return nsplit > 1 ? pick_nb<KIND, 3>(nb) : pick_nb<KIND, 1>(nb);
+  return nsplit == F16X3 ? pick_nb<KIND, F16X3>(nb) : (nsplit > 1 ? pick_nb<KIND, 3>(nb) : pick_nb<KIND, 1>(nb));
 }
 static KernelFn pick(int kind, int nsplit, int nb) {
   switch (kind) {
@@ -451,18 +611,24 @@ static KernelFn pick(int kind, int nsplit, int nb) {
 
 constexpr size_t SMEM_BUDGET = 227 * 1024 - 1024;  // leave room for the static barriers
 // ring depth that fits next to the resident P tile (0 = does not fit)
+static size_t stage_bytes(int nsplit) {
+  return nsplit == F16X3 ? 2 * (size_t)CHUNK_BYTES_H : (nsplit > 1 ? 2 : 1) * (size_t)CHUNK_BYTES;
+}
+static size_t aux_bytes(int nsplit, int nb) {
+  return (size_t)2 * ((nsplit == F16X3 ? 2 : 1) + nb) * 128 * sizeof(float) + 128;
+}
 static int stages_for(int KP, int nsplit, int nb) {
-  const size_t parts = nsplit > 1 ? 2 : 1;
-  if (parts * (size_t)KP > 256) return 0;  // the P tile must fit in the 256 tensor-memory columns next to the accumulators
-  const size_t fixed = (size_t)2 * (1 + nb) * 128 * sizeof(float) + 128;
+  // the P tile must fit in the 256 tensor-memory columns next to the accumulators (FP16: two features per column)
+  const size_t pcols = nsplit == F16X3 ? 3 * (size_t)KP / 2 : (nsplit > 1 ? 2 : 1) * (size_t)KP;
+  if (pcols > 256) return 0;
+  const size_t fixed = aux_bytes(nsplit, nb);
   if (fixed >= SMEM_BUDGET) return 0;
-  size_t st = (SMEM_BUDGET - fixed) / (parts * CHUNK_BYTES);
+  size_t st = (SMEM_BUDGET - fixed) / stage_bytes(nsplit);
   if (st > MAX_STAGES) st = MAX_STAGES;
   return st >= 2 ? (int)st : 0;
 }
 static size_t smem_bytes(int KP, int nsplit, int nb, int stages) {
-  const size_t parts = nsplit > 1 ? 2 : 1;
-  return parts * (size_t)stages * CHUNK_BYTES + (size_t)2 * (1 + nb) * 128 * sizeof(float) + 128;
+  return (size_t)stages * stage_bytes(nsplit) + aux_bytes(nsplit, nb);
 }
 }  // namespace tf32
 
@@ -483,6 +649,26 @@ extern "C" int cggp_tf32_prepare(cggp_ctx* ctx, const void* P, const void* norms
   return CGGP_OK;
 }
 
+// 3xFP16 arrays in the buffers cggp_tf32_prepare fills, with `small` longer by the row scales (every entry point
+// below stays as it is; pass nsplit = 16 to the products):  big = [H | L] (2 x rows x KP halfs, the column role),
+// small = [L' | H' (2 x rows x KP halfs, the row role) | 1 / row scale (rows floats)]
+extern "C" int cggp_f16x3_prepare(cggp_ctx* ctx, const void* P, const void* norms, int64_t n, int D, int64_t ldp,
+                                  void* big, void* small, void* norms_pad) {
+  if (!ctx) return CGGP_ERR_INVALID;
+  if (D < 1 || n < 0) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "bad shape");
+  const int KP = cggp_tf32_kp(D);
+  const int64_t n_pad = cggp_tf32_rows(n);
+  if (n_pad == 0) return CGGP_OK;
+  __half* H = (__half*)big;
+  __half* Lp = (__half*)small;
+  float* rinv = (float*)small + n_pad * KP;
+  const int warps = 8;
+  tf32::prepare_f16_kernel<<<(unsigned)((n_pad + warps - 1) / warps), warps * 32, 0, ctx->stream>>>(
+      (const float*)P, (const float*)norms, n, D, ldp, KP, n_pad, H, H + n_pad * KP, Lp, Lp + n_pad * KP, rinv, (float*)norms_pad);
+  CGGP_LAUNCH_CHECK(ctx);
+  return CGGP_OK;
+}
+
 extern "C" int cggp_tf32_supported(cggp_ctx* ctx, int D, int nsplit);
 bool cggp_matvec_tf32_supported(cggp_ctx* ctx, int D, int nsplit) {
   const int KP = cggp_tf32_kp(D);
@@ -490,7 +676,7 @@ bool cggp_matvec_tf32_supported(cggp_ctx* ctx, int D, int nsplit) {
 }
 
 extern "C" int cggp_tf32_supported(cggp_ctx* ctx, int D, int nsplit) {
-  if (!ctx || D < 1 || (nsplit != 1 && nsplit != 3)) return 0;
+  if (!ctx || D < 1 || (nsplit != 1 && nsplit != 3 && nsplit != tf32::F16X3)) return 0;
   return cggp_matvec_tf32_supported(ctx, D, nsplit) ? 1 : 0;
 }
 
@@ -530,12 +716,42 @@ static int gram_sweep(cggp_ctx* ctx, int kind, double variance, int nsplit, int 
     a.U = U + (int64_t)b0 * ldu; a.ldu = ldu;
     a.out = splits == 1 ? out + (int64_t)b0 * ldo : scratch;
     a.ldo = splits == 1 ? ldo : np;
+    a.np_pad = (np + BM - 1) / BM * BM;
+    a.nq_pad = (nq + BN - 1) / BN * BN;
     a.q_tiles_per_split = tiles_per_split;
     a.variance = (float)variance;
     a.stages = stages;
+    a.dbg = getenv("CGGP_TF32_DBG") ? atoi(getenv("CGGP_TF32_DBG")) : 0;
+    a.stamps = nullptr;
+    if (getenv("CGGP_TF32_STAMPS")) {
+      static long long* dev_stamps = nullptr;
+      if (!dev_stamps) cudaMalloc(&dev_stamps, 512 * sizeof(long long));
+      cudaMemsetAsync(dev_stamps, 0, 512 * sizeof(long long), ctx->stream);
+      a.stamps = dev_stamps;
+    }
     a.active = active;
     fn<<<dim3((unsigned)p_blocks, (unsigned)splits), 352, smem, ctx->stream>>>(a, KP);
     CGGP_LAUNCH_CHECK(ctx);
+    if (a.stamps) {
+      static int dumped = 0;
+      if (dumped < 2) {
+        ++dumped;
+        long long h[512];
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(h, a.stamps, sizeof(h), cudaMemcpyDeviceToHost);
+        const char* names[4] = {"tma", "aux", "mma", "epi"};
+        long long t0 = h[0];
+        for (int r = 0; r < 4; ++r)
+          for (int j = 0; j < 128; ++j)
+            if (h[r * 128 + j] && h[r * 128 + j] < t0) t0 = h[r * 128 + j];
+        for (int r = 0; r < 4; ++r) {
+          printf("stamps %s:", names[r]);
+          for (int j = 0; j < 40; ++j) printf(" %lld", h[r * 128 + j] ? h[r * 128 + j] - t0 : -1);
+          printf("\n");
+        }
+        fflush(stdout);
+      }
+    }
     if (splits > 1) {
       reduce_splits_kernel<<<dim3((unsigned)((np + 255) / 256), (unsigned)nb), 256, 0, ctx->stream>>>(
           scratch, (int)splits, nb, np, np, out + (int64_t)b0 * ldo, ldo, active);
@@ -592,7 +808,8 @@ extern "C" int cggp_kuf_times_tf32(cggp_ctx* ctx, int kind, double variance, con
   if (!ctx) return CGGP_ERR_INVALID;
   if (P <= 0 || m <= 0) return CGGP_OK;
   if (kind < CGGP_SE || kind > CGGP_MATERN52) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "unknown kernel kind %d", kind);
-  if (nsplit != 1 && nsplit != 3) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "nsplit must be 1 or 3");
+  if (nsplit != 1 && nsplit != 3 && nsplit != tf32::F16X3)
+    CGGP_FAIL(ctx, CGGP_ERR_INVALID, "nsplit must be 1, 3 (TF32) or 16 (3xFP16)");
   if (!cggp_matvec_tf32_supported(ctx, D, nsplit))
     CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "tcgen05 TF32 path: D=%d with nsplit=%d does not fit shared memory", D, nsplit);
   if (n == 0) {

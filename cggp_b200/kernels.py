@@ -66,7 +66,9 @@ class TF32Points:
     D: int
 
 
-def prepare_tf32(points: PreparedPoints) -> TF32Points:
+def prepare_tf32(points: PreparedPoints, nsplit: int = 3) -> TF32Points:
+    """Tensor-core operand arrays of prepared float32 points: TF32 big / small (``nsplit`` 1 or 3) or the 3xFP16
+    arrays (``nsplit`` 16), in the same buffers."""
     if points.P.dtype != torch.float32:
         raise TypeError("the TF32 tensor-core path is for float32 points")
     ctx = _lib.context(points.P.device)
@@ -75,11 +77,12 @@ def prepare_tf32(points: PreparedPoints) -> TF32Points:
     rows = int(ctx.lib.cggp_tf32_rows(points.n))
     dev = points.P.device
     big = torch.empty((rows * kp,), dtype=torch.float32, device=dev)
-    small = torch.empty((rows * kp,), dtype=torch.float32, device=dev)
+    small = torch.empty((rows * kp + (rows if int(nsplit) == 16 else 0),), dtype=torch.float32, device=dev)
     norms = torch.empty((rows,), dtype=torch.float32, device=dev)
     P = points.P if points.P.stride(1) == 1 else points.P.contiguous()
-    ctx.check(ctx.lib.cggp_tf32_prepare(ctx.handle, _lib.ptr(P), _lib.ptr(points.norms.contiguous()), points.n,
-                                        points.D, P.stride(0), _lib.ptr(big), _lib.ptr(small), _lib.ptr(norms)))
+    fn = ctx.lib.cggp_f16x3_prepare if int(nsplit) == 16 else ctx.lib.cggp_tf32_prepare
+    ctx.check(fn(ctx.handle, _lib.ptr(P), _lib.ptr(points.norms.contiguous()), points.n,
+                 points.D, P.stride(0), _lib.ptr(big), _lib.ptr(small), _lib.ptr(norms)))
     return TF32Points(big, small, norms, points.n, points.D)
 
 

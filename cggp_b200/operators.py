@@ -66,7 +66,9 @@ class SGPROperator(LinearOperator):
     def __init__(self, kernel: Stationary, X, Z, noise_variance: float, jitter: float = 1e-6, variant: int = 0,
                  tf32_nsplit: int = 3):
         """``variant``: 0 auto, 1 two-sweep kernels, 2 / 3 float64 fused kernels, 4 float32 tensor-core (tcgen05 TF32)
-        kernels - the default for float32 on sm_100 where the tiles fit (D <= 104 with ``tf32_nsplit = 3``)."""
+        kernels - the default for float32 on sm_100 where the tiles fit (D <= 104 with ``tf32_nsplit = 3``).
+        ``tf32_nsplit``: 3 = 3xTF32, 1 = one TF32 pass (fast, ~1e-3 on the distances), 16 = 3xFP16 (float32-accurate
+        like 3xTF32 at twice the tensor-core rate; per-row power-of-two scaling, ``cggp_f16x3_prepare``)."""
         self.kernel = kernel
         self.PZ = kernel.prepare(Z)
         self.PX = kernel.prepare(X, self.PZ.P.dtype)
@@ -82,7 +84,8 @@ class SGPROperator(LinearOperator):
         if self.dtype == torch.float32 and self.variant in (0, 4):
             ctx = _lib.context(self.device)
             if ctx.lib.cggp_tf32_supported(ctx.handle, self.PZ.D, self.tf32_nsplit):
-                self.X32, self.Z32 = prepare_tf32(self.PX), prepare_tf32(self.PZ)
+                self.X32 = prepare_tf32(self.PX, self.tf32_nsplit)
+                self.Z32 = prepare_tf32(self.PZ, self.tf32_nsplit)
             elif self.variant == 4:
                 raise _lib.CggpError("the tcgen05 TF32 path needs sm_100 and D <= 128 (3xTF32) / 256 (1xTF32)")
 

@@ -134,14 +134,20 @@ int cggp_kuf_kfu_matvec(cggp_ctx* ctx, int dtype, int kind, double variance,
  * a TF32 "big" and a TF32 "small" part (x = big + small to 2^-22), plus the norms padded with zeros.  Buffers:
  * big, small: rows_pad * KP floats each; norms_pad: rows_pad floats.
  * cggp_kuf_kfu_matvec_tf32: W[B, m] = V[B, m] @ (Kuf Kfu) from those arrays; nsplit = 3 -> 3xTF32 (float32-accurate
- * distances), nsplit = 1 -> single TF32 pass (3x fewer tensor-core flops, ~1e-3 relative on the distances). */
+ * distances), nsplit = 1 -> single TF32 pass (3x fewer tensor-core flops, ~1e-3 relative on the distances),
+ * nsplit = 16 -> 3xFP16: the arrays must come from cggp_f16x3_prepare (same buffers, dev_small longer by rows_pad
+ * floats): FP16 carries the same 11 significant bits as TF32 at twice the tensor-core rate; a per-row power-of-two
+ * scale supplies the exponent range, x 2^s = H + rem, x.z 2^(sx+sz) = H.H + L'.H + H'.L with L' = fp16(rem),
+ * L = fp16(rem 2^11), H' = H 2^-11 (kind::f16, FP32 accumulate); only H and L of the streamed point set travel. */
 int cggp_tf32_kp(int D);
 int64_t cggp_tf32_rows(int64_t n);
 /* 1 if the device is sm_100+ and the row tile fits in tensor memory next to the two accumulators
- * (D <= 128 for nsplit = 3, D <= 256 for nsplit = 1), else 0 */
+ * (D <= 128 for nsplit = 3, D <= 256 for nsplit = 1, D <= 160 for nsplit = 16), else 0 */
 int cggp_tf32_supported(cggp_ctx* ctx, int D, int nsplit);
 int cggp_tf32_prepare(cggp_ctx* ctx, const void* dev_P, const void* dev_norms, int64_t n, int D, int64_t ldp,
                       void* dev_big, void* dev_small, void* dev_norms_pad);
+int cggp_f16x3_prepare(cggp_ctx* ctx, const void* dev_P, const void* dev_norms, int64_t n, int D, int64_t ldp,
+                       void* dev_big, void* dev_small, void* dev_norms_pad);
 int cggp_kuf_kfu_matvec_tf32(cggp_ctx* ctx, int kind, double variance,
                              const void* dev_Xbig, const void* dev_Xsmall, const void* dev_xnorms_pad, int64_t n,
                              const void* dev_Zbig, const void* dev_Zsmall, const void* dev_znorms_pad, int64_t m,
@@ -202,7 +208,7 @@ typedef struct cggp_operator {
   const void* dev_Z32_big;
   const void* dev_Z32_small;
   const void* dev_z32_norms;
-  int32_t tf32_nsplit;  /* 3 or 1 */
+  int32_t tf32_nsplit;  /* 3, 1 or 16 (arrays from cggp_f16x3_prepare) */
   int32_t _pad2;
 } cggp_operator;
 

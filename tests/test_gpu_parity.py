@@ -508,6 +508,39 @@ def test_tf32_tensor_core_matvec_vs_oracle(cb, name, N, M, D, B):
     np.testing.assert_allclose(cpu(op.kuf_times(dev(Y))), kref, rtol=1e-4, atol=1e-4 * np.abs(kref).max())
 
 
+@pytest.mark.parametrize("name", KERNELS)
+@pytest.mark.parametrize("N,M,D,B", [(6000, 192, 90, 2), (1000, 130, 11, 1), (4097, 300, 3, 3), (129, 257, 24, 1)])
+def test_f16x3_tensor_core_matvec_vs_oracle(cb, name, N, M, D, B):
+    """3xFP16 mode of the tcgen05 product (FP16 inputs with a per-row power-of-two scale, FP32 accumulators) vs the
+    float64 oracle on the same float32 inputs: the float32 tolerance of the north star (1e-4 relative), and as close
+    to the oracle as 3xTF32 is.  Rows of wildly different magnitude exercise the per-row scaling."""
+    rng = np.random.default_rng(N + D + 1)
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    Z = rng.standard_normal((M, D)).astype(np.float32)
+    X[::7] *= np.float32(1e-3)   # tiny rows
+    X[3::11] *= np.float32(30.0)  # far-away rows (kernel values ~ 0)
+    Z[::5] *= np.float32(1e-2)
+    X[5] = 0.0                   # an all-zero row (scale exponent undefined -> 1)
+    V = rng.standard_normal((B, M)).astype(np.float32)
+    ls = np.full(D, np.sqrt(D), np.float32)
+    ok = g.KERNELS[name](variance=1.3, lengthscales=ls.astype(np.float64))
+    ref = om.kuf_kfu_matmul(ok, X.astype(np.float64), Z.astype(np.float64), V.astype(np.float64))
+    k = cb.kernels.KERNELS[name](variance=1.3, lengthscales=ls)
+    op = cb.SGPROperator(k, dev(X), dev(Z), 0.1, variant=4, tf32_nsplit=16)
+    assert op.X32 is not None
+    W = cpu(op.kuf_kfu_matmul(dev(V)))
+    assert W.dtype == np.float32
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(W, ref, rtol=1e-4, atol=1e-4 * scale)
+    assert np.array_equal(W, cpu(op.kuf_kfu_matmul(dev(V))))  # bitwise reproducible
+    W3 = cpu(cb.SGPROperator(k, dev(X), dev(Z), 0.1, variant=4, tf32_nsplit=3).kuf_kfu_matmul(dev(V)))
+    err16, err3 = np.abs(W - ref).max() / scale, np.abs(W3 - ref).max() / scale
+    assert err16 <= 4 * err3 + 2e-6, (err16, err3)
+    Y = rng.standard_normal((N, 3)).astype(np.float32)
+    kref = ok.K(Z.astype(np.float64), X.astype(np.float64)) @ Y.astype(np.float64)
+    np.testing.assert_allclose(cpu(op.kuf_times(dev(Y))), kref, rtol=1e-4, atol=1e-4 * np.abs(kref).max())
+
+
 def test_tf32_operator_inside_cg(cb):
     rng = np.random.default_rng(77)
     N, M, D = 5000, 128, 40

@@ -54,14 +54,18 @@ def main_f32():
     Z = torch.randn(M, D, dtype=torch.float32, device="cuda", generator=g)
     V = torch.randn(1, M, dtype=torch.float32, device="cuda", generator=g)
     k = cb.SquaredExponential(1.0, [D ** 0.5] * D)
-    for nsplit in (3, 1):
+    for nsplit in (16, 3, 1):
         op = cb.SGPROperator(k, X, Z, 0.1, variant=4, tf32_nsplit=nsplit)
         best, avg = timeit(lambda: op.kuf_kfu_matmul(V), reps=3, warm=1)
-        flop = 2.0 * 2.0 * N * M * 96 * (3 if nsplit == 3 else 1)
-        print(f"c5/4 (N={N}): tcgen05 TF32 x{nsplit}: best {best:.3f} ms -> {flop / best / 1e9:.1f} TFLOP/s tensor, "
+        flop = 2.0 * 2.0 * N * M * 96 * (1 if nsplit == 1 else 3)
+        name = "3xFP16" if nsplit == 16 else f"TF32 x{nsplit}"
+        print(f"c5/4 (N={N}): tcgen05 {name}: best {best:.3f} ms -> {flop / best / 1e9:.1f} TFLOP/s tensor, "
               f"{2 * N * M / best / 1e6:.1f} Gentry/s (two sweeps)", flush=True)
+        if nsplit == 16:
+            W16 = op.kuf_kfu_matmul(V)
     op = cb.SGPROperator(k, X, Z, 0.1, variant=4)
     W4 = op.kuf_kfu_matmul(V)
+    print(f"c5/4: max rel diff 3xFP16 vs 3xTF32 {float((W16 - W4).abs().max() / W4.abs().max()):.3e}", flush=True)
     best1, _ = timeit(lambda: op.kuf_kfu_matmul(V, variant=1), reps=2, warm=1)
     W1 = op.kuf_kfu_matmul(V, variant=1)
     print(f"c5/4: FFMA two-sweep: best {best1:.3f} ms; max rel diff tf32x3 vs ffma "
