@@ -143,20 +143,46 @@ __host__ __device__ inline int64_t canon_off_h(int64_t r, int k, int KP) {
   const int64_t chunk = (r >> 7) * (KP >> 5) + (k >> 5);
   return chunk * 4096 + ((((r & 127) >> 3) * 4 + ((k & 31) >> 3)) * 64) + (r & 7) * 8 + (k & 7);
 }
+// The STREAMED arrays keep everything the products need of a 128-row tile in ONE contiguous block:
+//   [K chunk 0: part 0 | part 1] [K chunk 1: ...] ... [trailer: |x|^2 of the 128 rows | 1 / row scale (FP16 mode)]
+// so that any run of consecutive K chunks - all parts, and with the last chunk the per-row scalars - is one TMA bulk
+// copy (a bulk copy costs its issuing thread ~400 cycles whatever its size: tools/microbench_tma.cu).
+constexpr int TRAILER_BYTES = 1024;  // 2 x 128 floats
+__host__ __device__ inline int64_t tile_bytes(int KP, int parts, int esz) {
+  return (int64_t)(KP >> 5) * parts * 4096 * esz + TRAILER_BYTES;
+}
+__host__ __device__ inline int64_t stream_off(int64_t r, int k, int KP, int parts, int part) {  // TF32 (floats)
+  return (r >> 7) * (tile_bytes(KP, parts, 4) / 4) + ((int64_t)(k >> 5) * parts + part) * 4096 +
+         ((((r & 127) >> 3) * 8 + ((k & 31) >> 2)) * 32) + (r & 7) * 4 + (k & 3);
+}
+__host__ __device__ inline int64_t stream_off_h(int64_t r, int k, int KP, int parts, int part) {  // FP16 (halfs)
+  return (r >> 7) * (tile_bytes(KP, parts, 2) / 2) + ((int64_t)(k >> 5) * parts + part) * 4096 +
+         ((((r & 127) >> 3) * 4 + ((k & 31) >> 3)) * 64) + (r & 7) * 8 + (k & 7);
+}
+// float index (from the start of the stream) of scalar `which` (0: |x|^2, 1: 1 / row scale) of row r
+__host__ __device__ inline int64_t trailer_off(int64_t r, int KP, int parts, int esz, int which) {
+  return ((r >> 7) * tile_bytes(KP, parts, esz) + (tile_bytes(KP, parts, esz) - TRAILER_BYTES)) / 4 + which * 128 +
+         (r & 127);
+}
 constexpr int CHUNK_FLOATS = 4096;                      // 128 rows x 32 features
 constexpr unsigned CHUNK_BYTES = CHUNK_FLOATS * 4;      // 16 KB
 constexpr unsigned CHUNK_BYTES_H = 4096 * 2;            // the same chunk in FP16: 8 KB
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 12;
 constexpr int F16X3 = 16;                               // `nsplit` code of the 3xFP16 mode
 
 // ---------------------------------------------------------------------------------------------------------
 // one-time conversion of prepared points into the canonical TF32 big / small arrays (rows padded to 128)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void prepare_kernel(const float* __restrict__ P, const float* __restrict__ norms, int64_t n, int D,
-                               int64_t ldp, int KP, int64_t n_pad, float* __restrict__ big, float* __restrict__ small,
+                               int64_t ldp, int KP, int64_t n_pad, int parts, float* __restrict__ stream,
                                float* __restrict__ norms_pad) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < n_pad) norms_pad[e] = e < n ? norms[e] : 0.f;
+  if (e < n_pad) {
+    const float nv = e < n ? norms[e] : 0.f;
+    norms_pad[e] = nv;
+    stream[trailer_off(e, KP, parts, 4, 0)] = nv;
+    stream[trailer_off(e, KP, parts, 4, 1)] = 1.f;
+  }
   if (e >= n_pad * KP) return;
   const int64_t r = e / KP;
   const int k = (int)(e % KP);
@@ -168,24 +194,20 @@ __global__ void prepare_kernel(const float* __restrict__ P, const float* __restr
   const float rem = x - b;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(su) : "f"(rem));
   const float s = __uint_as_float(su);
-  const int64_t o = canon_off(r, k, KP);
-  big[o] = b;
-  small[o] = s;
+  stream[stream_off(r, k, KP, parts, 0)] = b;
+  if (parts > 1) stream[stream_off(r, k, KP, parts, 1)] = s;
 }
 
 // 3xFP16 mode: the tensor cores run FP16 inputs (FP32 accumulate) at twice the TF32 rate, and FP16 carries the same
 // 11 significant bits as TF32 - what it lacks is exponent range, which a per-row power-of-two scale restores:
-//   xs = x 2^s (row maximum in [2^14, 2^15)),  H = fp16(xs),  rem = xs - H  (exact, |rem| <= 2^-11 |xs|)
-//   row role (tile resident in tensor memory):  H, L' = fp16(rem), H' = fp16(H 2^-11)
-//   column role (streamed through shared memory): H, L = fp16(rem 2^11)      - only TWO arrays travel per tile
-//   x.z 2^(sx + sz) = sum H_x H_z + L'_x H_z + H'_x L_z   (+ the dropped rem_x rem_z term, 2^-22, as in 3xTF32)
-// (values 2^-17 below their row maximum lose bits of L' / H' to FP16 subnormals: an absolute error of 2^-40 of the
-// row-norm product).  One warp per row: row maximum -> scale, then the four arrays in the canonical FP16 order;
-// 1 / 2^s goes to `rinv`.
+//   xs = x 2^s (row maximum in [2^14, 2^15)),  H = fp16(xs),  R = fp16(xs - H)   (xs - H is exact, <= 2^-11 |xs|)
+//   x.z 2^(sx + sz) = sum H_x H_z + R_x H_z + H_x R_z   (+ the dropped R_x R_z term, 2^-22, as in 3xTF32)
+// Elements 2^-18 below their row maximum have R in the FP16 subnormals (absolute error 2^-25): 2^-40 of the product of
+// the row maxima, far below the float32 rounding of the distance.  One warp per row: row maximum -> scale, H | R into
+// the interleaved stream (both roles of the point set read it), 1 / 2^s into `rinv`.
 __global__ void prepare_f16_kernel(const float* __restrict__ P, const float* __restrict__ norms, int64_t n, int D,
-                                   int64_t ldp, int KP, int64_t n_pad, __half* __restrict__ H, __half* __restrict__ L,
-                                   __half* __restrict__ Lp, __half* __restrict__ Hp, float* __restrict__ rinv,
-                                   float* __restrict__ norms_pad) {
+                                   int64_t ldp, int KP, int64_t n_pad, __half* __restrict__ HR,
+                                   float* __restrict__ rinv, float* __restrict__ norms_pad) {
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= n_pad) return;
@@ -203,19 +225,19 @@ __global__ void prepare_f16_kernel(const float* __restrict__ P, const float* __r
   }
   const float up = exp2f((float)s);
   if (lane == 0) {
-    rinv[r] = exp2f((float)-s);
-    norms_pad[r] = r < n ? norms[r] : 0.f;
+    const float nv = r < n ? norms[r] : 0.f, ri = exp2f((float)-s);
+    rinv[r] = ri;
+    norms_pad[r] = nv;
+    float* tr = reinterpret_cast<float*>(HR);
+    tr[trailer_off(r, KP, 2, 2, 0)] = nv;
+    tr[trailer_off(r, KP, 2, 2, 1)] = ri;
   }
   for (int k = lane; k < KP; k += 32) {
     float x = 0.f;
     if (r < n && k < D) x = P[r * ldp + k] * up;
     const __half h = __float2half_rn(x);
-    const float rem = x - __half2float(h);
-    const int64_t o = canon_off_h(r, k, KP);
-    H[o] = h;
-    L[o] = __float2half_rn(rem * 2048.f);
-    Lp[o] = __float2half_rn(rem);
-    Hp[o] = __float2half_rn(__half2float(h) * (1.f / 2048.f));
+    HR[stream_off_h(r, k, KP, 2, 0)] = h;
+    HR[stream_off_h(r, k, KP, 2, 1)] = __float2half_rn(x - __half2float(h));
   }
 }
 
@@ -249,44 +271,58 @@ __device__ __forceinline__ float kval32(float r2) {
 constexpr float HALF_LOG2E = 0.72134752044448170368f;  // exp(-r2 / 2) = 2^(-HALF_LOG2E r2)
 
 struct Args {
-  const float* Pb;   // canonical big / small parts of the row set (TMEM lanes)
-  const float* Ps;
+  const float* Pb;   // row set (TMEM lanes): interleaved stream (TF32 big | small; FP16 H | R)
+  const float* Ps;   // FP16 only: 1 / row scale
   const float* pn;   // padded norms of the row set
   int64_t np;        // valid rows
-  const float* Qb;   // column set
-  const float* Qs;
+  const float* Qb;   // column set: interleaved stream
+  const float* Qs;   // FP16: 1 / row scale
   const float* qn;
   int64_t nq;        // valid columns
-  const float* U;    // [NB, ldu] weights over the columns
+  const float* U;    // [NB, ldu] weights over the columns, zero-padded to whole tiles (ldu >= 128 * tiles)
   int64_t ldu;
   float* out;        // [gridDim.y][NB][ldo] partial results over the rows
   int64_t ldo;
   int64_t q_tiles_per_split;
   float variance;
   int64_t np_pad, nq_pad;  // rows padded to 128 (3xFP16: offsets of the L array and of the row scales)
-  int stages;        // Q chunk ring depth (what fits next to the resident P tile)
+  int stages;        // ring depth in stages (what fits next to the resident P tile)
+  int gc;            // K chunks per stage (divides KP / 32): one TMA bulk copy, one full barrier
+  int niss;          // MMA-issuing threads in use (1..3); the ring holds a multiple of `niss` tiles, so that a stage
+                     // is always consumed by the same issuer (which then sees its barrier's phases in order)
   int dbg;           // timing experiments only (env CGGP_TF32_DBG; results are WRONG when set): 1 = no epilogue math,
                      // 2 = no MMAs, 4 = no TMA copies, 8 = no global loads of the column scalars, 16 = no tcgen05.ld
-  long long* stamps;  // timing experiments: [4 roles][128] clock64 stamps of CTA (0, 0) at tile boundaries, or NULL
   const int* active;
 };
 
 template <int KIND, int NSPLIT, int NB>
-__global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, const int KP) {
+__global__ void __launch_bounds__(384, 1) gram_contract_kernel(const Args a, const int KP) {
   if (cg_inactive(a.active)) return;
   constexpr bool F16 = NSPLIT == F16X3;
   constexpr int PARTS = NSPLIT > 1 ? 2 : 1;  // arrays of the column set that travel through shared memory
   constexpr unsigned CHB = F16 ? CHUNK_BYTES_H : CHUNK_BYTES;  // bytes of one part of one K chunk
-  constexpr int AUXR = (F16 ? 2 : 1) + NB;                     // per-column scalars: |q|^2 term, (scale,) weights
+  // per-column scalars of a tile, behind the last K chunk of its last stage: |q|^2 | 1 / scale | NB x weights
+  constexpr unsigned AUX_BYTES = TRAILER_BYTES + NB * 512;
   constexpr int BN = 128;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nchunk = KP >> 5;
   const int STAGES = a.stages;
-  unsigned char* sQ = smem_raw;                                          // [STAGES][PARTS][CHB bytes]
-  float* aux = reinterpret_cast<float*>(sQ + (size_t)STAGES * PARTS * CHB);  // [2][AUXR * BN]
-  // TMEM: columns [0, 256) two accumulators; [256, 256 + PARTS * KP) the P tile as the A operand (row = lane)
-  constexpr uint32_t TM_P = 256;
-  __shared__ uint64_t bar_p, bar_qfull[MAX_STAGES], bar_qfree[MAX_STAGES], bar_full[2], bar_empty[2], bar_aux[2];
+  const int GC = a.gc, NG = nchunk / GC;  // chunks per stage, stages per tile
+  const unsigned stage_bytes = (unsigned)GC * PARTS * CHB;     // operand bytes of a stage
+  const unsigned stage_stride = stage_bytes + AUX_BYTES;
+  unsigned char* sQ = smem_raw;                                // [STAGES][GC x PARTS x CHB operands | AUX_BYTES]
+  // TMEM: NBUF accumulators of 128 columns, then the P tile as the A operand (row = lane).  FP16 packs two features
+  // per column (P tile = KP columns), which leaves room for a THIRD accumulator: an issuing thread can start the next
+  // tile while both of the previous ones are still being issued / drained.
+  constexpr int NBUF = F16 ? 3 : 2;
+  const int NISS = a.niss;  // MMA-issuing threads in use (warps 9, 11)
+  // Tiles are dealt round-robin to NBUF accumulators, NISS issuers and 2 epilogue groups.  The per-tile barriers are
+  // indexed j % NBAR with NBAR a common multiple of all three, so that every barrier always has the same producer and
+  // the same consumer, which therefore sees its phases strictly in order (a parity wait cannot tell phase k from
+  // phase k - 2).
+  constexpr int NBAR = 6;
+  constexpr uint32_t TM_P = NBUF * 128;
+  __shared__ uint64_t bar_p, bar_qfull[MAX_STAGES], bar_qfree[MAX_STAGES], bar_full[NBAR], bar_empty[NBAR];
   __shared__ uint32_t tmem_base_s;
   __shared__ float comb[BM * NB];  // partial sums of the second column half, combined at the end
 
@@ -297,17 +333,25 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
   int64_t njt = q_tiles_total - jt0;
   if (njt > a.q_tiles_per_split) njt = a.q_tiles_per_split;
   if (njt < 0) njt = 0;
+  // Every CTA of a sweep needs the same column tiles (operands and per-column scalars); started together and walking
+  // them in the same order, all SMs would pull the same lines from the same L2 slices at the same moment.  Each CTA
+  // therefore starts its walk at a different tile (a fixed function of its index: results stay reproducible).
+  const int64_t rot = (njt > 0 && !(a.dbg & 64)) ? (int64_t)((blockIdx.x * 7u + blockIdx.y * 3u) % (unsigned)njt) : 0;
+  auto tile_of = [&](int64_t j) {
+    int64_t jj = j + rot;
+    if (jj >= njt) jj -= njt;
+    return jt0 + jj;
+  };
 
   if (tid == 0) {
     mbar_init(&bar_p, 8);  // one elected lane per epilogue warp arrives (256 arrivals on one mbarrier serialise)
     for (int b = 0; b < MAX_STAGES; ++b) {
-      mbar_init(&bar_qfull[b], 1);
+      mbar_init(&bar_qfull[b], 2);  // operand producer + weights producer (each with its own expect_tx)
       mbar_init(&bar_qfree[b], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NBAR; ++b) {
       mbar_init(&bar_full[b], 1);
-      mbar_init(&bar_empty[b], 8);
-      mbar_init(&bar_aux[b], 1);
+      mbar_init(&bar_empty[b], 4);  // one elected lane of each of the 4 warps of the epilogue group
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -323,143 +367,134 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
   if (warp == 8) {
     // =============================== TMA producer warp ===============================
     if (lane == 0) {
-      int64_t g = 0;  // running chunk counter over the whole loop
+      int64_t g = 0;  // running stage counter over the whole loop
+      constexpr int ESZ = F16 ? 2 : 4;
+      const unsigned char* qstream = reinterpret_cast<const unsigned char*>(a.Qb);
       for (int64_t j = 0; j < njt; ++j) {
-        const int64_t q0 = (jt0 + j) * BN;
-        for (int c = 0; c < nchunk; ++c, ++g) {
+        const int64_t tile = tile_of(j);
+        for (int gi = 0; gi < NG; ++gi, ++g) {
           const int s = (int)(g % STAGES);
-          if (g >= STAGES) mbar_wait(&bar_qfree[s], (unsigned)(((g / STAGES) - 1) & 1));  // MMAs done with this stage
-          unsigned char* dst = sQ + (size_t)s * PARTS * CHB;
-          const int64_t src = (q0 >> 7) * (int64_t)nchunk * CHUNK_FLOATS + (int64_t)c * CHUNK_FLOATS;  // elements
+          // the epilogue releases a tile's stages once the MMAs that read them are done
+          if (g >= STAGES) mbar_wait(&bar_qfree[s], (unsigned)(((g / STAGES) - 1) & 1));
           if (a.dbg & 4) {
             mbar_arrive(&bar_qfull[s]);
             continue;
           }
-          mbar_expect_tx(&bar_qfull[s], PARTS * CHB);
-          if constexpr (F16) {
-            const __half* QH = reinterpret_cast<const __half*>(a.Qb);
-            const __half* QL = QH + a.nq_pad * KP;
-            tma_bulk_g2s(dst, QH + src, CHB, &bar_qfull[s]);
-            tma_bulk_g2s(dst + CHB, QL + src, CHB, &bar_qfull[s]);
-          } else {
-            tma_bulk_g2s(dst, a.Qb + src, CHB, &bar_qfull[s]);
-            if (PARTS > 1) tma_bulk_g2s(dst + CHB, a.Qs + src, CHB, &bar_qfull[s]);
-          }
+          const int64_t src = tile * tile_bytes(KP, PARTS, ESZ) + (int64_t)gi * stage_bytes;
+          const unsigned bytes = stage_bytes + (gi == NG - 1 ? (unsigned)TRAILER_BYTES : 0u);  // + the tile's scalars
+          mbar_expect_tx(&bar_qfull[s], bytes);
+          tma_bulk_g2s(sQ + (size_t)s * stage_stride, qstream + src, bytes, &bar_qfull[s]);
         }
-        if (a.stamps && blockIdx.x == 0 && blockIdx.y == 0 && j < 128) a.stamps[j] = clock64();
       }
     }
     __syncwarp();
   } else if (warp == 10) {
-    // =============================== column-scalar warp ===============================
-    // per-column scalars of every tile for the epilogue: |q|^2 (SE: its share of the exponent) and the weights U
-    // (zero past the end); kept off the TMA warp so that the global-load latency never delays a bulk copy
-    for (int64_t j = 0; j < njt; ++j) {
-      const int buf = (int)(j & 1);
-      const int64_t q0 = (jt0 + j) * BN;
-      float vals[BN / 32][AUXR];
-      constexpr int UO = AUXR - NB;  // first weight row
+    // =============================== weights producer ===============================
+    // the per-call weights U of every tile (NB x 512 bytes, from the zero-padded copy) land behind the tile's static
+    // scalars; a second thread, so that the operand producer stays at one bulk copy per stage
+    if (lane == 0) {
+      int64_t g = 0;
+      for (int64_t j = 0; j < njt; ++j) {
+        const int64_t tile = tile_of(j);
+        for (int gi = 0; gi < NG; ++gi, ++g) {
+          const int s = (int)(g % STAGES);
+          if (g >= STAGES) mbar_wait(&bar_qfree[s], (unsigned)(((g / STAGES) - 1) & 1));
+          if (gi != NG - 1 || (a.dbg & 8)) {
+            mbar_arrive(&bar_qfull[s]);
+            continue;
+          }
+          mbar_expect_tx(&bar_qfull[s], NB * 512u);
+          unsigned char* dst = sQ + (size_t)s * stage_stride + stage_bytes + TRAILER_BYTES;
 #pragma unroll
-      for (int i = 0; i < BN / 32; ++i) {
-        const int64_t q = q0 + i * 32 + lane;
-        if (a.dbg & 8) {
-#pragma unroll
-          for (int b = 0; b < AUXR; ++b) vals[i][b] = 0.f;
-          continue;
+          for (int b = 0; b < NB; ++b)
+            tma_bulk_g2s(dst + b * 512, a.U + (int64_t)b * a.ldu + tile * BN, 512u, &bar_qfull[s]);
         }
-        vals[i][0] = KIND == CGGP_SE ? -HALF_LOG2E * a.qn[q] : a.qn[q];  // padded array
-        if constexpr (F16) {
-          // the column's share of the accumulator scale, folded with the constant the kernel family multiplies by
-          const float rq = (a.Qs + a.nq_pad * KP)[q];
-          vals[i][1] = (KIND == CGGP_SE ? 2.f * HALF_LOG2E : -2.f) * rq;
-        }
-#pragma unroll
-        for (int b = 0; b < NB; ++b) vals[i][UO + b] = q < a.nq ? a.U[(int64_t)b * a.ldu + q] : 0.f;
       }
-      if (j >= 2) mbar_wait(&bar_empty[buf], (unsigned)(((j >> 1) - 1) & 1));  // epilogue of tile j-2 left aux[buf]
-      float* ax = aux + buf * AUXR * BN;
-#pragma unroll
-      for (int i = 0; i < BN / 32; ++i)
-#pragma unroll
-        for (int b = 0; b < AUXR; ++b) ax[b * BN + i * 32 + lane] = vals[i][b];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_aux[buf]);
-      if (a.stamps && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && j < 128) a.stamps[128 + j] = clock64();
     }
-  } else if (warp == 9) {
-    // =============================== MMA issuer warp ===============================
-    if (lane == 0 && njt > 0) {
+    __syncwarp();
+  } else if (warp == 9 || warp == 11) {
+    // =============================== MMA issuer warps ===============================
+    // NISS issuing threads (tiles j = t mod NISS): a single thread issues a 128 x 128 MMA only every ~135 cycles
+    // (measured; the instruction itself takes 64) and stalls ~500 more on its commit, so one issuer leaves the tensor
+    // pipe half idle.  The threads' MMAs interleave in the pipe; every tile accumulates into buffer j % NBUF and is
+    // committed by its issuer.
+    const int mt = warp == 9 ? 0 : warp - 10;
+    if (lane == 0 && njt > mt && mt < NISS) {
       const unsigned lbo = 128, sbo = F16 ? 512 : 1024;
       // instruction descriptor: FP32 accumulate, A / B format TF32 (2) resp. F16 (0), K-major, N, M
       const uint32_t idesc = (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       mbar_wait(&bar_p, 0);  // the epilogue warps have stored the P tile into tensor memory
       asm volatile("tcgen05.fence::after_thread_sync;");
-      int64_t g = 0;
-      for (int64_t j = 0; j < njt; ++j) {
-        const int buf = (int)(j & 1);
-        if (j >= 2) mbar_wait(&bar_empty[buf], (unsigned)(((j >> 1) - 1) & 1));  // accumulator drained by the epilogue
+      for (int64_t j = mt; j < njt; j += NISS) {
+        const int buf = (int)(j % NBUF);
+        int64_t g = j * NG;  // running stage counter of the producer
+        if (j >= NBUF) {  // accumulator drained by the epilogue of tile j - NBUF
+          mbar_wait(&bar_empty[(j - NBUF) % NBAR], (unsigned)(((j - NBUF) / NBAR) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;");           // its tcgen05.ld before our MMAs
+        }
         const uint32_t d = tmem_base + (uint32_t)(buf * BN);
         uint32_t acc = 0;
-        for (int c = 0; c < nchunk; ++c, ++g) {
+        for (int gi = 0; gi < NG; ++gi, ++g) {
           const int s = (int)(g % STAGES);
-          mbar_wait(&bar_qfull[s], (unsigned)((g / STAGES) & 1));
-          asm volatile("tcgen05.fence::after_thread_sync;");
-          const unsigned qb = smem_u32(sQ) + (unsigned)s * PARTS * CHB, qs = qb + CHB;
-          if (a.dbg & 2) {
-            umma_commit(&bar_qfree[s]);
-            continue;
-          }
-          if constexpr (F16) {
-            // A operand: H at TMEM columns [TM_P, + KP / 2), L' and H' behind it (two features per column); a K = 16
-            // step is 8 columns of A and two 128-byte core matrices of B; stage order: H | L
-            const uint32_t ph = tmem_base + TM_P + (uint32_t)c * 16, pl = ph + (uint32_t)(KP / 2),
-                           php = pl + (uint32_t)(KP / 2);
+          mbar_wait(&bar_qfull[s], (unsigned)((g / STAGES) & 1));  // TMA bytes landed (async proxy -> async proxy)
+          if (a.dbg & 2) continue;
+          for (int cc = 0; cc < GC; ++cc) {
+            const int c = gi * GC + cc;
+            const unsigned qb = smem_u32(sQ) + (unsigned)s * stage_stride + (unsigned)cc * PARTS * CHB, qs = qb + CHB;
+            if constexpr (F16) {
+              // A operand: H at TMEM columns [TM_P, + KP / 2), R behind it (two features per column); a K = 16 step
+              // is 8 columns of A and two 128-byte core matrices of B; chunk order in the stage: H | R
+              const uint32_t ph = tmem_base + TM_P + (uint32_t)c * 16, pr = ph + (uint32_t)(KP / 2);
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {  // D (+)= H_p H_q^T
-              umma_f16_ta(d, ph + k * 8, smem_desc(qb + k * 256, lbo, sbo), idesc, acc);
-              acc = 1;
+              for (int k = 0; k < 2; ++k) {  // D (+)= H_p H_q^T
+                umma_f16_ta(d, ph + k * 8, smem_desc(qb + k * 256, lbo, sbo), idesc, acc);
+                acc = 1;
+              }
+#pragma unroll
+              for (int k = 0; k < 2; ++k)  // + R_p H_q^T
+                umma_f16_ta(d, pr + k * 8, smem_desc(qb + k * 256, lbo, sbo), idesc, 1);
+#pragma unroll
+              for (int k = 0; k < 2; ++k)  // + H_p R_q^T
+                umma_f16_ta(d, ph + k * 8, smem_desc(qs + k * 256, lbo, sbo), idesc, 1);
+            } else {
+              const uint32_t pb = tmem_base + TM_P + (uint32_t)c * 32, ps = pb + (uint32_t)KP;  // A: TMEM columns
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {  // D (+)= Pb Qb^T
+                umma_tf32_ta(d, pb + k * 8, smem_desc(qb + k * 256, lbo, sbo), idesc, acc);
+                acc = 1;
+              }
+              if (PARTS > 1) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)  // + Ps Qb^T
+                  umma_tf32_ta(d, ps + k * 8, smem_desc(qb + k * 256, lbo, sbo), idesc, 1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)  // + Pb Qs^T
+                  umma_tf32_ta(d, pb + k * 8, smem_desc(qs + k * 256, lbo, sbo), idesc, 1);
+              }
             }
-#pragma unroll
-            for (int k = 0; k < 2; ++k)  // + L'_p H_q^T
-              umma_f16_ta(d, pl + k * 8, smem_desc(qb + k * 256, lbo, sbo), idesc, 1);
-#pragma unroll
-            for (int k = 0; k < 2; ++k)  // + H'_p L_q^T
-              umma_f16_ta(d, php + k * 8, smem_desc(qs + k * 256, lbo, sbo), idesc, 1);
-            umma_commit(&bar_qfree[s]);
-            continue;
           }
-          const uint32_t pb = tmem_base + TM_P + (uint32_t)c * 32, ps = pb + (uint32_t)KP;  // A operand: TMEM columns
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {  // D (+)= Pb Qb^T
-            umma_tf32_ta(d, pb + k * 8, smem_desc(qb + k * 256, lbo, sbo), idesc, acc);
-            acc = 1;
-          }
-          if (PARTS > 1) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)  // + Ps Qb^T
-              umma_tf32_ta(d, ps + k * 8, smem_desc(qb + k * 256, lbo, sbo), idesc, 1);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)  // + Pb Qs^T
-              umma_tf32_ta(d, pb + k * 8, smem_desc(qs + k * 256, lbo, sbo), idesc, 1);
-          }
-          umma_commit(&bar_qfree[s]);  // the stage may be refilled once these MMAs are done
         }
-        umma_commit(&bar_full[buf]);  // accumulator ready for the epilogue
-        if (a.stamps && blockIdx.x == 0 && blockIdx.y == 0 && j < 128) a.stamps[256 + j] = clock64();
+        // ONE commit per tile (a tcgen05.commit holds the issuing thread for ~550 cycles; one per K chunk made this
+        // thread the bottleneck of the kernel): it publishes the accumulator, and the epilogue releases the stages
+        umma_commit(&bar_full[j % NBAR]);  // accumulator ready for the epilogue
       }
     }
     __syncwarp();
   } else {
     // =============================== epilogue warps ===============================
-    // 8 warps: warp w reads TMEM lanes 32 (w % 4) .. + 31 (thread = row) and the column half w / 4 of every tile
-    const int quarter = warp & 3, half = warp >> 2;
+    // 8 warps in two groups of 4: group w / 4 owns accumulator buffer w / 4, i.e. every other tile, and warp w reads
+    // TMEM lanes 32 (w % 4) .. + 31 of it (thread = row, all 128 columns in two passes of 64).  While one group waits
+    // for its accumulator / its tcgen05.ld, the other group's math keeps the issue slots and the MUFU pipe busy (all 8
+    // warps on the same tile left both idle for the ~1000 cycles of hand-offs and loads of every tile).
+    const int quarter = warp & 3, half = warp >> 2;  // `half`: group (tile loop) / feature half (P tile gather)
     const int row = quarter * 32 + lane;
     const int64_t p = p0 + row;
     const float pn = a.pn[p];  // padded array
     const float cp = -HALF_LOG2E * pn;
-    float rp = 1.f;            // 3xFP16: this row's share of the accumulator scale
-    if constexpr (F16) rp = (a.Ps + a.np_pad * KP)[p];
+    // 3xFP16: accumulator = 2^(sp + sq) p.q; the row's 2^-sp, folded with the factor of the cross term
+    float rp = 1.f;
+    if constexpr (F16) rp = (KIND == CGGP_SE ? 2.f * HALF_LOG2E : -2.f) * a.Ps[p];
     if (njt > 0) {
       // P tile -> tensor memory (A operand of every MMA of this CTA): thread = row = TMEM lane; the two column halves
       // of the epilogue split the features.  Halves the shared-memory operand traffic of the MMAs (only Q is read
@@ -467,22 +502,20 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
       const int kper = KP / 2;  // KP is a multiple of 32
       if constexpr (F16) {
         const __half* PH = reinterpret_cast<const __half*>(a.Pb);
-        const __half* PLp = reinterpret_cast<const __half*>(a.Ps);
-        for (int part = 0; part < 3; ++part) {
-          const __half* src = part == 0 ? PH : (part == 1 ? PLp : PLp + a.np_pad * KP);
+        for (int part = 0; part < 2; ++part) {
           for (int k0 = half * kper; k0 < (half + 1) * kper; k0 += 16) {
-            const uint4 x0 = *reinterpret_cast<const uint4*>(src + canon_off_h(p, k0, KP));
-            const uint4 x1 = *reinterpret_cast<const uint4*>(src + canon_off_h(p, k0 + 8, KP));
+            const uint4 x0 = *reinterpret_cast<const uint4*>(PH + stream_off_h(p, k0, KP, 2, part));
+            const uint4 x1 = *reinterpret_cast<const uint4*>(PH + stream_off_h(p, k0 + 8, KP, 2, part));
             const uint32_t v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
             tmem_st8(tmem_base + ((uint32_t)(quarter * 32) << 16) + TM_P + (uint32_t)(part * (KP / 2) + k0 / 2), v);
           }
         }
       } else
       for (int part = 0; part < PARTS; ++part) {
-        const float* src = part == 0 ? a.Pb : a.Ps;
+        const float* src = a.Pb;
         for (int k0 = half * kper; k0 < (half + 1) * kper; k0 += 8) {
-          const float4 x0 = *reinterpret_cast<const float4*>(src + canon_off(p, k0, KP));
-          const float4 x1 = *reinterpret_cast<const float4*>(src + canon_off(p, k0 + 4, KP));
+          const float4 x0 = *reinterpret_cast<const float4*>(src + stream_off(p, k0, KP, PARTS, part));
+          const float4 x1 = *reinterpret_cast<const float4*>(src + stream_off(p, k0 + 4, KP, PARTS, part));
           const uint32_t v[8] = {__float_as_uint(x0.x), __float_as_uint(x0.y), __float_as_uint(x0.z),
                                  __float_as_uint(x0.w), __float_as_uint(x1.x), __float_as_uint(x1.y),
                                  __float_as_uint(x1.z), __float_as_uint(x1.w)};
@@ -497,70 +530,83 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
     float acc[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) acc[b] = 0.f;
-    for (int64_t j = 0; j < njt; ++j) {
-      const int buf = (int)(j & 1);
-      mbar_wait(&bar_aux[buf], (unsigned)((j >> 1) & 1));
-      mbar_wait(&bar_full[buf], (unsigned)((j >> 1) & 1));
+    for (int64_t j = half; j < njt; j += 2) {
+      const int buf = (int)(j % NBUF);
+      mbar_wait(&bar_full[j % NBAR], (unsigned)((j / NBAR) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;");
-      const float* ax = aux + buf * AUXR * BN + half * 64;
-      constexpr int UO = AUXR - NB;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + half * 64);
-      uint32_t v[2][32];
-      if (!(a.dbg & 16)) {
-        tmem_ld32_nowait(taddr, v[0]);
-        tmem_ld32_nowait(taddr + 32, v[1]);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      } else {
-        v[0][0] = v[1][31] = 0;
+      // The MMAs of tile j are done, so its bytes have landed and its stages cannot have been refilled: the phase of
+      // the last stage's barrier is exactly the tile's.  Waiting on it (it completes at once) makes the scalars the
+      // TMA wrote behind the operands visible to this thread.
+      const int64_t glast = j * NG + NG - 1;
+      const int slast = (int)(glast % STAGES);
+      mbar_wait(&bar_qfull[slast], (unsigned)((glast / STAGES) & 1));
+      if (quarter == 0 && lane == 0) {  // all stages but the one holding the scalars may be refilled
+        for (int gi = 0; gi < NG - 1; ++gi) mbar_arrive(&bar_qfree[(int)((j * NG + gi) % STAGES)]);
       }
-      // the accumulator is in registers: hand the TMEM buffer back before the math
-      asm volatile("tcgen05.fence::before_thread_sync;");
+      const float* axt = reinterpret_cast<const float*>(sQ + (size_t)slast * stage_stride + stage_bytes);
+      constexpr int UO = 2;  // trailer rows: |q|^2, 1 / scale, weights
       float part[NB];
 #pragma unroll
       for (int b = 0; b < NB; ++b) part[b] = 0.f;
-      if (a.dbg & 1) {
-        part[0] = __uint_as_float(v[0][0] ^ v[1][31]);
-      } else
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {  // the two 64-column halves of the tile
+        const float* ax = axt + ch * 64;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + ch * 64);
+        uint32_t v[2][32];
+        if (!(a.dbg & 16)) {
+          tmem_ld32_nowait(taddr, v[0]);
+          tmem_ld32_nowait(taddr + 32, v[1]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+          v[0][0] = v[1][31] = 0;
+        }
+        if (a.dbg & 1) {
+          part[0] += __uint_as_float(v[0][0] ^ v[1][31]);
+          continue;
+        }
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int c4 = 0; c4 < 32; c4 += 4) {
-          const float4 qv = *reinterpret_cast<const float4*>(ax + h * 32 + c4);
-          float4 uv[NB];
+          for (int c4 = 0; c4 < 32; c4 += 4) {
+            const float4 qv = *reinterpret_cast<const float4*>(ax + h * 32 + c4);
+            float4 uv[NB];
 #pragma unroll
-          for (int b = 0; b < NB; ++b) uv[b] = *reinterpret_cast<const float4*>(ax + (UO + b) * BN + h * 32 + c4);
-          const float qs[4] = {qv.x, qv.y, qv.z, qv.w};
-          float aq[4] = {0.f, 0.f, 0.f, 0.f};
-          if constexpr (F16) {
-            const float4 av = *reinterpret_cast<const float4*>(ax + BN + h * 32 + c4);
-            aq[0] = av.x; aq[1] = av.y; aq[2] = av.z; aq[3] = av.w;
-          }
-          float kv[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float d = __uint_as_float(v[h][c4 + i]);
+            for (int b = 0; b < NB; ++b) uv[b] = *reinterpret_cast<const float4*>(ax + (UO + b) * BN + h * 32 + c4);
+            const float qs[4] = {qv.x, qv.y, qv.z, qv.w};
+            float aq[4] = {0.f, 0.f, 0.f, 0.f};
             if constexpr (F16) {
-              // accumulator = 2^(sp + sq) p.q; aq carries 2^-sq and the family's factor on the cross term
-              if constexpr (KIND == CGGP_SE) kv[i] = ex2_approx(fmaf(d * aq[i], rp, cp + qs[i]));
-              else kv[i] = kval32<KIND>(fmaf(d * aq[i], rp, pn + qs[i]));
-            } else if constexpr (KIND == CGGP_SE) {
-              // exp(-r2 / 2) with r2 = |p|^2 + |q|^2 - 2 p.q: one FADD + one FFMA + MUFU.EX2
-              kv[i] = ex2_approx(fmaf(2.f * HALF_LOG2E, d, cp + qs[i]));
-            } else {
-              kv[i] = kval32<KIND>(fmaf(-2.f, d, pn + qs[i]));  // GPflow: dist = -2 p.q; dist += |p|^2 + |q|^2
+              const float4 av = *reinterpret_cast<const float4*>(ax + BN + h * 32 + c4);
+              aq[0] = av.x; aq[1] = av.y; aq[2] = av.z; aq[3] = av.w;
+            }
+            float kv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float d = __uint_as_float(v[h][c4 + i]);
+              if constexpr (F16) {
+                // aq = 2^-sq of the column, rp = 2^-sp of the row times the factor of the cross term
+                if constexpr (KIND == CGGP_SE) kv[i] = ex2_approx(fmaf(d * aq[i], rp, fmaf(-HALF_LOG2E, qs[i], cp)));
+                else kv[i] = kval32<KIND>(fmaf(d * aq[i], rp, pn + qs[i]));
+              } else if constexpr (KIND == CGGP_SE) {
+                // exp(-r2 / 2) with r2 = |p|^2 + |q|^2 - 2 p.q: two FFMA + MUFU.EX2
+                kv[i] = ex2_approx(fmaf(2.f * HALF_LOG2E, d, fmaf(-HALF_LOG2E, qs[i], cp)));
+              } else {
+                kv[i] = kval32<KIND>(fmaf(-2.f, d, pn + qs[i]));  // GPflow: dist = -2 p.q; dist += |p|^2 + |q|^2
+              }
+            }
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+              part[b] = fmaf(kv[0], uv[b].x, part[b]);
+              part[b] = fmaf(kv[1], uv[b].y, part[b]);
+              part[b] = fmaf(kv[2], uv[b].z, part[b]);
+              part[b] = fmaf(kv[3], uv[b].w, part[b]);
             }
           }
-#pragma unroll
-          for (int b = 0; b < NB; ++b) {
-            part[b] = fmaf(kv[0], uv[b].x, part[b]);
-            part[b] = fmaf(kv[1], uv[b].y, part[b]);
-            part[b] = fmaf(kv[2], uv[b].z, part[b]);
-            part[b] = fmaf(kv[3], uv[b].w, part[b]);
-          }
-        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_empty[buf]);  // the warp has read its accumulator slice and aux[buf]
-      if (a.stamps && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && j < 128) a.stamps[384 + j] = clock64();
+      if (lane == 0) mbar_arrive(&bar_empty[j % NBAR]);  // the warp has read its accumulator slice
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");  // the 4 warps of the group have read the scalars
+      if (quarter == 0 && lane == 0) mbar_arrive(&bar_qfree[slast]);
 #pragma unroll
       for (int b = 0; b < NB; ++b) acc[b] += part[b];
     }
@@ -578,6 +624,14 @@ __global__ void __launch_bounds__(352, 1) gram_contract_kernel(const Args a, con
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+}
+
+// zero-padded copy of the weights, so that every 128-column tile of them is one aligned 512-byte bulk copy
+__global__ void pad_weights_kernel(const float* __restrict__ U, int64_t ldu, int64_t nq, int64_t nq_pad,
+                                   float* __restrict__ out, const int* __restrict__ active) {
+  if (cg_inactive(active)) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nq_pad) out[(int64_t)blockIdx.y * nq_pad + i] = i < nq ? U[(int64_t)blockIdx.y * ldu + i] : 0.f;
 }
 
 __global__ void reduce_splits_kernel(const float* __restrict__ part, int splits, int NB, int64_t ld, int64_t n,
@@ -610,61 +664,102 @@ static KernelFn pick(int kind, int nsplit, int nb) {
 }
 
 constexpr size_t SMEM_BUDGET = 227 * 1024 - 1024;  // leave room for the static barriers
-// ring depth that fits next to the resident P tile (0 = does not fit)
-static size_t stage_bytes(int nsplit) {
+static size_t chunk_bytes(int nsplit) {  // all streamed parts of one K chunk of a 128-row tile
   return nsplit == F16X3 ? 2 * (size_t)CHUNK_BYTES_H : (nsplit > 1 ? 2 : 1) * (size_t)CHUNK_BYTES;
 }
-static size_t aux_bytes(int nsplit, int nb) {
-  return (size_t)2 * ((nsplit == F16X3 ? 2 : 1) + nb) * 128 * sizeof(float) + 128;
+static size_t aux_bytes(int nb) {  // per stage: the tile's static scalars + nb rows of weights
+  return (size_t)TRAILER_BYTES + (size_t)nb * 512;
 }
-static int stages_for(int KP, int nsplit, int nb) {
+struct RingPlan {
+  int gc = 0, stages = 0, niss = 0;  // K chunks per stage, ring depth (0 = does not fit), issuing threads
+};
+// Stage = `gc` consecutive K chunks (one bulk copy).  A whole tile per stage keeps the producer at one copy per tile
+// (its per-copy cost is what matters when the MMAs of a tile are short: FP16 and single-pass TF32); 3xTF32 tiles are
+// long enough for one copy per chunk, which overlaps better.  A tile's stages are released together, so the ring
+// must hold at least one tile - two for overlap.
+static RingPlan ring_for(int KP, int nsplit, int nb) {
+  RingPlan r;
   // the P tile must fit in the 256 tensor-memory columns next to the accumulators (FP16: two features per column)
-  const size_t pcols = nsplit == F16X3 ? 3 * (size_t)KP / 2 : (nsplit > 1 ? 2 : 1) * (size_t)KP;
-  if (pcols > 256) return 0;
-  const size_t fixed = aux_bytes(nsplit, nb);
-  if (fixed >= SMEM_BUDGET) return 0;
-  size_t st = (SMEM_BUDGET - fixed) / stage_bytes(nsplit);
-  if (st > MAX_STAGES) st = MAX_STAGES;
-  return st >= 2 ? (int)st : 0;
+  const size_t pcols = nsplit == F16X3 ? (size_t)KP : (nsplit > 1 ? 2 : 1) * (size_t)KP;
+  if (pcols > (nsplit == F16X3 ? 128u : 256u)) return r;
+  const int nchunk = KP / 32;
+  const size_t room = SMEM_BUDGET;
+  // two issuers where the tiles are long enough to profit (a third one did not pay: the 13th warp caps the epilogue
+  // at 128 registers), then one; for each, the coarsest stage that still leaves `niss` whole tiles (and at least
+  // two) in the ring
+  // measured at the c5 shape (ms per product, 1 / 2 issuers): 3xFP16 5.02 / 4.17, 3xTF32 8.63 / 7.88, 1xTF32 4.14 / 5.08
+  static const int niss_env = getenv("CGGP_TF32_NISS") ? atoi(getenv("CGGP_TF32_NISS")) : 0;  // tuning knob
+  const int niss_max = niss_env > 0 ? niss_env : (nsplit == 1 ? 1 : 2);
+  for (int niss = niss_max >= 2 ? 2 : 1; niss >= 1; --niss) {
+    for (int gc = (nsplit == 3 ? 1 : nchunk); gc >= 1; --gc) {
+      if (nchunk % gc) continue;
+      const int ng = nchunk / gc;
+      size_t st = room / (chunk_bytes(nsplit) * gc + aux_bytes(nb));
+      if (st > MAX_STAGES) st = MAX_STAGES;
+      st = st / (size_t)(ng * niss) * (size_t)(ng * niss);  // whole groups of `niss` tiles
+      if ((int)st >= 2 * ng) {
+        r.gc = gc;
+        r.stages = (int)st;
+        r.niss = niss;
+        return r;
+      }
+    }
+  }
+  // last resort (wide tiles): one issuer and a single tile in the ring, in the finest stages that hold it
+  for (int gc = 1; gc <= nchunk; ++gc) {
+    if (nchunk % gc) continue;
+    const int ng = nchunk / gc;
+    size_t st = room / (chunk_bytes(nsplit) * gc + aux_bytes(nb));
+    if (st > MAX_STAGES) st = MAX_STAGES;
+    st = st / (size_t)ng * (size_t)ng;
+    if ((int)st >= ng) {
+      r.gc = gc;
+      r.stages = (int)st;
+      r.niss = 1;
+      return r;
+    }
+  }
+  return r;
 }
-static size_t smem_bytes(int KP, int nsplit, int nb, int stages) {
-  return (size_t)stages * stage_bytes(nsplit) + aux_bytes(nsplit, nb);
+static size_t smem_bytes(int nsplit, int nb, const RingPlan& r) {
+  return (size_t)r.stages * (r.gc * chunk_bytes(nsplit) + aux_bytes(nb));
 }
 }  // namespace tf32
 
 extern "C" int cggp_tf32_kp(int D) { return (D + 31) / 32 * 32; }
 extern "C" int64_t cggp_tf32_rows(int64_t n) { return (n + 127) / 128 * 128; }
 
-extern "C" int cggp_tf32_prepare(cggp_ctx* ctx, const void* P, const void* norms, int64_t n, int D, int64_t ldp,
-                                 void* big, void* small, void* norms_pad) {
-  if (!ctx) return CGGP_ERR_INVALID;
-  if (D < 1 || n < 0) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "bad shape");
-  const int KP = cggp_tf32_kp(D);
-  const int64_t n_pad = cggp_tf32_rows(n);
-  if (n_pad == 0) return CGGP_OK;
-  const int64_t total = n_pad * KP;
-  tf32::prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
-      (const float*)P, (const float*)norms, n, D, ldp, KP, n_pad, (float*)big, (float*)small, (float*)norms_pad);
-  CGGP_LAUNCH_CHECK(ctx);
+// Buffer sizes in floats for a point set of n rows (header): dev_stream holds the interleaved arrays the products
+// stream (TF32 big [| small]; FP16 H | R), dev_rows the 1 / row scales of the 3xFP16 mode.
+extern "C" int cggp_tf32_sizes(int nsplit, int64_t n, int D, int64_t* stream_floats, int64_t* rows_floats) {
+  if (nsplit != 1 && nsplit != 3 && nsplit != tf32::F16X3) return CGGP_ERR_INVALID;
+  const int64_t rows = cggp_tf32_rows(n), kp = cggp_tf32_kp(D);
+  if (stream_floats)
+    *stream_floats = (rows / 128) * (tf32::tile_bytes((int)kp, nsplit == 1 ? 1 : 2, nsplit == tf32::F16X3 ? 2 : 4) / 4);
+  if (rows_floats) *rows_floats = nsplit == tf32::F16X3 ? (rows > 0 ? rows : 1) : 1;
   return CGGP_OK;
 }
 
-// 3xFP16 arrays in the buffers cggp_tf32_prepare fills, with `small` longer by the row scales (every entry point
-// below stays as it is; pass nsplit = 16 to the products):  big = [H | L] (2 x rows x KP halfs, the column role),
-// small = [L' | H' (2 x rows x KP halfs, the row role) | 1 / row scale (rows floats)]
-extern "C" int cggp_f16x3_prepare(cggp_ctx* ctx, const void* P, const void* norms, int64_t n, int D, int64_t ldp,
-                                  void* big, void* small, void* norms_pad) {
+extern "C" int cggp_tf32_prepare(cggp_ctx* ctx, int nsplit, const void* P, const void* norms, int64_t n, int D,
+                                 int64_t ldp, void* stream, void* rows_buf, void* norms_pad) {
   if (!ctx) return CGGP_ERR_INVALID;
   if (D < 1 || n < 0) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "bad shape");
+  if (nsplit != 1 && nsplit != 3 && nsplit != tf32::F16X3)
+    CGGP_FAIL(ctx, CGGP_ERR_INVALID, "nsplit must be 1, 3 (TF32) or 16 (3xFP16)");
   const int KP = cggp_tf32_kp(D);
   const int64_t n_pad = cggp_tf32_rows(n);
   if (n_pad == 0) return CGGP_OK;
-  __half* H = (__half*)big;
-  __half* Lp = (__half*)small;
-  float* rinv = (float*)small + n_pad * KP;
-  const int warps = 8;
-  tf32::prepare_f16_kernel<<<(unsigned)((n_pad + warps - 1) / warps), warps * 32, 0, ctx->stream>>>(
-      (const float*)P, (const float*)norms, n, D, ldp, KP, n_pad, H, H + n_pad * KP, Lp, Lp + n_pad * KP, rinv, (float*)norms_pad);
+  if (nsplit == tf32::F16X3) {
+    const int warps = 8;
+    tf32::prepare_f16_kernel<<<(unsigned)((n_pad + warps - 1) / warps), warps * 32, 0, ctx->stream>>>(
+        (const float*)P, (const float*)norms, n, D, ldp, KP, n_pad, (__half*)stream, (float*)rows_buf,
+        (float*)norms_pad);
+  } else {
+    const int64_t total = n_pad * KP;
+    tf32::prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
+        (const float*)P, (const float*)norms, n, D, ldp, KP, n_pad, nsplit == 3 ? 2 : 1, (float*)stream,
+        (float*)norms_pad);
+  }
   CGGP_LAUNCH_CHECK(ctx);
   return CGGP_OK;
 }
@@ -672,7 +767,7 @@ extern "C" int cggp_f16x3_prepare(cggp_ctx* ctx, const void* P, const void* norm
 extern "C" int cggp_tf32_supported(cggp_ctx* ctx, int D, int nsplit);
 bool cggp_matvec_tf32_supported(cggp_ctx* ctx, int D, int nsplit) {
   const int KP = cggp_tf32_kp(D);
-  return ctx->cc_major >= 10 && tf32::stages_for(KP, nsplit, 2) >= 2;
+  return ctx->cc_major >= 10 && tf32::ring_for(KP, nsplit, 2).stages >= 1;
 }
 
 extern "C" int cggp_tf32_supported(cggp_ctx* ctx, int D, int nsplit) {
@@ -684,8 +779,10 @@ extern "C" int cggp_tf32_supported(cggp_ctx* ctx, int D, int nsplit) {
 // alone does not fill the machine (fixed-order reduction of the partials)
 static int gram_sweep(cggp_ctx* ctx, int kind, double variance, int nsplit, int KP, const float* Pb, const float* Ps,
                       const float* pn, int64_t np, const float* Qb, const float* Qs, const float* qn, int64_t nq,
-                      const float* U, int64_t ldu, int B, float* out, int64_t ldo, float* scratch, const int* active) {
+                      const float* U, int64_t ldu, int B, float* out, int64_t ldo, float* scratch, float* upad,
+                      const int* active) {
   using namespace tf32;
+  const int64_t nq_pad = (nq + BN - 1) / BN * BN;  // `upad`: [2][nq_pad] floats
   const int64_t p_blocks = (np + BM - 1) / BM, q_tiles = (nq + BN - 1) / BN;
   // grid.y: 1 when the row set alone fills the machine; else the split count (<= ~6 waves) whose CTA total wastes the
   // least of its last wave (1 CTA per SM: 64 row blocks x 7 splits = 448 CTAs would leave a 4-CTA fourth wave)
@@ -707,51 +804,29 @@ static int gram_sweep(cggp_ctx* ctx, int kind, double variance, int nsplit, int 
   for (int b0 = 0; b0 < B; b0 += 2) {
     const int nb = (B - b0) >= 2 ? 2 : 1;
     KernelFn fn = pick(kind, nsplit, nb);
-    const int stages = stages_for(KP, nsplit, nb);
-    const size_t smem = smem_bytes(KP, nsplit, nb, stages);
+    const RingPlan ring = ring_for(KP, nsplit, nb);
+    const size_t smem = smem_bytes(nsplit, nb, ring);
     CGGP_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     Args a;
     a.Pb = Pb; a.Ps = Ps; a.pn = pn; a.np = np;
     a.Qb = Qb; a.Qs = Qs; a.qn = qn; a.nq = nq;
-    a.U = U + (int64_t)b0 * ldu; a.ldu = ldu;
+    pad_weights_kernel<<<dim3((unsigned)((nq_pad + 255) / 256), (unsigned)nb), 256, 0, ctx->stream>>>(
+        U + (int64_t)b0 * ldu, ldu, nq, nq_pad, upad, active);
+    CGGP_LAUNCH_CHECK(ctx);
+    a.U = upad; a.ldu = nq_pad;
     a.out = splits == 1 ? out + (int64_t)b0 * ldo : scratch;
     a.ldo = splits == 1 ? ldo : np;
     a.np_pad = (np + BM - 1) / BM * BM;
     a.nq_pad = (nq + BN - 1) / BN * BN;
     a.q_tiles_per_split = tiles_per_split;
     a.variance = (float)variance;
-    a.stages = stages;
+    a.stages = ring.stages;
+    a.gc = ring.gc;
+    a.niss = ring.niss;
     a.dbg = getenv("CGGP_TF32_DBG") ? atoi(getenv("CGGP_TF32_DBG")) : 0;
-    a.stamps = nullptr;
-    if (getenv("CGGP_TF32_STAMPS")) {
-      static long long* dev_stamps = nullptr;
-      if (!dev_stamps) cudaMalloc(&dev_stamps, 512 * sizeof(long long));
-      cudaMemsetAsync(dev_stamps, 0, 512 * sizeof(long long), ctx->stream);
-      a.stamps = dev_stamps;
-    }
     a.active = active;
-    fn<<<dim3((unsigned)p_blocks, (unsigned)splits), 352, smem, ctx->stream>>>(a, KP);
+    fn<<<dim3((unsigned)p_blocks, (unsigned)splits), 384, smem, ctx->stream>>>(a, KP);
     CGGP_LAUNCH_CHECK(ctx);
-    if (a.stamps) {
-      static int dumped = 0;
-      if (dumped < 2) {
-        ++dumped;
-        long long h[512];
-        cudaStreamSynchronize(ctx->stream);
-        cudaMemcpy(h, a.stamps, sizeof(h), cudaMemcpyDeviceToHost);
-        const char* names[4] = {"tma", "aux", "mma", "epi"};
-        long long t0 = h[0];
-        for (int r = 0; r < 4; ++r)
-          for (int j = 0; j < 128; ++j)
-            if (h[r * 128 + j] && h[r * 128 + j] < t0) t0 = h[r * 128 + j];
-        for (int r = 0; r < 4; ++r) {
-          printf("stamps %s:", names[r]);
-          for (int j = 0; j < 40; ++j) printf(" %lld", h[r * 128 + j] ? h[r * 128 + j] - t0 : -1);
-          printf("\n");
-        }
-        fflush(stdout);
-      }
-    }
     if (splits > 1) {
       reduce_splits_kernel<<<dim3((unsigned)((np + 255) / 256), (unsigned)nb), 256, 0, ctx->stream>>>(
           scratch, (int)splits, nb, np, np, out + (int64_t)b0 * ldo, ldo, active);
@@ -783,18 +858,21 @@ int cggp_matvec_tf32(cggp_ctx* ctx, int kind, double variance, const float* Xb, 
   // scratch: T [2][n_pad], then the split partials of whichever sweep needs them
   const size_t t_bytes = sizeof(float) * 2 * (size_t)n_pad;
   const size_t sa = gram_scratch_bytes(ctx, n), sb = gram_scratch_bytes(ctx, m);
-  const size_t s_bytes = sa > sb ? sa : sb;
-  int rc = cggp_ws_reserve(ctx, t_bytes + s_bytes + 256);
+  const size_t s_bytes = ((sa > sb ? sa : sb) + 255) / 256 * 256;
+  const int64_t m_pad = cggp_tf32_rows(m);
+  const size_t u_bytes = sizeof(float) * 2 * (size_t)(n_pad > m_pad ? n_pad : m_pad);
+  int rc = cggp_ws_reserve(ctx, t_bytes + s_bytes + u_bytes + 512);
   if (rc) return rc;
   float* T = (float*)ctx->ws;
   float* scratch = (float*)((char*)ctx->ws + t_bytes);
+  float* upad = (float*)((char*)ctx->ws + t_bytes + s_bytes);
   for (int b0 = 0; b0 < B; b0 += 2) {
     const int nb = (B - b0) >= 2 ? 2 : 1;
     rc = gram_sweep(ctx, kind, variance, nsplit, KP, Xb, Xs, xn, n, Zb, Zs, zn, m, V + (int64_t)b0 * ldv, ldv, nb, T,
-                    n_pad, scratch, active);
+                    n_pad, scratch, upad, active);
     if (rc) return rc;
     rc = gram_sweep(ctx, kind, variance, nsplit, KP, Zb, Zs, zn, m, Xb, Xs, xn, n, T, n_pad, nb, W + (int64_t)b0 * ldw,
-                    ldw, scratch, active);
+                    ldw, scratch, upad, active);
     if (rc) return rc;
   }
   return CGGP_OK;
@@ -817,10 +895,11 @@ extern "C" int cggp_kuf_times_tf32(cggp_ctx* ctx, int kind, double variance, con
       CGGP_CUDA(ctx, cudaMemsetAsync((float*)W + (int64_t)b * ldw, 0, sizeof(float) * m, ctx->stream));
     return CGGP_OK;
   }
-  int rc = cggp_ws_reserve(ctx, gram_scratch_bytes(ctx, m) + 256);
+  const size_t s_bytes = (gram_scratch_bytes(ctx, m) + 255) / 256 * 256;
+  int rc = cggp_ws_reserve(ctx, s_bytes + sizeof(float) * 2 * (size_t)cggp_tf32_rows(n) + 512);
   if (rc) return rc;
   ProfScope prof(ctx, 0);
   return gram_sweep(ctx, kind, variance, nsplit, cggp_tf32_kp(D), (const float*)Zb, (const float*)Zs, (const float*)zn,
                     m, (const float*)Xb, (const float*)Xs, (const float*)xn, n, (const float*)Yt, ldy, P, (float*)W, ldw,
-                    (float*)ctx->ws, nullptr);
+                    (float*)ctx->ws, (float*)((char*)ctx->ws + s_bytes), nullptr);
 }

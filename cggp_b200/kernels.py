@@ -56,34 +56,39 @@ def prepare_points(X, lengthscales, dtype=None) -> PreparedPoints:
 
 @dataclass
 class TF32Points:
-    """Prepared float32 points in the layout the tensor cores read (``cggp_tf32_prepare``): canonical K-major order,
-    rows padded to 128, split into a TF32 big and small part; norms padded with zeros."""
+    """Prepared float32 points in the layout the tensor cores read (``cggp_tf32_prepare``): canonical K-major chunks,
+    rows padded to 128; ``big`` = the interleaved arrays the products stream (TF32 big [| small], FP16 H | L),
+    ``small`` = the row-role arrays of the 3xFP16 mode; norms padded with zeros."""
 
     big: torch.Tensor
     small: torch.Tensor
     norms: torch.Tensor
     n: int
     D: int
+    nsplit: int = 3
 
 
 def prepare_tf32(points: PreparedPoints, nsplit: int = 3) -> TF32Points:
-    """Tensor-core operand arrays of prepared float32 points: TF32 big / small (``nsplit`` 1 or 3) or the 3xFP16
-    arrays (``nsplit`` 16), in the same buffers."""
+    """Tensor-core operand arrays of prepared float32 points for ``nsplit`` = 3 (3xTF32), 1 (one TF32 pass) or 16
+    (3xFP16)."""
+    import ctypes as C
+
     if points.P.dtype != torch.float32:
-        raise TypeError("the TF32 tensor-core path is for float32 points")
+        raise TypeError("the tensor-core path is for float32 points")
     ctx = _lib.context(points.P.device)
     ctx.use_current_stream()
-    kp = int(ctx.lib.cggp_tf32_kp(points.D))
     rows = int(ctx.lib.cggp_tf32_rows(points.n))
+    ns, nr = C.c_int64(0), C.c_int64(0)
+    ctx.check(ctx.lib.cggp_tf32_sizes(int(nsplit), points.n, points.D, C.byref(ns), C.byref(nr)))
     dev = points.P.device
-    big = torch.empty((rows * kp,), dtype=torch.float32, device=dev)
-    small = torch.empty((rows * kp + (rows if int(nsplit) == 16 else 0),), dtype=torch.float32, device=dev)
-    norms = torch.empty((rows,), dtype=torch.float32, device=dev)
+    big = torch.empty((max(ns.value, 1),), dtype=torch.float32, device=dev)
+    small = torch.empty((max(nr.value, 1),), dtype=torch.float32, device=dev)
+    norms = torch.empty((max(rows, 1),), dtype=torch.float32, device=dev)
     P = points.P if points.P.stride(1) == 1 else points.P.contiguous()
-    fn = ctx.lib.cggp_f16x3_prepare if int(nsplit) == 16 else ctx.lib.cggp_tf32_prepare
-    ctx.check(fn(ctx.handle, _lib.ptr(P), _lib.ptr(points.norms.contiguous()), points.n,
-                 points.D, P.stride(0), _lib.ptr(big), _lib.ptr(small), _lib.ptr(norms)))
-    return TF32Points(big, small, norms, points.n, points.D)
+    ctx.check(ctx.lib.cggp_tf32_prepare(ctx.handle, int(nsplit), _lib.ptr(P), _lib.ptr(points.norms.contiguous()),
+                                        points.n, points.D, P.stride(0), _lib.ptr(big), _lib.ptr(small),
+                                        _lib.ptr(norms)))
+    return TF32Points(big, small, norms, points.n, points.D, int(nsplit))
 
 
 def kernel_matrix(kind, variance, A: PreparedPoints, B: PreparedPoints, *, output=_lib.OUT_KERNEL,

@@ -64,11 +64,12 @@ class SGPROperator(LinearOperator):
     initialised on the context (``_lib.context().init_comm()``) every application all-reduces the partial product."""
 
     def __init__(self, kernel: Stationary, X, Z, noise_variance: float, jitter: float = 1e-6, variant: int = 0,
-                 tf32_nsplit: int = 3):
+                 tf32_nsplit: int = 16):
         """``variant``: 0 auto, 1 two-sweep kernels, 2 / 3 float64 fused kernels, 4 float32 tensor-core (tcgen05 TF32)
-        kernels - the default for float32 on sm_100 where the tiles fit (D <= 104 with ``tf32_nsplit = 3``).
-        ``tf32_nsplit``: 3 = 3xTF32, 1 = one TF32 pass (fast, ~1e-3 on the distances), 16 = 3xFP16 (float32-accurate
-        like 3xTF32 at twice the tensor-core rate; per-row power-of-two scaling, ``cggp_f16x3_prepare``)."""
+        kernels - the default for float32 on sm_100 where the tiles fit (D <= 128).
+        ``tf32_nsplit`` selects the tensor-core arithmetic: 16 (default) = 3xFP16 with a per-row power-of-two scale
+        (float32-accurate distances at twice the TF32 rate), 3 = 3xTF32 (same accuracy), 1 = one TF32 pass (~1e-3
+        relative on the distances)."""
         self.kernel = kernel
         self.PZ = kernel.prepare(Z)
         self.PX = kernel.prepare(X, self.PZ.P.dtype)
@@ -87,7 +88,7 @@ class SGPROperator(LinearOperator):
                 self.X32 = prepare_tf32(self.PX, self.tf32_nsplit)
                 self.Z32 = prepare_tf32(self.PZ, self.tf32_nsplit)
             elif self.variant == 4:
-                raise _lib.CggpError("the tcgen05 TF32 path needs sm_100 and D <= 128 (3xTF32) / 256 (1xTF32)")
+                raise _lib.CggpError("the tcgen05 path needs sm_100 and D <= 128 (3xFP16, 3xTF32) / 256 (1xTF32)")
 
     def c_struct(self):
         op = _lib.Operator()

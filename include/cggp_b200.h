@@ -127,36 +127,37 @@ int cggp_kuf_kfu_matvec(cggp_ctx* ctx, int dtype, int kind, double variance,
                         const void* dev_PZ, const void* dev_normsZ, int64_t m, int D, int64_t ldp,
                         const void* dev_V, int64_t ldv, int B, void* dev_W, int64_t ldw, int variant);
 
-/* float32 on the 5th-generation tensor cores (tcgen05.mma kind::tf32, FP32 accumulators in TMEM; csrc/matvec_tf32.cu).
+/* float32 on the 5th-generation tensor cores (tcgen05.mma, FP32 accumulators in TMEM; csrc/matvec_tf32.cu).
  * cggp_tf32_prepare converts prepared float32 points ONCE into the layout the tensor cores read: features padded to
  * KP = cggp_tf32_kp(D) (a multiple of 32), rows padded to cggp_tf32_rows(n) (a multiple of 128), 128-row x 32-feature
- * chunks of 16 KB in the UMMA canonical K-major order [row/8][k/4][row%8][k%4], split into
- * a TF32 "big" and a TF32 "small" part (x = big + small to 2^-22), plus the norms padded with zeros.  Buffers:
- * big, small: rows_pad * KP floats each; norms_pad: rows_pad floats.
- * cggp_kuf_kfu_matvec_tf32: W[B, m] = V[B, m] @ (Kuf Kfu) from those arrays; nsplit = 3 -> 3xTF32 (float32-accurate
- * distances), nsplit = 1 -> single TF32 pass (3x fewer tensor-core flops, ~1e-3 relative on the distances),
- * nsplit = 16 -> 3xFP16: the arrays must come from cggp_f16x3_prepare (same buffers, dev_small longer by rows_pad
- * floats): FP16 carries the same 11 significant bits as TF32 at twice the tensor-core rate; a per-row power-of-two
- * scale supplies the exponent range, x 2^s = H + rem, x.z 2^(sx+sz) = H.H + L'.H + H'.L with L' = fp16(rem),
- * L = fp16(rem 2^11), H' = H 2^-11 (kind::f16, FP32 accumulate); only H and L of the streamed point set travel. */
+ * chunks in the UMMA canonical K-major order, the parts of a chunk interleaved ([row tile][K chunk][part]) so that a
+ * tile's operands are one contiguous block = one TMA bulk copy.  `nsplit` selects the arithmetic:
+ *   3  -> 3xTF32 (kind::tf32): x = big + small to 2^-22, x.z = b.b + s.b + b.s; float32-accurate distances
+ *   1  -> one TF32 pass: 3x fewer tensor-core flops, ~1e-3 relative on the distances
+ *   16 -> 3xFP16 (kind::f16): FP16 carries the same 11 significant bits as TF32 at twice the tensor-core rate; a
+ *         per-row power-of-two scale supplies the exponent range: x 2^s = H + R (+ 2^-22),
+ *         x.z 2^(sx+sz) = H.H + R.H + H.R.  Same accuracy as 3xTF32.
+ * Buffers (sizes in floats from cggp_tf32_sizes): dev_stream = the interleaved arrays the products stream (TF32 big
+ * [| small]; FP16 H | R), dev_rows = the 1 / row scales of nsplit 16 (1 float otherwise),
+ * dev_norms_pad = cggp_tf32_rows(n) floats.  The products take the same nsplit the arrays were prepared with.
+ * cggp_kuf_kfu_matvec_tf32: W[B, m] = V[B, m] @ (Kuf Kfu) from those arrays. */
 int cggp_tf32_kp(int D);
 int64_t cggp_tf32_rows(int64_t n);
+int cggp_tf32_sizes(int nsplit, int64_t n, int D, int64_t* stream_floats, int64_t* rows_floats);
 /* 1 if the device is sm_100+ and the row tile fits in tensor memory next to the two accumulators
- * (D <= 128 for nsplit = 3, D <= 256 for nsplit = 1, D <= 160 for nsplit = 16), else 0 */
+ * (D <= 128 for nsplit = 3 and 16, D <= 256 for nsplit = 1), else 0 */
 int cggp_tf32_supported(cggp_ctx* ctx, int D, int nsplit);
-int cggp_tf32_prepare(cggp_ctx* ctx, const void* dev_P, const void* dev_norms, int64_t n, int D, int64_t ldp,
-                      void* dev_big, void* dev_small, void* dev_norms_pad);
-int cggp_f16x3_prepare(cggp_ctx* ctx, const void* dev_P, const void* dev_norms, int64_t n, int D, int64_t ldp,
-                       void* dev_big, void* dev_small, void* dev_norms_pad);
+int cggp_tf32_prepare(cggp_ctx* ctx, int nsplit, const void* dev_P, const void* dev_norms, int64_t n, int D,
+                      int64_t ldp, void* dev_stream, void* dev_rows, void* dev_norms_pad);
 int cggp_kuf_kfu_matvec_tf32(cggp_ctx* ctx, int kind, double variance,
-                             const void* dev_Xbig, const void* dev_Xsmall, const void* dev_xnorms_pad, int64_t n,
-                             const void* dev_Zbig, const void* dev_Zsmall, const void* dev_znorms_pad, int64_t m,
+                             const void* dev_Xstream, const void* dev_Xrows, const void* dev_xnorms_pad, int64_t n,
+                             const void* dev_Zstream, const void* dev_Zrows, const void* dev_znorms_pad, int64_t m,
                              int D, const void* dev_V, int64_t ldv, int B, void* dev_W, int64_t ldw, int nsplit);
 
 /* float32 Kuf @ Y on the tensor cores: W[p, j] = sum_i k(z_j, x_i) Yt[p, i], Y given TRANSPOSED ([P, ldy] row-major) */
 int cggp_kuf_times_tf32(cggp_ctx* ctx, int kind, double variance,
-                        const void* dev_Xbig, const void* dev_Xsmall, const void* dev_xnorms_pad, int64_t n,
-                        const void* dev_Zbig, const void* dev_Zsmall, const void* dev_znorms_pad, int64_t m,
+                        const void* dev_Xstream, const void* dev_Xrows, const void* dev_xnorms_pad, int64_t n,
+                        const void* dev_Zstream, const void* dev_Zrows, const void* dev_znorms_pad, int64_t m,
                         int D, const void* dev_Yt, int64_t ldy, int P, void* dev_W, int64_t ldw, int nsplit);
 
 /* W[p, j] = sum_i k(z_j, x_i) Y[i, p]   (Kuf @ Y over this rank's shard, the right-hand side `Kuf y` of the SGPR
@@ -208,7 +209,7 @@ typedef struct cggp_operator {
   const void* dev_Z32_big;
   const void* dev_Z32_small;
   const void* dev_z32_norms;
-  int32_t tf32_nsplit;  /* 3, 1 or 16 (arrays from cggp_f16x3_prepare) */
+  int32_t tf32_nsplit;  /* 3, 1 or 16: what the arrays were prepared with */
   int32_t _pad2;
 } cggp_operator;
 

@@ -491,7 +491,7 @@ def test_tf32_tensor_core_matvec_vs_oracle(cb, name, N, M, D, B):
     ok = g.KERNELS[name](variance=1.3, lengthscales=ls.astype(np.float64))
     ref = om.kuf_kfu_matmul(ok, X.astype(np.float64), Z.astype(np.float64), V.astype(np.float64))
     k = cb.kernels.KERNELS[name](variance=1.3, lengthscales=ls)
-    op = cb.SGPROperator(k, dev(X), dev(Z), 0.1, variant=4)
+    op = cb.SGPROperator(k, dev(X), dev(Z), 0.1, variant=4, tf32_nsplit=3)
     assert op.X32 is not None
     W = cpu(op.kuf_kfu_matmul(dev(V)))
     assert W.dtype == np.float32
