@@ -3,7 +3,7 @@
 operator  Sigma = Kuu + s^-2 Kuf Kfu  at  N = 2 000 000, M = 4096, D = 11, Matern-5/2  (config c3), N sharded over
 the GPUs of one box (one process per GPU, one NCCL all-reduce of the partial M-vector per iteration).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload c3|c2|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload c3|c2|c1|c4|c5]
 
 A "step" is ONE CG iteration (cggp/conjugate_gradient.py:64-85): one application of Sigma to the search direction
 (fused Kuf Kfu product + all-reduce + Kuu product) and the fused vector update.  The timed region is one call of
@@ -33,7 +33,8 @@ WORKLOADS = {
     "c3": (2_000_000, 4096, 11, "matern52", "CDGP/SGPR CG solve, synthetic houseelectric-shaped (BASELINE configs[2])"),
     "c2": (434_874, 2048, 3, "se", "synthetic 3droad-shaped (BASELINE configs[1])"),
     "c1": (10_000, 500, 2, "se", "synthetic 2-D regression (BASELINE configs[0])"),
-    "c5": (2_000_000, 8192, 90, "se", "float32, YearPredictionMSD-shaped, TF32 distance GEMM (BASELINE configs[4])"),
+    "c4": (8_000_000, 16384, 2, "matern32", "synthetic geospatial-shaped, SGPR system (BASELINE configs[3]; quoted on 8 B200)"),
+    "c5": (2_000_000, 8192, 90, "se", "float32, YearPredictionMSD-shaped, tensor-core distance GEMM (BASELINE configs[4])"),
 }
 FLOAT32 = {"c5"}   # every other workload is float64
 NOISE = 0.1        # likelihood variance, cggp/cli_utils.py:153

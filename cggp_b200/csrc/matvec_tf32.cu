@@ -1,24 +1,27 @@
-// float32 matrix-free product  W = V @ (Kuf Kfu)  on the 5th-generation tensor cores (tcgen05, TF32 inputs, FP32
-// accumulators in TMEM), the float32 counterpart of matvec_pipe.cu (BASELINE configs[4]: N = 2M, D = 90, M = 8192).
+// float32 matrix-free product  W = V @ (Kuf Kfu)  on the 5th-generation tensor cores (tcgen05, FP32 accumulators in
+// TMEM), the float32 counterpart of matvec_pipe.cu (BASELINE configs[4]: N = 2M, D = 90, M = 8192).
 //
-// At D = 90 the distance contraction dominates (2 N M D flop per sweep), so it runs as a TF32 GEMM:
-//   * the scaled points are converted ONCE (cggp_tf32_prepare) into the order the tensor cores read: 128-row tiles x
-//     32-feature chunks, each chunk a contiguous 16 KB block in the UMMA "canonical K-major, no swizzle" order
-//     [row / 8][k / 4][row % 8][k % 4] (LBO = 128 B, SBO = 1 KB), split  x = x_big + x_small  (both round-to-nearest
-//     TF32).  One TMA bulk copy (cp.async.bulk) per chunk drops it into shared memory exactly as the tcgen05
-//     shared-memory descriptors describe it;
-//   * 3xTF32:  x.z ~ xb.zb + xs.zb + xb.zs  (three accumulating MMA groups; the dropped xs.zs term is 2^-22 relative),
-//     which keeps the expanded squared distance at float32 accuracy - a single TF32 pass (NSPLIT = 1) loses ~3 digits
-//     to the cancellation in |x|^2 + |z|^2 - 2 x.z;
+// At D = 90 the distance contraction dominates (2 N M D flop per sweep), so it runs as a tensor-core GEMM:
+//   * cggp_tf32_prepare converts the scaled points ONCE into what the tensor cores read: 128-row tiles x 32-feature
+//     chunks in the UMMA "canonical K-major, no swizzle" order, all parts of all chunks of a tile contiguous and
+//     followed by the tile's per-row scalars, so that a tile (or any run of its chunks) is ONE TMA bulk copy;
+//   * arithmetic (`nsplit`): 3xFP16 (default) - x 2^s = H + R with a per-row power-of-two scale, x.z = H.H + R.H + H.R
+//     (kind::f16, the same 11 significant bits per part as TF32 at twice the rate); 3xTF32 - x = big + small,
+//     b.b + s.b + b.s (kind::tf32); both keep the expanded squared distance at float32 accuracy (dropped term 2^-22);
+//     a single TF32 pass loses ~3 digits to the cancellation in |x|^2 + |z|^2 - 2 x.z;
 //   * generic "gram contraction"  out[b, p] = sum_q k(P_p, Q_q) U[b, q]:  a CTA owns 128 P rows (= the 128 TMEM lanes;
-//     both parts of the P tile live in TENSOR MEMORY as the A operand of every MMA, next to the accumulators) and
-//     loops over 128-column Q tiles that stream through a ring of K-chunk stages in shared memory.  Warp 8 is the TMA producer, warp 9 issues the tcgen05.mma chain (one elected lane each) and commits
-//     onto mbarriers, warp 10 stages the per-column scalars (|q|^2, U); warps 0-7 are the epilogue: tcgen05.ld of a finished accumulator (thread = row, registers = 64
-//     columns), r2 = |p|^2 + |q|^2 - 2 p.q, kernel value with MUFU ex2 / sqrt, dot with U.  Two TMEM accumulators
-//     (2 x 128 columns) let the MMAs of tile j+1 run under the epilogue of tile j.
+//     the parts of the P tile live in TENSOR MEMORY as the A operand of every MMA, next to the accumulators) and walks
+//     128-column Q tiles that stream through a ring of stages in shared memory.  Roles (one elected lane each unless
+//     noted): warp 8 operand producer (one bulk copy per stage), warp 10 weights producer (the per-call U of a tile,
+//     behind the tile's scalars in the same stage), warps 9 and 11 MMA issuers (tiles dealt round-robin; ONE
+//     tcgen05.commit per tile), warps 0-7 epilogue in two groups of four that take every other tile (tcgen05.ld,
+//     thread = row, r2 = |p|^2 + |q|^2 - 2 p.q, kernel value with MUFU ex2 / sqrt, dot with U; the group releases the
+//     tile's stages and its accumulator).  Two (TF32) or three (FP16) TMEM accumulators.
+//   What the clock stamps showed: a tcgen05.commit holds its thread ~550 cycles, a bulk copy ~400, an
+//   MMA issue ~135 (the 128 x 128 x 32-byte instruction itself runs 64) - the kernel is bound by what single threads
+//   can issue per tile, hence few large copies, one commit per tile and two issuers.
 //   The product is two such sweeps:  T = gram(X, Z, V)  then  W = gram(Z, X, T)  (roles swapped, X split over
-//   grid.y with a fixed-order reduction), i.e. every Gram entry is evaluated twice - parking a 128 x 128 FP32 tile per
-//   block would be the next step, as matvec_pipe.cu does for float64.
+//   grid.y with a fixed-order reduction), i.e. every Gram entry is evaluated twice.
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -131,18 +134,9 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
       : "r"(taddr));
 }
 
-// offset (in floats) of element (r, k): [r / 128][k / 32] chunks of 4096 floats, inside a chunk the UMMA canonical
-// K-major order [(r % 128) / 8][(k % 32) / 4][r % 8][k % 4]
-__host__ __device__ inline int64_t canon_off(int64_t r, int k, int KP) {
-  const int64_t chunk = (r >> 7) * (KP >> 5) + (k >> 5);
-  return chunk * 4096 + ((((r & 127) >> 3) * 8 + ((k & 31) >> 2)) * 32) + (r & 7) * 4 + (k & 3);
-}
-// same for the FP16 arrays (offset in halfs): core matrices are 8 rows x 8 halfs (16 bytes per row), a 128-row x
-// 32-feature chunk is 8 KB: [(r % 128) / 8][(k % 32) / 8][r % 8][k % 8] (LBO = 128 B, SBO = 512 B)
-__host__ __device__ inline int64_t canon_off_h(int64_t r, int k, int KP) {
-  const int64_t chunk = (r >> 7) * (KP >> 5) + (k >> 5);
-  return chunk * 4096 + ((((r & 127) >> 3) * 4 + ((k & 31) >> 3)) * 64) + (r & 7) * 8 + (k & 7);
-}
+// Inside a 128-row x 32-feature chunk (4096 elements) the operands sit in the UMMA canonical K-major order:
+// TF32 [(r % 128) / 8][(k % 32) / 4][r % 8][k % 4] (LBO = 128 B, SBO = 1 KB), FP16 [(r % 128) / 8][(k % 32) / 8][r % 8]
+// [k % 8] (core matrices of 8 rows x 16 bytes; LBO = 128 B, SBO = 512 B).
 // The STREAMED arrays keep everything the products need of a 128-row tile in ONE contiguous block:
 //   [K chunk 0: part 0 | part 1] [K chunk 1: ...] ... [trailer: |x|^2 of the 128 rows | 1 / row scale (FP16 mode)]
 // so that any run of consecutive K chunks - all parts, and with the last chunk the per-row scalars - is one TMA bulk
@@ -285,7 +279,6 @@ struct Args {
   int64_t ldo;
   int64_t q_tiles_per_split;
   float variance;
-  int64_t np_pad, nq_pad;  // rows padded to 128 (3xFP16: offsets of the L array and of the row scales)
   int stages;        // ring depth in stages (what fits next to the resident P tile)
   int gc;            // K chunks per stage (divides KP / 32): one TMA bulk copy, one full barrier
   int niss;          // MMA-issuing threads in use (1..3); the ring holds a multiple of `niss` tiles, so that a stage
@@ -816,8 +809,6 @@ static int gram_sweep(cggp_ctx* ctx, int kind, double variance, int nsplit, int 
     a.U = upad; a.ldu = nq_pad;
     a.out = splits == 1 ? out + (int64_t)b0 * ldo : scratch;
     a.ldo = splits == 1 ? ldo : np;
-    a.np_pad = (np + BM - 1) / BM * BM;
-    a.nq_pad = (nq + BN - 1) / BN * BN;
     a.q_tiles_per_split = tiles_per_split;
     a.variance = (float)variance;
     a.stages = ring.stages;
