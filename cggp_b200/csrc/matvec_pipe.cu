@@ -32,8 +32,9 @@
 
 namespace kpipe {
 constexpr int XS = 2;     // X-tile ring stages
-constexpr int SLOTS = 4;  // exchange slot ring: a CTA publishes block j+1 only after it gathered block j, and block j+2
-                          // only after every CTA published j+1 (= finished reading j), so 2 slots would already do
+constexpr int SLOTS = 4;  // exchange slot ring.  Blocks j and j + 2 belong to the same exchange warp in every CTA, which
+                          // publishes j + 2 only after it gathered j; so once a warp has gathered j + 2 (all CTAs
+                          // published it) every CTA is done reading slot j, and the warp may publish j + 4 into it
 
 struct Args {
   const double* PX;
@@ -197,12 +198,12 @@ __device__ __forceinline__ void mbar_arrive(void* bar) {
 constexpr int BAR_T = 1;  // + parity of the block
 
 template <int KIND, int KS, int WARPS, int RB, int CBW, int NB, int NBUF, int ET, int SQ>
-__global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args a) {
+__global__ void __launch_bounds__(WARPS * 32 + 64, 1) kfu_pipe_kernel(const Args a) {
   if (cg_inactive(a.active)) return;
   using L = Layout<WARPS, RB, CBW, NB, KS, NBUF, ET>;
   constexpr int LAG = NBUF - 1;  // phase 2 of block j runs after phase 1 of block j + LAG
   constexpr int THREADS = L::THREADS, BM = L::BM, WN = L::WN, BN = L::BN, LDX = L::LDX;
-  constexpr int ALL = THREADS + 32;  // compute warps + the exchange warp
+  constexpr int ALL = THREADS + 32;  // compute warps + the exchange warp of a block (hand-off barrier T)
   const int g = blockIdx.x / a.C, rank = blockIdx.x % a.C;
   if (g >= a.G) return;  // CTAs beyond the last full group stay idle
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
   const int2* etab = reinterpret_cast<const int2*>(reinterpret_cast<unsigned char*>(mbar) + L::bar_bytes);
   if constexpr (ET != 0) {
     int2* et = const_cast<int2*>(etab);
-    for (int j = tid; j < (1 << ET); j += ALL) et[j] = a.etab[j];
+    for (int j = tid; j < (1 << ET); j += THREADS + 64) et[j] = a.etab[j];
   }
 
   const int64_t nit = a.nblocks > g ? (a.nblocks - g + a.G - 1) / a.G : 0;  // row blocks of this group
@@ -234,11 +235,14 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
   }
   __syncthreads();
 
-  if (warp == WARPS) {
-    // =============================== exchange warp ===============================
-    // Stages X tiles (TMA bulk copies, two blocks ahead), reduces the 16 per-warp partial t, publishes them to the
-    // group through L2, waits for the other CTAs, sums the C partials in rank order and hands t to the compute
-    // warps - all while those are already busy with phase 1 of the next block.
+  if (warp >= WARPS) {
+    // =============================== exchange warps ===============================
+    // Stage X tiles (TMA bulk copies, two blocks ahead), reduce the 16 per-warp partial t, publish them to the
+    // group through L2, wait for the other CTAs, sum the C partials in rank order and hand t to the compute
+    // warps - all while those are already busy with phase 1 of the next block.  TWO such warps take alternate
+    // blocks: the chain of one block (two bulk copies, fence + atomic + poll, C loads from L2: ~3 us) is longer than
+    // phase 1 of a cheap block (D <= 3: ~2 us), and a single warp made it the pace of the kernel.
+    const int ew = warp - WARPS;
     auto stage_tile = [&](int64_t it) {
       if (it >= nit) return;
       const int s = (int)(it % XS);
@@ -262,12 +266,12 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
         if (lane == 0) mbar_arrive(&mbar[s]);  // release: the tile written by the 32 lanes is visible to the waiters
       }
     };
-#pragma unroll
-    for (int s = 0; s < XS; ++s) stage_tile(s);
+    static_assert(XS == 2, "exchange warp w refills X stage w");
+    stage_tile(ew);
     __threadfence_block();
     __syncthreads();  // (S) first tiles staged (manual ones visible)
     double* slots_g = a.part + (int64_t)g * SLOTS * a.C * (BM * NB);
-    for (int64_t it = 0; it < nit; ++it) {
+    for (int64_t it = ew; it < nit; it += 2) {
       const int par = (int)(it % NBUF);
       bar_sync(BAR_T + par, ALL);  // every compute warp finished phase 1 of block it
       stage_tile(it + XS);         // X stage it % XS is free again
@@ -320,8 +324,17 @@ __global__ void __launch_bounds__(WARPS * 32 + 32, 1) kfu_pipe_kernel(const Args
         for (int q = 0; q < (BM * NB + 31) / 32; ++q) {
           const int e = q * 32 + lane;
           if (e < BM * NB) {
+            // the C partials in rank order (same order on every CTA); 16 loads in flight at a time, so that a large
+            // group (M = 16384: 64 CTAs) costs 4 L2 round trips per block instead of one per few partials
             double v = 0.0;
-            for (int c = 0; c < a.C; ++c) v += __ldcg(&sl[(int64_t)c * BM * NB + e]);  // same order on every rank
+            for (int c0 = 0; c0 < a.C; c0 += 16) {
+              double tmp[16];
+#pragma unroll
+              for (int u = 0; u < 16; ++u)
+                tmp[u] = (c0 + u < a.C) ? __ldcg(&sl[(int64_t)(c0 + u) * BM * NB + e]) : 0.0;
+#pragma unroll
+              for (int u = 0; u < 16; ++u) v += tmp[u];
+            }
             sum[q] = v;
           }
         }
@@ -482,7 +495,7 @@ static Plan make_plan() {
   using L = Layout<WARPS, RB, CBW, NB, KS, NBUF, ET>;
   Plan p;
   p.fn = (const void*)kfu_pipe_kernel<KIND, KS, WARPS, RB, CBW, NB, NBUF, ET, SQ>;
-  p.threads = L::THREADS + 32;  // + the exchange warp
+  p.threads = L::THREADS + 64;  // + the two exchange warps
   p.BM = L::BM;
   p.BN = L::BN;
   p.NB = NB;
