@@ -10,8 +10,9 @@ Same names, positional order and return values as the reference:
 
 Extensions, at the same argument positions: ``matrix`` may be a ``LinearOperator`` (``operators.py``); tensors may
 be anything exposing ``__dlpack__``.  The whole loop runs on the device inside ``cggp_cg_solve`` (C ABI); like the
-reference's ``tf.custom_gradient`` the solve is differentiable for dense matrices (backward = a second CG solve,
-``dA = -solution^T db``, conjugate_gradient.py:100-118).
+reference's ``tf.custom_gradient`` the solve is differentiable (backward = a second CG solve, ``dA = -solution^T db``,
+conjugate_gradient.py:100-118): for dense matrices as in the reference, and for the matrix-free ``SGPROperator`` with
+``dA`` pulled back to the kernel hyper-parameters / likelihood variance chunk by chunk (``_SGPRSolveFn``).
 """
 from __future__ import annotations
 
@@ -21,7 +22,7 @@ from typing import Optional, Tuple, Union
 import torch
 
 from . import _lib
-from .operators import DenseOperator, LinearOperator, as_operator
+from .operators import DenseOperator, LinearOperator, SGPROperator, _SGPRSolveFn, as_operator
 
 Tensor = torch.Tensor
 
@@ -205,9 +206,18 @@ def conjugate_gradient(
         max_iterations = n  # :47-48
     cfg = (float(error_threshold), preconditioner, int(max_iterations), int(max_steps_cycle), bool(return_history))
     needs_grad = dense and torch.is_grad_enabled() and (matrix.requires_grad or rhs_t.requires_grad)
+    op_grad = (not dense) and isinstance(matrix, SGPROperator) and torch.is_grad_enabled() and \
+        (matrix.trainable or rhs_t.requires_grad)
     if needs_grad:
         sol, err = _CGFunction.apply(matrix, rhs_t, x0_t, cfg)
         # stats of the forward pass are attached by the Function
+        steps, _, hist = sol.grad_fn.stats if sol.grad_fn is not None and hasattr(sol.grad_fn, "stats") else (-1, None, None)
+    elif op_grad:
+        # matrix-free operator with trainable hyper-parameters (or a right-hand side that needs a gradient)
+        var_t, ls_t = matrix.kernel.param_tensors(rhs_t.dtype, rhs_t.device)
+        noise_t = matrix._noise_t if matrix._noise_t is not None else \
+            torch.tensor(matrix.noise_variance, dtype=rhs_t.dtype, device=rhs_t.device)
+        sol, err = _SGPRSolveFn.apply(var_t, ls_t, noise_t, rhs_t, matrix, x0_t, cfg)
         steps, _, hist = sol.grad_fn.stats if sol.grad_fn is not None and hasattr(sol.grad_fn, "stats") else (-1, None, None)
     else:
         sol, steps, err, hist = _solve(as_operator(matrix), rhs_t, x0_t, *cfg)

@@ -111,6 +111,22 @@ def kernel_matrix(kind, variance, A: PreparedPoints, B: PreparedPoints, *, outpu
     return out
 
 
+def kernel_matrix_param_grads(kind, variance, lengthscales, A: PreparedPoints, B: PreparedPoints, G) -> torch.Tensor:
+    """``[dL/dvariance, dL/dlengthscales (D)]`` of ``K(A, B)`` from ``G = dL/dK`` in one fused, deterministic sweep
+    (``cggp_kernel_matrix_backward``)."""
+    G = _lib.row_major(G.contiguous())
+    c = _lib.context(A.P.device)
+    c.use_current_stream()
+    ls = torch.as_tensor(lengthscales, dtype=torch.float64).reshape(-1).cpu()
+    arr = (C.c_double * ls.numel())(*ls.tolist())
+    g_var = torch.empty((1,), dtype=A.P.dtype, device=A.P.device)
+    g_ls = torch.empty((A.D,), dtype=A.P.dtype, device=A.P.device)
+    c.check(c.lib.cggp_kernel_matrix_backward(
+        c.handle, _lib.dtype_code(A.P.dtype), int(kind), float(variance), _lib.ptr(A.P), A.n, _lib.ptr(B.P), B.n, A.D,
+        A.P.shape[1], arr, ls.numel(), _lib.ptr(G), G.stride(0), _lib.ptr(g_var), _lib.ptr(g_ls)))
+    return torch.cat([g_var, g_ls])
+
+
 class _KernelMatrixFn(torch.autograd.Function):
     """``K(X, X2)`` differentiable in the hyper-parameters: forward = ``cggp_kernel_matrix``, backward =
     ``cggp_kernel_matrix_backward`` (dL/dvariance, dL/dlengthscales from dL/dK in one fused sweep).  No gradient is

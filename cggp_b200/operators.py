@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .kernels import PreparedPoints, Stationary, kernel_matrix, prepare_tf32
+from .kernels import PreparedPoints, Stationary, kernel_matrix, kernel_matrix_param_grads, prepare_tf32
 
 
 class LinearOperator:
@@ -73,7 +73,11 @@ class SGPROperator(LinearOperator):
         self.kernel = kernel
         self.PZ = kernel.prepare(Z)
         self.PX = kernel.prepare(X, self.PZ.P.dtype)
-        self.noise_variance = float(noise_variance)
+        # a tensor that requires grad makes the solve differentiable in the likelihood variance (_SGPRSolveFn)
+        self._noise_t = noise_variance if isinstance(noise_variance, torch.Tensor) and noise_variance.requires_grad \
+            else None
+        self.noise_variance = float(noise_variance.detach()) if isinstance(noise_variance, torch.Tensor) \
+            else float(noise_variance)
         self.jitter = float(jitter)
         self.variant = int(variant)
         self.n = self.PZ.n
@@ -146,6 +150,36 @@ class SGPROperator(LinearOperator):
     def matmul(self, V):
         W = self.kuf_kfu_matmul(V)
         return DenseOperator(self.Kuu).matmul(V) + W / self.noise_variance
+
+    @property
+    def trainable(self) -> bool:
+        return self.kernel.trainable or self._noise_t is not None
+
+    def solve_param_grads(self, sol, lam):
+        """Hyper-parameter gradients of a loss through the solve ``sol Sigma = rhs``, given ``lam = dL/dsol Sigma^-1``
+        (the adjoint solve): ``dL/dSigma = -sol^T lam`` (cggp/conjugate_gradient.py:117), pulled back through
+        ``Sigma = Kuu + Kuf Kfu / s2`` without forming anything of size N x M at once:
+        ``dL/dKuf = -(sol^T (lam Kuf) + lam^T (sol Kuf)) / s2`` chunk by chunk into ``cggp_kernel_matrix_backward``,
+        ``dL/ds2 = sum_b <sol_b Kuf, lam_b Kuf> / s2^2``.  The shard terms are all-reduced.  Returns
+        ``(dL/dvariance [1], dL/dlengthscales [D], dL/ds2 [1])``."""
+        kind, var, ls = self.kernel.kind, self.kernel.variance, self.kernel.lengthscales
+        D, M = self.PZ.D, self.n
+        g = kernel_matrix_param_grads(kind, var, ls, self.PZ, self.PZ, -(sol.t() @ lam))  # replicated Kuu term
+        shard = torch.zeros((2 + D,), dtype=self.dtype, device=self.device)
+        inv = 1.0 / self.noise_variance
+        step = max(1, (1 << 27) // max(M, 1))
+        for s in range(0, self.PX.n, step):
+            rows = self.PX.rows(s, min(self.PX.n, s + step))
+            Kc = kernel_matrix(kind, var, self.PZ, rows)
+            Ts, Tl = sol @ Kc, lam @ Kc
+            dK = torch.addmm(sol.t() @ Tl, lam.t(), Ts).mul_(-inv)
+            shard[: 1 + D] += kernel_matrix_param_grads(kind, var, ls, self.PZ, rows, dK)
+            shard[1 + D] += (Ts * Tl).sum()
+        ctx = _lib.context(self.device)
+        if ctx.world > 1:
+            ctx.allreduce_sum_(shard)
+        g = g + shard[: 1 + D]
+        return g[:1], g[1:], shard[1 + D:] * (inv * inv)
 
     def kuf_times(self, Y):
         """``Kuf @ Y`` for the local shard ``Y [n_local, P]`` (+ all-reduce): the right-hand side ``Kuf y``.
@@ -231,6 +265,43 @@ class SGPROperator(LinearOperator):
         P = self.Kuu + scale * gram
         L = torch.linalg.cholesky(P)
         return DensePreconditioner(torch.cholesky_inverse(L))
+
+
+class _SGPRSolveFn(torch.autograd.Function):
+    """Differentiable matrix-free solve ``sol Sigma = rhs`` on an ``SGPROperator``: forward = the device CG loop,
+    backward = a second CG solve with the incoming gradient as right-hand side (the reference's custom gradient,
+    cggp/conjugate_gradient.py:100-118), ``dL/drhs = lam``, and ``dL/dSigma = -sol^T lam`` pulled back to the kernel
+    hyper-parameters and the likelihood variance by ``SGPROperator.solve_param_grads``."""
+
+    @staticmethod
+    def forward(ctx, variance_t, lengthscales_t, noise_t, rhs, op, v0, cfg):
+        from .conjugate_gradient import _solve
+
+        sol, steps, err, hist = _solve(op, rhs.detach(), None if v0 is None else v0.detach(), *cfg)
+        ctx.save_for_backward(sol)
+        ctx.op, ctx.cfg = op, cfg
+        ctx.shapes = (variance_t, lengthscales_t, noise_t)
+        ctx.stats = (steps, err, hist)
+        ctx.mark_non_differentiable(err)
+        return sol, err
+
+    @staticmethod
+    def backward(ctx, dx, _derr):
+        from .conjugate_gradient import _solve
+
+        (sol,) = ctx.saved_tensors
+        op = ctx.op
+        lam, _, _, _ = _solve(op, dx.contiguous(), None, *ctx.cfg)
+        variance_t, lengthscales_t, noise_t = ctx.shapes
+        g_var = g_ls = g_noise = None
+        if op.trainable:
+            gv, gl, gn = op.solve_param_grads(sol, lam)
+            if lengthscales_t.numel() == 1:
+                gl = gl.sum()
+            g_var = gv.reshape(variance_t.shape).to(variance_t.dtype)
+            g_ls = gl.reshape(lengthscales_t.shape).to(lengthscales_t.dtype)
+            g_noise = gn.reshape(noise_t.shape).to(noise_t.dtype)
+        return g_var, g_ls, g_noise, lam, None, None, None
 
 
 def as_operator(matrix) -> LinearOperator:

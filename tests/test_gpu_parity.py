@@ -584,6 +584,45 @@ def test_matrix_free_cg_matches_oracle(cb, variant):
     assert_history_parity(cpu(h), hist, hist_alt)
 
 
+def test_matrix_free_solve_is_differentiable(cb):
+    """Gradients through the matrix-free CG solve on the SGPR system (backward = a second CG solve + the chunked
+    pull-back of dL/dSigma = -sol^T lam to variance / lengthscales / likelihood variance / rhs) against autograd
+    through a dense solve of the same system built from the differentiable kernel matrices."""
+    rng = np.random.default_rng(11)
+    N, M, D = 3000, 48, 3
+    X = dev(rng.uniform(-2, 2, (N, D)))
+    Z = dev(rng.uniform(-2, 2, (M, D)))
+    w = dev(rng.standard_normal((2, M)))
+    rhs0 = rng.standard_normal((2, M))
+
+    def params():
+        return (torch.tensor(1.3, dtype=torch.float64, device="cuda", requires_grad=True),
+                torch.tensor([1.1, 0.8, 1.4], dtype=torch.float64, device="cuda", requires_grad=True),
+                torch.tensor(0.7, dtype=torch.float64, device="cuda", requires_grad=True),
+                dev(rhs0).clone().requires_grad_(True))
+
+    var, ls, noise, rhs = params()
+    op = cb.SGPROperator(cb.Matern52(var, ls), X, Z, noise, jitter=1e-6)
+    assert op.trainable
+    sol, (steps, err) = cb.conjugate_gradient(op, rhs, None, 1e-28, None, 600, 100000)
+    (sol * w).sum().backward()
+    var2, ls2, noise2, rhs2 = params()
+    k2 = cb.Matern52(var2, ls2)
+    Kzx = k2.K(Z, X)
+    Sigma = k2.K(Z, Z, jitter=1e-6) + Kzx @ Kzx.t() / noise2
+    sol2 = torch.linalg.solve(Sigma.t(), rhs2.t()).t()
+    (sol2 * w).sum().backward()
+    np.testing.assert_allclose(cpu(sol.detach()), cpu(sol2.detach()), rtol=1e-8, atol=1e-10)
+    for a, b in ((var, var2), (ls, ls2), (noise, noise2), (rhs, rhs2)):
+        np.testing.assert_allclose(cpu(a.grad), cpu(b.grad), rtol=2e-6, atol=1e-9 * float(b.grad.abs().max()))
+    # fixed hyper-parameters: only the right-hand side gets a gradient, nothing else is touched
+    rhs3 = dev(rhs0).clone().requires_grad_(True)
+    op3 = cb.SGPROperator(cb.Matern52(1.3, [1.1, 0.8, 1.4]), X, Z, 0.7, jitter=1e-6)
+    sol3, _ = cb.conjugate_gradient(op3, rhs3, None, 1e-28, None, 600, 100000)
+    (sol3 * w).sum().backward()
+    np.testing.assert_allclose(cpu(rhs3.grad), cpu(rhs2.grad), rtol=2e-6, atol=1e-12)
+
+
 # ------------------------------------------------------------------------------------------------ models
 def build_models(cb, c):
     name = str(c["kernel"])
