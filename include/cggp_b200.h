@@ -145,7 +145,7 @@ int cggp_tf32_kp(int D);
 int64_t cggp_tf32_rows(int64_t n);
 int cggp_tf32_sizes(int nsplit, int64_t n, int D, int64_t* stream_floats, int64_t* rows_floats);
 /* 1 if the device is sm_100+ and the row tile fits in tensor memory next to the two accumulators
- * (D <= 128 for nsplit = 3 and 16, D <= 256 for nsplit = 1), else 0 */
+ * (D <= 128: the limit of cggp_prepare_points), else 0 */
 int cggp_tf32_supported(cggp_ctx* ctx, int D, int nsplit);
 int cggp_tf32_prepare(cggp_ctx* ctx, int nsplit, const void* dev_P, const void* dev_norms, int64_t n, int D,
                       int64_t ldp, void* dev_stream, void* dev_rows, void* dev_norms_pad);

@@ -59,6 +59,29 @@ def test_prepared_ld_and_version(lib):
     assert b"sm_100a" in lib.cggp_version()
 
 
+def test_tensor_core_buffer_sizes(lib):
+    """Host-side size queries of the float32 tensor-core arrays (no GPU needed): rows padded to 128, features to 32,
+    one 1 KB trailer of per-row scalars per 128-row tile; the 3xFP16 mode adds one scale per row."""
+    lib.cggp_tf32_rows.restype = ctypes.c_int64
+    lib.cggp_tf32_rows.argtypes = [ctypes.c_int64]
+    lib.cggp_tf32_sizes.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(ctypes.c_int64),
+                                    ctypes.POINTER(ctypes.c_int64)]
+    assert [lib.cggp_tf32_kp(d) for d in (1, 32, 33, 90)] == [32, 32, 64, 96]
+    assert [lib.cggp_tf32_rows(n) for n in (0, 1, 128, 129)] == [0, 128, 128, 256]
+    ns, nr = ctypes.c_int64(), ctypes.c_int64()
+    for nsplit, parts, esz, rows_extra in ((1, 1, 4, False), (3, 2, 4, False), (16, 2, 2, True)):
+        assert lib.cggp_tf32_sizes(nsplit, 1000, 90, ctypes.byref(ns), ctypes.byref(nr)) == 0
+        tiles, kp = 8, 96
+        assert ns.value * 4 == tiles * ((kp // 32) * parts * 4096 * esz + 1024)
+        assert nr.value == (1024 if rows_extra else 1)
+    assert lib.cggp_tf32_sizes(2, 1000, 90, ctypes.byref(ns), ctypes.byref(nr)) != 0
+    # the FP16 stream is half the bytes of the 3xTF32 one (the SASS must hold the kind::f16 tensor-core path)
+    out = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "cggp_b200", "libcggp_b200.so")],
+                         capture_output=True, text=True)
+    if out.returncode == 0:
+        assert "UTCHMMA" in out.stdout or "UTCMMA" in out.stdout or "tcgen05" in out.stdout.lower()
+
+
 def test_no_cpu_fallback_and_no_oracle_in_product():
     import torch
 

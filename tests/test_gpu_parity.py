@@ -541,6 +541,26 @@ def test_f16x3_tensor_core_matvec_vs_oracle(cb, name, N, M, D, B):
     np.testing.assert_allclose(cpu(op.kuf_times(dev(Y))), kref, rtol=1e-4, atol=1e-4 * np.abs(kref).max())
 
 
+@pytest.mark.parametrize("D,nsplit,tol", [(100, 16, 1e-4), (128, 16, 1e-4), (128, 3, 1e-4), (100, 3, 1e-4),
+                                          (128, 1, 2e-2), (96, 1, 2e-2), (33, 16, 1e-4), (64, 3, 1e-4)])
+def test_tensor_core_matvec_wide_features(cb, D, nsplit, tol):
+    """Feature counts that exercise the other ring plans of the tcgen05 kernel (several K chunks per stage, one
+    issuer, a single tile in the ring) against the float64 oracle."""
+    rng = np.random.default_rng(D + nsplit)
+    N, M, B = 1500, 260, 2
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    Z = rng.standard_normal((M, D)).astype(np.float32)
+    V = rng.standard_normal((B, M)).astype(np.float32)
+    ls = np.full(D, np.sqrt(D), np.float32)
+    ok = g.SquaredExponential(variance=0.9, lengthscales=ls.astype(np.float64))
+    ref = om.kuf_kfu_matmul(ok, X.astype(np.float64), Z.astype(np.float64), V.astype(np.float64))
+    op = cb.SGPROperator(cb.SquaredExponential(0.9, ls), dev(X), dev(Z), 0.1, variant=4, tf32_nsplit=nsplit)
+    assert op.X32 is not None
+    W = cpu(op.kuf_kfu_matmul(dev(V)))
+    np.testing.assert_allclose(W, ref, rtol=tol, atol=tol * np.abs(ref).max())
+    assert np.array_equal(W, cpu(op.kuf_kfu_matmul(dev(V))))
+
+
 def test_tf32_operator_inside_cg(cb):
     rng = np.random.default_rng(77)
     N, M, D = 5000, 128, 40
