@@ -357,6 +357,14 @@ def run_native(args):
         "sections_ms": {k: round(v[0], 4) for k, v in prof.items()},
         "gentries_per_s": (n_local * M / (mv_ms / mv_cnt * 1e-3) / 1e9) if mv_cnt else None,
     }
+    if not f32w and achieved and peak_tflops:
+        # what the FP64 pipe actually executes per Gram entry (SASS count of the tile loop): the DMMA
+        # distance (4 ceil((D+1)/4) FMA) + sqrt / exp / polynomial / contractions - the algorithmic D + 2 FMA of
+        # `achieved` leave the transcendental work out
+        slots = 4 * ((D + 4) // 4) + (17.75 if kern.startswith("matern") else 9.75)
+        roofline["executed"] = {"fp64_fma_slots_per_entry": slots,
+                                "frac_of_peak": achieved / peak_tflops * slots / (D + 2),
+                                "note": "FP64-pipe occupancy by executed FMA slots; `frac` counts algorithmic flop only"}
 
     hbm = None
     try:
