@@ -387,6 +387,8 @@ def run_native(args):
                             f"D={D}, {kern}, B=1 right-hand side; {desc}",
                 "operator": "Kuu + jitter I + Kuf Kfu / noise_variance, matrix-free (Kfu never materialised)",
                 "step": "one CG iteration: fused Kuf Kfu product + all-reduce + Kuu product + fused vector update",
+                "allreduce": (("one-shot kernel over NVLink peer memory (rank-ordered sum)" if ctx.peer_allreduce
+                               else "ncclAllReduce") if world > 1 else "none (one rank)"),
                 "l2": "inputs larger than L2: prepared X shard %.0f MB + Kuu %.0f MB streamed every iteration (126 MB L2)"
                       % (n_local * (4 * ((D + 4) // 4)) * esize / 1e6, M * M * esize / 1e6),
                 "seconds_per_solve": f"{ms_max * 1e-3:.4f} s for {args.steps} iterations (threshold 0, fixed count)",

@@ -229,7 +229,9 @@ extern "C" int cggp_ctx_comm_init(cggp_ctx* ctx, const void* host_id128, int ran
   return CGGP_OK;
 }
 
+extern "C" int cggp_peer_close(cggp_ctx* ctx);
 extern "C" int cggp_ctx_comm_destroy(cggp_ctx* ctx) {
+  cggp_peer_close(ctx);
   if (!ctx) return CGGP_ERR_INVALID;
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   ctx->comm = nullptr;
@@ -238,9 +240,134 @@ extern "C" int cggp_ctx_comm_destroy(cggp_ctx* ctx) {
   return CGGP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// One-shot all-reduce over NVLink peer memory.  The per-iteration collective of the path is tiny (M x 8 bytes = 32 KiB
+// at c3): NCCL spends ~60 us on it, most of it launch and protocol latency.  Here every rank copies its vector into a
+// slot of its own IPC-shared buffer, publishes a sequence number, waits for the other ranks' numbers and sums all
+// slots in RANK ORDER straight out of peer memory (NVLink loads) - one kernel, bit-identical results on all ranks.
+// Two slots alternate: a rank reaches call k + 2 only after every peer has published k + 1, i.e. finished reading k.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <typename T>
+__global__ void peer_allreduce_kernel(T* __restrict__ buf, int64_t count, char* const* __restrict__ peers, int rank,
+                                      int world, unsigned seq, int64_t slot_bytes, int* __restrict__ counter) {
+  const int slot = (int)(seq & 1u);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  T* mine = reinterpret_cast<T*>(peers[rank] + slot * slot_bytes);
+  if (i < count) mine[i] = buf[i];
+  __syncthreads();  // the block's stores are ordered before thread 0's fence (cumulativity through the barrier)
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(counter, 1) == (int)gridDim.x - 1) {  // the last block of this rank: the whole vector is in the slot
+      *counter = 0;
+      __threadfence_system();
+      st_release_sys(reinterpret_cast<unsigned*>(peers[rank] + 2 * slot_bytes) + slot, seq);
+    }
+    for (int r = 0; r < world; ++r) {
+      const unsigned* flag = reinterpret_cast<const unsigned*>(peers[r] + 2 * slot_bytes) + slot;
+      while ((int)(ld_acquire_sys(flag) - seq) < 0) {
+      }
+    }
+  }
+  __syncthreads();
+  if (i < count) {
+    T v = T(0);
+    for (int r = 0; r < world; ++r) v += __ldcv(reinterpret_cast<const T*>(peers[r] + slot * slot_bytes) + i);
+    buf[i] = v;
+  }
+}
+
+extern "C" int cggp_peer_close(cggp_ctx* ctx) {
+  if (!ctx) return CGGP_OK;
+  for (int r = 0; r < ctx->peer_world; ++r)
+    if (ctx->peer_ptrs_host[r] && ctx->peer_ptrs_host[r] != ctx->peer_local) cudaIpcCloseMemHandle(ctx->peer_ptrs_host[r]);
+  if (ctx->peer_ptrs_dev) cudaFree(ctx->peer_ptrs_dev);
+  if (ctx->peer_counter) cudaFree(ctx->peer_counter);
+  if (ctx->peer_local) cudaFree(ctx->peer_local);
+  for (int r = 0; r < 16; ++r) ctx->peer_ptrs_host[r] = nullptr;
+  ctx->peer_ptrs_dev = nullptr;
+  ctx->peer_counter = nullptr;
+  ctx->peer_local = nullptr;
+  ctx->peer_world = 0;
+  ctx->peer_seq = 0;
+  return CGGP_OK;
+}
+
+// step 1 (every rank): allocate this rank's buffer (2 slots of slot_bytes + flags) and export its 64-byte IPC handle
+extern "C" int cggp_peer_alloc(cggp_ctx* ctx, int64_t slot_bytes, void* host_handle64) {
+  if (!ctx || !host_handle64 || slot_bytes <= 0) return CGGP_ERR_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cggp_peer_close(ctx);
+  slot_bytes = (slot_bytes + 255) / 256 * 256;
+  CGGP_CUDA(ctx, cudaMalloc(&ctx->peer_local, (size_t)(2 * slot_bytes + 256)));
+  CGGP_CUDA(ctx, cudaMemset(ctx->peer_local, 0, (size_t)(2 * slot_bytes + 256)));
+  CGGP_CUDA(ctx, cudaMalloc(&ctx->peer_counter, sizeof(int)));
+  CGGP_CUDA(ctx, cudaMemset(ctx->peer_counter, 0, sizeof(int)));
+  cudaIpcMemHandle_t h;
+  CGGP_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->peer_local));
+  memcpy(host_handle64, &h, 64);
+  ctx->peer_slot_bytes = slot_bytes;
+  CGGP_CUDA(ctx, cudaDeviceSynchronize());
+  return CGGP_OK;
+}
+
+// step 2 (every rank, after the handles went round): map all ranks' buffers; `host_handles` = world x 64 bytes in rank
+// order.  Call only after cggp_ctx_comm_init (rank / world).
+extern "C" int cggp_peer_open(cggp_ctx* ctx, const void* host_handles, int world) {
+  if (!ctx || !host_handles) return CGGP_ERR_INVALID;
+  if (!ctx->peer_local) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "cggp_peer_alloc first");
+  if (world != ctx->world || world < 2 || world > 16) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "peer table: bad world size %d", world);
+  for (int r = 0; r < world; ++r) {
+    if (r == ctx->rank) {
+      ctx->peer_ptrs_host[r] = ctx->peer_local;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)host_handles + 64 * r, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      ctx->peer_world = r;  // close what was opened
+      cggp_peer_close(ctx);
+      CGGP_FAIL(ctx, CGGP_ERR_COMM, "cudaIpcOpenMemHandle (rank %d): %s", r, cudaGetErrorString(e));
+    }
+    ctx->peer_ptrs_host[r] = p;
+  }
+  ctx->peer_world = world;
+  CGGP_CUDA(ctx, cudaMalloc((void**)&ctx->peer_ptrs_dev, sizeof(void*) * 16));
+  CGGP_CUDA(ctx, cudaMemcpy(ctx->peer_ptrs_dev, ctx->peer_ptrs_host, sizeof(void*) * 16, cudaMemcpyHostToDevice));
+  ctx->peer_seq = 0;
+  return CGGP_OK;
+}
+
+extern "C" int cggp_peer_enabled(cggp_ctx* ctx) { return ctx && ctx->peer_ptrs_dev && ctx->peer_world == ctx->world; }
+
 extern "C" int cggp_allreduce_sum(cggp_ctx* ctx, int dtype, void* buf, int64_t count) {
   if (!ctx) return CGGP_ERR_INVALID;
   if (ctx->world == 1 || count == 0) return CGGP_OK;
+  const int64_t bytes = count * (dtype == CGGP_F64 ? 8 : 4);
+  if (cggp_peer_enabled(ctx) && bytes <= ctx->peer_slot_bytes) {
+    ProfScope prof(ctx, 3);
+    const unsigned seq = ++ctx->peer_seq;
+    const unsigned blocks = (unsigned)((count + 1023) / 1024);  // <= 128 blocks of 1024 threads: all co-resident
+    if (dtype == CGGP_F64)
+      peer_allreduce_kernel<double><<<blocks, 1024, 0, ctx->stream>>>((double*)buf, count, (char* const*)ctx->peer_ptrs_dev,
+                                                                     ctx->rank, ctx->world, seq, ctx->peer_slot_bytes,
+                                                                     ctx->peer_counter);
+    else
+      peer_allreduce_kernel<float><<<blocks, 1024, 0, ctx->stream>>>((float*)buf, count, (char* const*)ctx->peer_ptrs_dev,
+                                                                    ctx->rank, ctx->world, seq, ctx->peer_slot_bytes,
+                                                                    ctx->peer_counter);
+    CGGP_LAUNCH_CHECK(ctx);
+    return CGGP_OK;
+  }
   if (!ctx->comm) CGGP_FAIL(ctx, CGGP_ERR_COMM, "communicator not initialised");
   const int nccl_dtype = dtype == CGGP_F64 ? 8 : 7;  // ncclFloat64 / ncclFloat32
   ProfScope prof(ctx, 3);

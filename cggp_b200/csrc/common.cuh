@@ -26,6 +26,15 @@ struct cggp_ctx {
   // NCCL (dlopen'ed)
   void* comm = nullptr;
   int rank = 0, world = 1;
+  // one-shot all-reduce over NVLink peer memory for the small per-iteration vectors (cggp_peer_*): every rank's
+  // buffer = two data slots + two flags, mapped into every other rank through CUDA IPC
+  void* peer_local = nullptr;        // this rank's buffer (cudaMalloc)
+  void* peer_ptrs_host[16] = {};     // all ranks' buffers as seen from this process
+  void** peer_ptrs_dev = nullptr;    // the same table on the device
+  int peer_world = 0;
+  int64_t peer_slot_bytes = 0;
+  unsigned peer_seq = 0;
+  int* peer_counter = nullptr;
   // optional per-section device timing (cggp_profile_*): event pairs recorded on the ctx stream
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev[CGGP_PROF_SECTIONS];  // start, stop, start, stop, ...

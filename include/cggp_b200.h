@@ -67,8 +67,19 @@ int cggp_profile_read(cggp_ctx* ctx, int section, double* host_ms_total, int64_t
 int cggp_comm_unique_id(void* host_id128);
 int cggp_ctx_comm_init(cggp_ctx* ctx, const void* host_id128, int rank, int world);
 int cggp_ctx_comm_destroy(cggp_ctx* ctx);
-/* In-place sum all-reduce of `count` elements on the ctx stream (no-op when world == 1). */
+/* In-place sum all-reduce of `count` elements on the ctx stream (no-op when world == 1): ncclAllReduce, or - when
+ * the peer buffers below have been set up and the vector fits a slot - ONE kernel over NVLink peer memory: every rank
+ * publishes its vector in its own IPC-shared buffer and sums all ranks' slots in rank order (bit-identical on all
+ * ranks).  Measured on 2 B200 for the 32 KiB vector of c3: 31 us against NCCL's 24 us per call, both dominated by
+ * waiting for the slower rank; the Python layer therefore sets the peers up only on request (CGGP_PEER_ALLREDUCE=1). */
 int cggp_allreduce_sum(cggp_ctx* ctx, int dtype, void* dev_buf, int64_t count);
+/* Peer buffers of the one-shot all-reduce (after cggp_ctx_comm_init; ranks of ONE node): cggp_peer_alloc allocates
+ * this rank's buffer (two slots of slot_bytes + flags) and writes its 64-byte CUDA IPC handle; the host sends the
+ * handles round (torch.distributed all_gather); cggp_peer_open maps all ranks' buffers (world x 64 bytes, rank order). */
+int cggp_peer_alloc(cggp_ctx* ctx, int64_t slot_bytes, void* host_handle64);
+int cggp_peer_open(cggp_ctx* ctx, const void* host_handles, int world);
+int cggp_peer_close(cggp_ctx* ctx);
+int cggp_peer_enabled(cggp_ctx* ctx);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Kernel evaluation  (replaces the GPflow calls at cggp/models.py:112,141-143,236,255-257,300,333-335 and
