@@ -494,15 +494,30 @@ __global__ void __launch_bounds__(384, 1) gram_contract_kernel(const Args a, con
       // from shared memory) and frees 96 KB for a deeper Q ring.
       const int kper = KP / 2;  // KP is a multiple of 32
       if constexpr (F16) {
+        // all loads of the thread's row first (one round trip to memory instead of one per 16 features: the tile
+        // loop cannot start before the P tile is in place, and a CTA lives for only ~64 tiles), then the stores
         const __half* PH = reinterpret_cast<const __half*>(a.Pb);
-        for (int part = 0; part < 2; ++part) {
-          for (int k0 = half * kper; k0 < (half + 1) * kper; k0 += 16) {
-            const uint4 x0 = *reinterpret_cast<const uint4*>(PH + stream_off_h(p, k0, KP, 2, part));
-            const uint4 x1 = *reinterpret_cast<const uint4*>(PH + stream_off_h(p, k0 + 8, KP, 2, part));
-            const uint32_t v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-            tmem_st8(tmem_base + ((uint32_t)(quarter * 32) << 16) + TM_P + (uint32_t)(part * (KP / 2) + k0 / 2), v);
-          }
-        }
+        const int cnt = kper / 16;  // <= 4: KP <= 128 in this mode
+        uint4 x[2][8];
+#pragma unroll
+        for (int part = 0; part < 2; ++part)
+#pragma unroll
+          for (int it = 0; it < 4; ++it)
+            if (it < cnt) {
+              const int k0 = half * kper + it * 16;
+              x[part][2 * it] = *reinterpret_cast<const uint4*>(PH + stream_off_h(p, k0, KP, 2, part));
+              x[part][2 * it + 1] = *reinterpret_cast<const uint4*>(PH + stream_off_h(p, k0 + 8, KP, 2, part));
+            }
+#pragma unroll
+        for (int part = 0; part < 2; ++part)
+#pragma unroll
+          for (int it = 0; it < 4; ++it)
+            if (it < cnt) {
+              const int k0 = half * kper + it * 16;
+              const uint4 x0 = x[part][2 * it], x1 = x[part][2 * it + 1];
+              const uint32_t v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+              tmem_st8(tmem_base + ((uint32_t)(quarter * 32) << 16) + TM_P + (uint32_t)(part * (KP / 2) + k0 / 2), v);
+            }
       } else
       for (int part = 0; part < PARTS; ++part) {
         const float* src = a.Pb;

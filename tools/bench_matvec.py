@@ -63,7 +63,7 @@ def main_f32():
               f"{2 * N * M / best / 1e6:.1f} Gentry/s (two sweeps)", flush=True)
         if nsplit == 16:
             W16 = op.kuf_kfu_matmul(V)
-    op = cb.SGPROperator(k, X, Z, 0.1, variant=4)
+    op = cb.SGPROperator(k, X, Z, 0.1, variant=4, tf32_nsplit=3)
     W4 = op.kuf_kfu_matmul(V)
     print(f"c5/4: max rel diff 3xFP16 vs 3xTF32 {float((W16 - W4).abs().max() / W4.abs().max()):.3e}", flush=True)
     best1, _ = timeit(lambda: op.kuf_kfu_matmul(V, variant=1), reps=2, warm=1)
