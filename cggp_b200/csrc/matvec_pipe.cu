@@ -504,8 +504,7 @@ static Plan make_plan() {
 }
 
 // `deep`: three K buffers of 32 rows instead of two of 48, i.e. the group exchange of a block has TWO phase-1 periods
-// to complete.  The default for one right-hand side (with the two exchange warps it is never slower; it wins where the
-// group is large - M = 16384: 64 CTAs to wait for - or phase 1 is cheap).
+// to complete.  Chosen where the group is large (M = 16384: 64 CTAs to wait for) or phase 1 is cheap (D <= 3).
 template <int KIND, int KS>
 static bool plan_for_nb(int nb, bool deep, int et, Plan& p) {
   // et = 10 (default for one right-hand side): 1024-entry shared-memory exp table (degree-3 polynomial) + third-order
@@ -597,8 +596,10 @@ static int pipe_launch(cggp_ctx* ctx, int kind, double variance, const double* P
     const int nb = (B - b0) >= 2 ? 2 : 1;
     Plan p;
     static const int deep_env = getenv("CGGP_PIPE_DEEP") ? atoi(getenv("CGGP_PIPE_DEEP")) : -1;  // tuning knob
-    // measured with the two exchange warps (one right-hand side): c2 1.56 vs 1.65 ms, c3 20.39 vs 20.40, c4 wins big
-    const bool deep = deep_env >= 0 ? deep_env != 0 : (nb == 1 || m > 8192);
+    // measured with the two exchange warps (one right-hand side, ms deep / not): c2 (D = 3) 1.56 / 1.65, c4 shape
+    // (M = 16384) wins big; c3 (D = 11) 20.39 / 20.40 at N = 2M but 2.600 / 2.562 at an 8-GPU shard of 250k rows:
+    // three buffers where phase 1 is cheap (one DMMA k-step) or the group is large, two otherwise
+    const bool deep = deep_env >= 0 ? deep_env != 0 : ((nb == 1 && ks <= 1) || m > 8192);
     static const int et_env = getenv("CGGP_PIPE_ET") ? atoi(getenv("CGGP_PIPE_ET")) : 10;  // tuning knob
     const int et = (nb == 1 && et_env == 10) ? 10 : 0;
     if (!plan_for(kind, ks, nb, deep, et, p)) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "pipelined matvec: no plan for D=%d", D);
