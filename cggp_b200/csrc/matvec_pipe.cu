@@ -629,7 +629,8 @@ static int pipe_launch(cggp_ctx* ctx, int kind, double variance, const double* P
     a.part = (double*)(base + wp_bytes);
     a.counters = (int*)(base + wp_bytes + part_bytes);
     a.C = C; a.G = G; a.nblocks = nblocks; a.active = active;
-    a.dbg = getenv("CGGP_PIPE_DBG") ? atoi(getenv("CGGP_PIPE_DBG")) : 0;
+    static const int dbg_env = getenv("CGGP_PIPE_DBG") ? atoi(getenv("CGGP_PIPE_DBG")) : 0;  // timing experiments
+    a.dbg = dbg_env;
     a.etab = nullptr;
     if (et == 10) {
       rc = cggp_exp_tables(ctx, &a.etab);

@@ -829,7 +829,8 @@ static int gram_sweep(cggp_ctx* ctx, int kind, double variance, int nsplit, int 
     a.stages = ring.stages;
     a.gc = ring.gc;
     a.niss = ring.niss;
-    a.dbg = getenv("CGGP_TF32_DBG") ? atoi(getenv("CGGP_TF32_DBG")) : 0;
+    static const int dbg_env = getenv("CGGP_TF32_DBG") ? atoi(getenv("CGGP_TF32_DBG")) : 0;  // timing experiments
+    a.dbg = dbg_env;
     a.active = active;
     fn<<<dim3((unsigned)p_blocks, (unsigned)splits), 384, smem, ctx->stream>>>(a, KP);
     CGGP_LAUNCH_CHECK(ctx);
