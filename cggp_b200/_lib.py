@@ -86,6 +86,8 @@ SIGNATURES = {
     "cggp_tf32_kp": (_i, [_i]),
     "cggp_tf32_rows": (_i64, [_i64]),
     "cggp_tf32_supported": (_i, [_vp, _i, _i]),
+    "cggp_tf32_ring_plan": (_i, [_i, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                 C.POINTER(C.c_int64)]),
     "cggp_tf32_sizes": (_i, [_i, _i64, _i, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "cggp_tf32_prepare": (_i, [_vp, _i, _vp, _vp, _i64, _i, _i64, _vp, _vp, _vp]),
     "cggp_kuf_kfu_matvec_tf32": (_i, [_vp, _i, _d, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _vp,

@@ -772,6 +772,18 @@ extern "C" int cggp_tf32_prepare(cggp_ctx* ctx, int nsplit, const void* P, const
   return CGGP_OK;
 }
 
+// The shared-memory ring the kernel would run with (host-side query, no GPU needed; tests check its invariants):
+// K chunks per stage, stages, MMA-issuing threads, dynamic shared memory.  0 stages = does not fit.
+extern "C" int cggp_tf32_ring_plan(int nsplit, int D, int nb, int* gc, int* stages, int* niss, int64_t* smem_bytes_out) {
+  if (D < 1 || nb < 1 || nb > 2 || (nsplit != 1 && nsplit != 3 && nsplit != tf32::F16X3)) return CGGP_ERR_INVALID;
+  const tf32::RingPlan r = tf32::ring_for(cggp_tf32_kp(D), nsplit, nb);
+  if (gc) *gc = r.gc;
+  if (stages) *stages = r.stages;
+  if (niss) *niss = r.niss;
+  if (smem_bytes_out) *smem_bytes_out = r.stages ? (int64_t)tf32::smem_bytes(nsplit, nb, r) : 0;
+  return CGGP_OK;
+}
+
 extern "C" int cggp_tf32_supported(cggp_ctx* ctx, int D, int nsplit);
 bool cggp_matvec_tf32_supported(cggp_ctx* ctx, int D, int nsplit) {
   const int KP = cggp_tf32_kp(D);

@@ -158,6 +158,9 @@ int cggp_tf32_sizes(int nsplit, int64_t n, int D, int64_t* stream_floats, int64_
 /* 1 if the device is sm_100+ and the row tile fits in tensor memory next to the two accumulators
  * (D <= 128: the limit of cggp_prepare_points), else 0 */
 int cggp_tf32_supported(cggp_ctx* ctx, int D, int nsplit);
+/* host-side query of the kernel's shared-memory ring for feature count D and nb (1 or 2) right-hand sides: K chunks per
+ * stage, stages (0 = does not fit), MMA-issuing threads, dynamic shared memory in bytes */
+int cggp_tf32_ring_plan(int nsplit, int D, int nb, int* gc, int* stages, int* niss, int64_t* smem_bytes);
 int cggp_tf32_prepare(cggp_ctx* ctx, int nsplit, const void* dev_P, const void* dev_norms, int64_t n, int D,
                       int64_t ldp, void* dev_stream, void* dev_rows, void* dev_norms_pad);
 int cggp_kuf_kfu_matvec_tf32(cggp_ctx* ctx, int kind, double variance,

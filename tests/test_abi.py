@@ -82,6 +82,35 @@ def test_tensor_core_buffer_sizes(lib):
         assert "UTCHMMA" in out.stdout or "UTCMMA" in out.stdout or "tcgen05" in out.stdout.lower()
 
 
+def test_tensor_core_ring_plans_keep_their_invariants(lib):
+    """The tcgen05 kernel releases a tile's stages together and deals tiles round-robin to its MMA-issuing threads:
+    the ring must hold whole tiles, a whole multiple of `niss` of them (every stage always consumed by the same
+    issuer), and fit the 227 KB of shared memory - for every feature count and arithmetic mode."""
+    lib.cggp_tf32_ring_plan.argtypes = [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int)] * 3 + \
+        [ctypes.POINTER(ctypes.c_int64)]
+    gc, st, ni, sm = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
+    seen = set()
+    for nsplit in (1, 3, 16):
+        for nb in (1, 2):
+            for D in range(1, 129):
+                assert lib.cggp_tf32_ring_plan(nsplit, D, nb, ctypes.byref(gc), ctypes.byref(st), ctypes.byref(ni),
+                                               ctypes.byref(sm)) == 0
+                nchunk = lib.cggp_tf32_kp(D) // 32
+                parts_cols = (1 if nsplit == 1 else 2) * lib.cggp_tf32_kp(D) // (2 if nsplit == 16 else 1)
+                if st.value == 0:
+                    # only when the row tile does not fit tensor memory next to the accumulators
+                    assert parts_cols > (128 if nsplit == 16 else 256), (nsplit, nb, D)
+                    continue
+                assert nchunk % gc.value == 0
+                ng = nchunk // gc.value
+                assert 1 <= ni.value <= 2
+                assert st.value % (ng * ni.value) == 0 and st.value >= ng
+                assert sm.value <= 227 * 1024
+                seen.add((nsplit, gc.value, ni.value))
+    assert (16, 3, 2) in seen and (3, 1, 2) in seen and (1, 3, 1) in seen  # the c5 shape (D = 90) in the three modes
+    assert lib.cggp_tf32_ring_plan(2, 10, 1, None, None, None, None) != 0
+
+
 def test_no_cpu_fallback_and_no_oracle_in_product():
     import torch
 
