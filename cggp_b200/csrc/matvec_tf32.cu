@@ -270,7 +270,7 @@ struct Args {
   const float* pn;   // padded norms of the row set
   int64_t np;        // valid rows
   const float* Qb;   // column set: interleaved stream
-  const float* Qs;   // FP16: 1 / row scale
+  const float* Qs;   // (the column set's scales and norms travel in the trailers of its stream)
   const float* qn;
   int64_t nq;        // valid columns
   const float* U;    // [NB, ldu] weights over the columns, zero-padded to whole tiles (ldu >= 128 * tiles)
@@ -281,10 +281,11 @@ struct Args {
   float variance;
   int stages;        // ring depth in stages (what fits next to the resident P tile)
   int gc;            // K chunks per stage (divides KP / 32): one TMA bulk copy, one full barrier
-  int niss;          // MMA-issuing threads in use (1..3); the ring holds a multiple of `niss` tiles, so that a stage
+  int niss;          // MMA-issuing threads in use (1 or 2); the ring holds a multiple of `niss` tiles, so that a stage
                      // is always consumed by the same issuer (which then sees its barrier's phases in order)
   int dbg;           // timing experiments only (env CGGP_TF32_DBG; results are WRONG when set): 1 = no epilogue math,
-                     // 2 = no MMAs, 4 = no TMA copies, 8 = no global loads of the column scalars, 16 = no tcgen05.ld
+                     // 2 = no MMAs, 4 = no operand copies, 8 = no weights copies, 16 = no tcgen05.ld, 64 = all CTAs walk
+                     // the tiles in the same order
   const int* active;
 };
 
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(384, 1) gram_contract_kernel(const Args a, con
   constexpr uint32_t TM_P = NBUF * 128;
   __shared__ uint64_t bar_p, bar_qfull[MAX_STAGES], bar_qfree[MAX_STAGES], bar_full[NBAR], bar_empty[NBAR];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float comb[BM * NB];  // partial sums of the second column half, combined at the end
+  __shared__ float comb[BM * NB];  // partial sums of the second epilogue group, combined at the end
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t p0 = (int64_t)blockIdx.x * BM;
