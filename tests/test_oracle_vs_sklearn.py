@@ -31,3 +31,26 @@ def test_restated_kernels_agree_with_scikit_learn(name, nu, D):
     Kxx = g.KERNELS[name](variance=var, lengthscales=ls).K(X)
     np.testing.assert_allclose(Kxx, var * base(X), rtol=5e-13, atol=1e-6 if nu else 5e-15)
     np.testing.assert_allclose(g.KERNELS[name](variance=var, lengthscales=ls).K_diag(X), np.full(40, var))
+
+
+def test_restated_sgpr_with_all_points_inducing_is_exact_gp_regression():
+    """GPflow's SGPR (the model behind the north-star operator, cggp/cli_utils.py:444-446) with Z = X is exact GP
+    regression: its collapsed bound equals the log marginal likelihood and its predictions the GP posterior.  An
+    independent implementation of both: scikit-learn's GaussianProcessRegressor with the same fixed kernel and
+    alpha = noise variance.  Pins the restated SGPR formulas (L, A, B, LB, c; elbo terms; t1 / t2 in predict_f)."""
+    gpr = pytest.importorskip("sklearn.gaussian_process")
+    rng = np.random.default_rng(5)
+    N, D, noise = 60, 2, 0.3
+    X = rng.uniform(-2, 2, (N, D))
+    Y = np.sin(X.sum(-1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
+    Xs = rng.uniform(-2, 2, (17, D))
+    ls, var = np.array([0.9, 1.4]), 1.7
+    model = g.SGPR((X, Y), g.Matern52(variance=var, lengthscales=ls), X.copy(), noise_variance=noise, jitter=1e-10)
+    kern = sk.ConstantKernel(var, constant_value_bounds="fixed") * sk.Matern(length_scale=ls, nu=2.5,
+                                                                            length_scale_bounds="fixed")
+    ref = gpr.GaussianProcessRegressor(kernel=kern, alpha=noise, optimizer=None).fit(X, Y[:, 0])
+    mu_ref, sd_ref = ref.predict(Xs, return_std=True)
+    mu, v = model.predict_f(Xs)
+    np.testing.assert_allclose(np.ravel(mu), mu_ref, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(np.ravel(v), sd_ref ** 2, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(float(model.elbo()), ref.log_marginal_likelihood_value_, rtol=1e-7)
