@@ -9,7 +9,10 @@ vendored under /root/reference and not installable here), so this file restates 
 expectations), ``cggp/optimize.py:50`` (square_distance), ``cggp/cli_utils.py:444-446`` (SGPR),
 ``cggp/distance.py:17-20,26-29`` (kernel __call__).
 
-PARITY UNPINNED: the reference holds no golden vectors for these values.
+PARITY UNPINNED: the reference holds no golden vectors for these values.  What pins them
+instead: closed forms and the CGGP / ClusterGP / dense cross-checks (tests/test_oracle_gpflow.py), and an independent
+third-party implementation of the same published formulas - scikit-learn's RBF / Matern kernels and exact GP
+regression (tests/test_oracle_vs_sklearn.py).
 """
 from __future__ import annotations
 
