@@ -95,6 +95,7 @@ SIGNATURES = {
     "cggp_kuf_times_tf32": (_i, [_vp, _i, _d, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _vp, _i64,
                                   _i]),
     "cggp_kuf_times": (_i, [_vp, _i, _i, _d, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i64, _vp, _i64, _i, _vp, _i64]),
+    "cggp_kuf_gram": (_i, [_vp, _i, _i, _d, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i64, _vp, _i64, _i]),
     "cggp_symm_matmul": (_i, [_vp, _i, _vp, _i64, _i64, _vp, _i64, _i, _vp, _i64]),
     "cggp_block_cholesky": (_i, [_vp, _i, _vp, _i64, _i64, _vp, _i, _i, _vp]),
     "cggp_cg_fused_step": (_i, [_vp, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(Precond)]),

@@ -9,10 +9,6 @@
 int cggp_matvec_simple(cggp_ctx* ctx, int dtype, int kind, double variance, const void* PX, const void* nX, int64_t n,
                        const void* PZ, const void* nZ, int64_t m, int D, int64_t ldp, const void* V, int64_t ldv,
                        int B, void* W, int64_t ldw, const int* active);
-int cggp_matvec_fused(cggp_ctx* ctx, int kind, double variance, const double* PX, const double* nX, int64_t n,
-                      const double* PZ, const double* nZ, int64_t m, int D, int64_t ldp, const double* V, int64_t ldv,
-                      int B, double* W, int64_t ldw, const int* active);
-bool cggp_matvec_fused_supported(cggp_ctx* ctx, int dtype, int64_t m, int D, int B);
 int cggp_matvec_pipe(cggp_ctx* ctx, int kind, double variance, const double* PX, const double* nX, int64_t n,
                      const double* PZ, const double* nZ, int64_t m, int D, int64_t ldp, const double* V, int64_t ldv,
                      int B, double* W, int64_t ldw, const int* active);
@@ -77,6 +73,7 @@ extern "C" int cggp_ctx_destroy(cggp_ctx* ctx) {
   Ws2& w = ws2_of(ctx);
   if (w.p) { cudaFree(w.p); w.p = nullptr; w.bytes = 0; }
   if (ctx->exp_tab) cudaFree(ctx->exp_tab);
+  if (ctx->xa2) cudaFree(ctx->xa2);
   if (ctx->cg_state) cudaFree(ctx->cg_state);
   if (ctx->cg_state_host) cudaFreeHost(ctx->cg_state_host);
   for (int s = 0; s < CGGP_PROF_SECTIONS; ++s)
@@ -384,7 +381,6 @@ int cggp_matvec_dispatch(cggp_ctx* ctx, int dtype, int kind, double variance, co
                          int64_t n, const void* PZ, const void* nZ, int64_t m, int D, int64_t ldp, const void* V,
                          int64_t ldv, int B, void* W, int64_t ldw, int variant, const int* active) {
   if (kind < CGGP_SE || kind > CGGP_MATERN52) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "unknown kernel kind %d", kind);
-  const bool can_fuse = cggp_matvec_fused_supported(ctx, dtype, m, D, B);
   const bool can_pipe = cggp_matvec_pipe_supported(ctx, dtype, m, D, B);
   ProfScope prof(ctx, 0);
   if (variant == 3 && !can_pipe)
@@ -393,12 +389,6 @@ int cggp_matvec_dispatch(cggp_ctx* ctx, int dtype, int kind, double variance, co
   if ((variant == 0 && can_pipe) || variant == 3)
     return cggp_matvec_pipe(ctx, kind, variance, (const double*)PX, (const double*)nX, n, (const double*)PZ,
                             (const double*)nZ, m, D, ldp, (const double*)V, ldv, B, (double*)W, ldw, active);
-  if (variant == 2 && !can_fuse)
-    CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "fused matvec does not support dtype=%d m=%lld D=%d B=%d", dtype,
-              (long long)m, D, B);
-  if ((variant == 0 && can_fuse) || variant == 2)
-    return cggp_matvec_fused(ctx, kind, variance, (const double*)PX, (const double*)nX, n, (const double*)PZ,
-                             (const double*)nZ, m, D, ldp, (const double*)V, ldv, B, (double*)W, ldw, active);
   return cggp_matvec_simple(ctx, dtype, kind, variance, PX, nX, n, PZ, nZ, m, D, ldp, V, ldv, B, W, ldw, active);
 }
 
@@ -407,7 +397,7 @@ extern "C" int cggp_kuf_kfu_matvec(cggp_ctx* ctx, int dtype, int kind, double va
                                    int64_t ldp, const void* V, int64_t ldv, int B, void* W, int64_t ldw, int variant) {
   if (!ctx) return CGGP_ERR_INVALID;
   if (B <= 0 || m <= 0) return CGGP_OK;
-  if (variant < 0 || variant > 3) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "variant must be 0, 1, 2 or 3");
+  if (variant != 0 && variant != 1 && variant != 3) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "variant must be 0, 1 or 3");
   return cggp_matvec_dispatch(ctx, dtype, kind, variance, PX, nX, n, PZ, nZ, m, D, ldp, V, ldv, B, W, ldw, variant,
                               nullptr);
 }
@@ -438,7 +428,7 @@ extern "C" int cggp_kuf_times(cggp_ctx* ctx, int dtype, int kind, double varianc
   if (P <= 0 || m <= 0) return CGGP_OK;
   if (kind < CGGP_SE || kind > CGGP_MATERN52) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "unknown kernel kind %d", kind);
   if (!cggp_matvec_pipe_supported(ctx, dtype, m, D, P))
-    CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "fused Kuf @ Y needs float64 and D <= 15 (dtype=%d, D=%d)", dtype, D);
+    CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "fused Kuf @ Y needs float64 and D <= 31 (dtype=%d, D=%d)", dtype, D);
   ProfScope prof(ctx, 0);
   return cggp_kuf_times_pipe(ctx, kind, variance, (const double*)PX, (const double*)nX, n, (const double*)PZ,
                              (const double*)nZ, m, D, ldp, (const double*)Y, ldy, P, (double*)W, ldw);

@@ -547,9 +547,13 @@ extern "C" int cggp_cg_solve(cggp_ctx* ctx, const cggp_operator* op, const void*
   if (op->type != CGGP_OP_DENSE && op->type != CGGP_OP_SGPR) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "bad operator type");
   int rc = check_precond(ctx, pc, op->n);
   if (rc) return rc;
+  ctx->solve_epoch = ++ctx->solve_counter;  // per-solve caches of the product kernels are valid until the return
   if (op->dtype == CGGP_F64)
-    return cg_solve_impl<double>(ctx, op, rhs, x0, B, error_threshold, max_iterations, max_steps_cycle, pc,
-                                 check_every, solution, host_steps, half_rz, history, history_cap);
-  return cg_solve_impl<float>(ctx, op, rhs, x0, B, error_threshold, max_iterations, max_steps_cycle, pc, check_every,
+    rc = cg_solve_impl<double>(ctx, op, rhs, x0, B, error_threshold, max_iterations, max_steps_cycle, pc,
+                               check_every, solution, host_steps, half_rz, history, history_cap);
+  else
+    rc = cg_solve_impl<float>(ctx, op, rhs, x0, B, error_threshold, max_iterations, max_steps_cycle, pc, check_every,
                               solution, host_steps, half_rz, history, history_cap);
+  ctx->solve_epoch = 0;
+  return rc;
 }

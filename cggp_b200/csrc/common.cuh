@@ -23,6 +23,15 @@ struct cggp_ctx {
   int* cg_state = nullptr;
   int* cg_state_host = nullptr;  // pinned
   void* exp_tab = nullptr;  // exp tables of the pipelined matvec (built on first use)
+  // pre-scaled, duplicated row norms of the pipelined kernels (kpipe::dup_scaled_norms); valid for the current solve
+  void* xa2 = nullptr;
+  size_t xa2_bytes = 0;
+  const void* xa2_key = nullptr;
+  int64_t xa2_n = 0;
+  double xa2_alpha = 0.0;
+  int64_t solve_epoch = 0;  // > 0 while cggp_cg_solve runs (a fresh value per solve), 0 outside
+  int64_t xa2_epoch = -1;
+  int64_t solve_counter = 0;
   // NCCL (dlopen'ed)
   void* comm = nullptr;
   int rank = 0, world = 1;

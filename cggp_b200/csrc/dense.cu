@@ -149,3 +149,68 @@ extern "C" int cggp_symm_matmul(cggp_ctx* ctx, int dtype, const void* A, int64_t
   if (B <= 0 || n <= 0) return CGGP_OK;
   return cggp_symm_matmul_ex(ctx, dtype, A, lda, n, V, ldv, B, Y, ldy, nullptr, 0, 0.0, nullptr);
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// G (+)= Kuf Kfu over this rank's rows: the [M, M] Gram matrix GPflow's SGPR materialises as A A^T.
+// Kuf is evaluated in row chunks sized to stay L2-resident (cggp_kernel_matrix -> [M, nc], never more than one chunk
+// alive) and contracted by the DMMA GEMM of this library as a symmetric rank-k update: only tiles touching the lower
+// triangle are computed, the result is mirrored once at the end.  (Evaluating the Gram entries INSIDE the GEMM tiles
+// would re-evaluate every entry M / 256 times: 27 FP64 slots per evaluation against 128 FMAs of use per tile pass is
+// +21 % on the binding pipe, against +1 % for the chunked form - DESIGN.md 4.3.)
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void mirror_lower_kernel(T* __restrict__ G, int64_t ldg, int64_t m) {
+  __shared__ T tile[32][33];
+  const int64_t bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;  // read lower tile (bi, bj), write upper tile (bj, bi)
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = bi * 32 + r, j = bj * 32 + tx;
+    tile[r][tx] = (i < m && j < m) ? G[i * ldg + j] : T(0);
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = bj * 32 + r, j = bi * 32 + tx;  // upper element (i, j) = lower element (j, i)
+    if (i < m && j < m && j > i) G[i * ldg + j] = tile[tx][r];
+  }
+}
+
+int cggp_ws2_reserve(cggp_ctx* ctx, size_t bytes);
+void* cggp_ws2_ptr(cggp_ctx* ctx);
+
+extern "C" int cggp_kuf_gram(cggp_ctx* ctx, int dtype, int kind, double variance, const void* PX, const void* nX,
+                             int64_t n, const void* PZ, const void* nZ, int64_t m, int D, int64_t ldp, void* G,
+                             int64_t ldg, int accumulate) {
+  if (!ctx) return CGGP_ERR_INVALID;
+  if (m <= 0) return CGGP_OK;
+  if (!G || ldg < m) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "gram: output must be [m, m] with ldg >= m");
+  const size_t es = dtype == CGGP_F64 ? 8 : 4;
+  if (!accumulate) CGGP_CUDA(ctx, cudaMemset2DAsync(G, (size_t)ldg * es, 0, (size_t)m * es, (size_t)m, ctx->stream));
+  if (n <= 0) return CGGP_OK;
+  int64_t nc = (int64_t)((size_t)(1u << 26) / ((size_t)m * es));  // 64 MB chunks
+  nc = nc < 256 ? 256 : nc;
+  nc = (nc + 31) / 32 * 32;
+  if (nc > n) nc = (n + 1) / 2 * 2;
+  int rc = cggp_ws2_reserve(ctx, (size_t)m * (size_t)nc * es);
+  if (rc) return rc;
+  char* Kc = (char*)cggp_ws2_ptr(ctx);
+  for (int64_t s = 0; s < n; s += nc) {
+    const int64_t rows = n - s < nc ? n - s : nc;
+    rc = cggp_kernel_matrix(ctx, dtype, kind, variance, CGGP_OUT_KERNEL, 0, PZ, nZ, m, (const char*)PX + (size_t)s * ldp * es,
+                            (const char*)nX + (size_t)s * es, rows, D, ldp, 0.0, Kc, nc);
+    if (rc) return rc;
+    if (dtype == CGGP_F64)
+      rc = dmma_gemm_nt<double>(ctx, (const double*)Kc, nc, m, (const double*)Kc, nc, m, rows, (double*)G, ldg,
+                                (const double*)G, ldg, 1.0, nullptr, 1);
+    else
+      rc = dmma_gemm_nt<float>(ctx, (const float*)Kc, nc, m, (const float*)Kc, nc, m, rows, (float*)G, ldg,
+                               (const float*)G, ldg, 1.0f, nullptr, 0);
+    if (rc) return rc;
+  }
+  if (dtype == CGGP_F64) {
+    dim3 grid((unsigned)((m + 31) / 32), (unsigned)((m + 31) / 32));
+    mirror_lower_kernel<double><<<grid, 256, 0, ctx->stream>>>((double*)G, ldg, m);
+    CGGP_LAUNCH_CHECK(ctx);
+  }
+  return CGGP_OK;
+}

@@ -91,9 +91,11 @@ __global__ void __launch_bounds__(256)
 dmma_gemm_nt_kernel(const double* __restrict__ A, int64_t lda, int64_t M, const double* __restrict__ Bm, int64_t ldb,
                     int64_t N, int64_t K, double* __restrict__ C, int64_t ldc, const double* __restrict__ addend,
                     int64_t ldadd, double scale, const int* __restrict__ active, const int vec16, const int64_t k_chunk,
-                    double* __restrict__ partial) {
+                    double* __restrict__ partial, const int lower) {
   if (cg_inactive(active)) return;
   constexpr int BM = WMB * 16;
+  // symmetric rank-k update (C = A A^T): tiles entirely above the diagonal are skipped, the caller mirrors
+  if (lower && (int64_t)blockIdx.x * BN >= ((int64_t)blockIdx.y + 1) * BM) return;
   if (gridDim.z > 1) {
     // split-K: this CTA contracts k in [z * k_chunk, min(K, (z + 1) * k_chunk)) and writes its partial [M, N] tile
     // set; a fixed-order reduction adds the partials (and the addend) afterwards
@@ -228,14 +230,15 @@ __global__ void splitk_reduce_kernel(const double* __restrict__ partial, int spl
   C[r * ldc + c] = v;
 }
 
+// lower != 0 (float64 only): only the tiles touching the lower triangle are computed (A == Bm, M == N)
 template <typename T>
 int dmma_gemm_nt(cggp_ctx* ctx, const T* A, int64_t lda, int64_t M, const T* Bm, int64_t ldb, int64_t N, int64_t K,
-                 T* C, int64_t ldc, const T* addend, int64_t ldadd, T scale, const int* active);
+                 T* C, int64_t ldc, const T* addend, int64_t ldadd, T scale, const int* active, int lower = 0);
 
 template <>
 inline int dmma_gemm_nt<float>(cggp_ctx* ctx, const float* A, int64_t lda, int64_t M, const float* Bm, int64_t ldb,
                                int64_t N, int64_t K, float* C, int64_t ldc, const float* addend, int64_t ldadd,
-                               float scale, const int* active) {
+                               float scale, const int* active, int /*lower*/) {
   dim3 grid((unsigned)((N + TILE - 1) / TILE), (unsigned)((M + TILE - 1) / TILE));
   tile_gemm_nt_kernel<float><<<grid, TILE_THREADS, 0, ctx->stream>>>(A, lda, M, Bm, ldb, N, K, C, ldc, addend, ldadd,
                                                                       scale, active);
@@ -246,7 +249,7 @@ inline int dmma_gemm_nt<float>(cggp_ctx* ctx, const float* A, int64_t lda, int64
 template <>
 inline int dmma_gemm_nt<double>(cggp_ctx* ctx, const double* A, int64_t lda, int64_t M, const double* Bm, int64_t ldb,
                                 int64_t N, int64_t K, double* C, int64_t ldc, const double* addend, int64_t ldadd,
-                                double scale, const int* active) {
+                                double scale, const int* active, int lower) {
   using namespace dg;
   // 16-byte cp.async needs 16-byte aligned rows on both operands
   const int vec16 = ((lda | ldb) % 2 == 0) && ((((uintptr_t)A) | ((uintptr_t)Bm)) % 16 == 0) ? 1 : 0;
@@ -275,24 +278,15 @@ inline int dmma_gemm_nt<double>(cggp_ctx* ctx, const double* A, int64_t lda, int
       grid.z = (unsigned)splits;
     }
   }
+  // the opt-in is per device and a process may drive several (one ctx each): set it on every launch (cheap)
   if (small) {
-    static bool attr = false;
-    if (!attr) {
-      CGGP_CUDA(ctx, cudaFuncSetAttribute(dmma_gemm_nt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem));
-      attr = true;
-    }
+    CGGP_CUDA(ctx, cudaFuncSetAttribute(dmma_gemm_nt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dmma_gemm_nt_kernel<4><<<grid, 256, smem, ctx->stream>>>(A, lda, M, Bm, ldb, N, K, C, ldc, addend, ldadd, scale,
-                                                             active, vec16, k_chunk, partial);
+                                                             active, vec16, k_chunk, partial, lower);
   } else {
-    static bool attr = false;
-    if (!attr) {
-      CGGP_CUDA(ctx, cudaFuncSetAttribute(dmma_gemm_nt_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem));
-      attr = true;
-    }
+    CGGP_CUDA(ctx, cudaFuncSetAttribute(dmma_gemm_nt_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dmma_gemm_nt_kernel<8><<<grid, 256, smem, ctx->stream>>>(A, lda, M, Bm, ldb, N, K, C, ldc, addend, ldadd, scale,
-                                                             active, vec16, k_chunk, partial);
+                                                             active, vec16, k_chunk, partial, lower);
   }
   CGGP_LAUNCH_CHECK(ctx);
   if (grid.z > 1) {

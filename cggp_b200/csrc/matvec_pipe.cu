@@ -5,7 +5,7 @@
 // Every Gram entry k(x_i, z_j) is evaluated ONCE per application and is never written to global memory.
 //
 // What binds on B200 (profiles/r01_fused_v2_summary.md): the FP64 pipe (64 FMA/clk/SM, shared by DFMA and DMMA).
-// The first fused kernel (matvec_fused.cu, K tile in registers, 2 x 4 warps per SM) kept that pipe only 45 % busy:
+// The first fused kernel of round 1 (K tile in registers, 2 x 4 warps per SM; removed) kept that pipe only 45 % busy:
 // 8 warps/SM cannot cover the DFMA dependency chains of sqrt / exp, and every row block ends in an exposed L2
 // round trip for the exchange of the partial t.  This kernel fixes both:
 //   * 1 CTA of 16 warps per SM (4 warps per scheduler, 4 independent epilogue chains each); the K values a thread
@@ -27,8 +27,15 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "common.cuh"
-#include "kmath.cuh"
+#include "pipe_common.cuh"
+
+// Timing experiments that switch parts of the product OFF (wrong results) exist only in builds with
+// -DCGGP_DEBUG_KNOBS; the shipped library ignores CGGP_PIPE_DBG.
+#ifdef CGGP_DEBUG_KNOBS
+#define CGGP_DBG(x) (x)
+#else
+#define CGGP_DBG(x) false
+#endif
 
 namespace kpipe {
 constexpr int XS = 2;     // X-tile ring stages
@@ -60,112 +67,10 @@ struct Args {
                   // 2 = skip the L2 exchange
   const int* active;
   const int2* etab;  // exp table of the shared-memory variant (ET = 10: 1024 entries)
+  const double2* xa2;  // DUP: (alpha |x_i|^2, alpha |x_i|^2) per row - the initial DMMA accumulator pair, one LDS.128
 };
 
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(void* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-// a2 = alpha (|x|^2 + |z|^2) + beta x.z : the argument the kernel family wants, produced directly by the DMMA
-template <int KIND>
-struct Fam;
-template <>
-struct Fam<CGGP_SE> {  // K = exp(-r2 / 2): the DMMA delivers the exponent itself
-  static constexpr double alpha = -0.5, beta = 1.0;
-};
-template <>
-struct Fam<CGGP_MATERN12> {  // a = r
-  static constexpr double alpha = 1.0, beta = -2.0;
-  static constexpr double clampv = 1e-36;
-  static constexpr int clamp_hi = 0x38754484;
-};
-template <>
-struct Fam<CGGP_MATERN32> {  // a = sqrt(3) r
-  static constexpr double alpha = 3.0, beta = -6.0;
-  static constexpr double clampv = 3e-36;
-  static constexpr int clamp_hi = 0x388fe6c6;
-};
-template <>
-struct Fam<CGGP_MATERN52> {  // a = sqrt(5) r
-  static constexpr double alpha = 5.0, beta = -10.0;
-  static constexpr double clampv = 5e-36;
-  static constexpr int clamp_hi = 0x389a95a5;
-};
-
-// Unit-variance kernel value from the scaled argument q.  FP64-pipe instructions: SE 9, Matern-1/2 14, 3/2 16,
-// 5/2 17.  Range handling costs two integer min / max on the high word (ALU pipe), no FP64 compare / select:
-//   Matern: hi(q) -> clamp to [hi(alpha 1e-36), hi(708^2)] as SIGNED ints: negative q (rounding noise at x == z) and
-//           q below GPflow's max(r2, 1e-36) land on the lower clamp, q beyond (708 lengthscales)^2 on the upper one
-//           (exp(-708) = 3e-308 instead of an underflowed 0: absolute error 3e-308);
-//   SE:     hi(q) -> min with hi(-708) as UNSIGNED ints (more negative = larger).
-template <int KIND, int ET, int SQ = 0>
-__device__ __forceinline__ double kval(double q, const FastExpTable& tab, const int2* etab) {
-  if constexpr (KIND == CGGP_SE) {
-    const unsigned h = min((unsigned)__double2hiint(q), 0xC0862000u);
-    const double x = __hiloint2double((int)h, __double2loint(q));
-    if constexpr (ET == 0) return fast_exp_core(x, tab);
-    else return fast_exp_core_smem<ET>(x, etab);
-  } else {
-    // in place on the register pair (the compiler otherwise copies the low word to a fresh pair)
-    double qc = q;
-    asm("{\n"
-        ".reg .b32 lo, hi;\n"
-        "mov.b64 {lo, hi}, %0;\n"
-        "max.s32 hi, hi, %1;\n"
-        "min.s32 hi, hi, 0x411e9840;\n"
-        "mov.b64 %0, {lo, hi};\n"
-        "}\n"
-        : "+d"(qc)
-        : "n"(Fam<KIND>::clamp_hi));
-    const double a = SQ == 1 ? fast_sqrt_pos_cubic(qc) : fast_sqrt_pos_lean(qc);
-    double e;
-    if constexpr (ET == 0) e = fast_exp_neg_core(a, tab);
-    else e = fast_exp_neg_core_smem<ET>(a, etab);
-    if constexpr (KIND == CGGP_MATERN12) {
-      return e;
-    } else if constexpr (KIND == CGGP_MATERN32) {
-      return (1.0 + a) * e;
-    } else {
-      return fma(qc, 1.0 / 3.0, 1.0 + a) * e;  // 1 + sqrt5 r + 5/3 r^2, with a^2 = 5 r2 (= qc up to one rounding)
-    }
-  }
-}
-
-template <int WARPS, int RB, int CBW, int NB, int KS, int NBUF, int ET>
+template <int WARPS, int RB, int CBW, int NB, int KS, int NBUF, int ET, int DUP = 0>
 struct Layout {
   static constexpr int THREADS = WARPS * 32;
   static constexpr int BM = RB * 8;
@@ -174,7 +79,8 @@ struct Layout {
   static constexpr int LDX = KS * 4;
   static constexpr size_t kbuf_bytes = (size_t)NBUF * RB * CBW * THREADS * sizeof(double2);
   static constexpr size_t xt_bytes = (size_t)XS * BM * LDX * sizeof(double);
-  static constexpr size_t xn_bytes = (size_t)XS * BM * sizeof(double);
+  static constexpr int XNW = DUP ? 2 : 1;  // doubles per row of the staged norms (DUP: the accumulator pair)
+  static constexpr size_t xn_bytes = (size_t)XS * BM * XNW * sizeof(double);
   static constexpr size_t tred_bytes = (size_t)NBUF * WARPS * BM * NB * sizeof(double);
   static constexpr size_t tfull_bytes = (size_t)NBUF * BM * NB * sizeof(double);
   static constexpr size_t etab_bytes = ET ? ((size_t)sizeof(int2) << ET) : 0;
@@ -182,25 +88,13 @@ struct Layout {
   static constexpr size_t total = kbuf_bytes + xt_bytes + xn_bytes + tred_bytes + tfull_bytes + bar_bytes + etab_bytes;
 };
 
-// Hand-offs inside a CTA.  T (named barrier 1 + parity): "the partial t of block j is in tred[j & 1] and X stage
-// j % XS is free" - the compute warps arrive without waiting, the exchange warp waits.  F (mbarrier per parity):
-// "t of block j is in tfull[j & 1]" - the 32 exchange lanes arrive, every compute warp waits on its own, so the
-// compute warps are never synchronised with each other and drift apart by up to a phase.
-__device__ __forceinline__ void bar_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void bar_arrive(int id, int count) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(void* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 constexpr int BAR_T = 1;  // + parity of the block
 
-template <int KIND, int KS, int WARPS, int RB, int CBW, int NB, int NBUF, int ET, int SQ>
+template <int KIND, int KS, int WARPS, int RB, int CBW, int NB, int NBUF, int ET, int SQ, int DUP>
 __global__ void __launch_bounds__(WARPS * 32 + 64, 1) kfu_pipe_kernel(const Args a) {
   if (cg_inactive(a.active)) return;
-  using L = Layout<WARPS, RB, CBW, NB, KS, NBUF, ET>;
+  using L = Layout<WARPS, RB, CBW, NB, KS, NBUF, ET, DUP>;
+  constexpr int XNW = L::XNW;
   constexpr int LAG = NBUF - 1;  // phase 2 of block j runs after phase 1 of block j + LAG
   constexpr int THREADS = L::THREADS, BM = L::BM, WN = L::WN, BN = L::BN, LDX = L::LDX;
   constexpr int ALL = THREADS + 32;  // compute warps + the exchange warp of a block (hand-off barrier T)
@@ -249,10 +143,11 @@ __global__ void __launch_bounds__(WARPS * 32 + 64, 1) kfu_pipe_kernel(const Args
       const int64_t r0 = row0_of(it);
       if (!is_manual(it)) {
         if (lane == 0) {
-          constexpr unsigned xb = BM * LDX * sizeof(double), nb = BM * sizeof(double);
+          constexpr unsigned xb = BM * LDX * sizeof(double), nb = BM * XNW * sizeof(double);
           mbar_expect_tx(&mbar[s], xb + nb);
           tma_bulk_g2s(xt + s * BM * LDX, a.PX + r0 * a.ldp, xb, &mbar[s]);
-          tma_bulk_g2s(xn + s * BM, a.nX + r0, nb, &mbar[s]);
+          if constexpr (DUP) tma_bulk_g2s(xn + s * BM * 2, a.xa2 + r0, nb, &mbar[s]);
+          else tma_bulk_g2s(xn + s * BM, a.nX + r0, nb, &mbar[s]);
         }
       } else {  // ragged last block / unaligned caller: guarded loads, completed on the same mbarrier as a TMA tile
         for (int e = lane; e < BM * LDX; e += 32) {
@@ -261,7 +156,11 @@ __global__ void __launch_bounds__(WARPS * 32 + 64, 1) kfu_pipe_kernel(const Args
           if (r0 + r < a.n) x = (k < a.D) ? a.PX[(r0 + r) * a.ldp + k] : (k == a.D ? 1.0 : 0.0);
           xt[s * BM * LDX + e] = x;
         }
-        for (int e = lane; e < BM; e += 32) xn[s * BM + e] = (r0 + e < a.n) ? a.nX[r0 + e] : 0.0;
+        for (int e = lane; e < BM; e += 32) {
+          const double v = (r0 + e < a.n) ? a.nX[r0 + e] : 0.0;
+          if constexpr (DUP) xn[(s * BM + e) * 2] = xn[(s * BM + e) * 2 + 1] = Fam<KIND>::alpha * v;
+          else xn[s * BM + e] = v;
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&mbar[s]);  // release: the tile written by the 32 lanes is visible to the waiters
       }
@@ -303,7 +202,7 @@ __global__ void __launch_bounds__(WARPS * 32 + 64, 1) kfu_pipe_kernel(const Args
         mbar_arrive(&mbarF[par]);
         continue;
       }
-      if (a.C > 1 && !(a.dbg & 2)) {
+      if (a.C > 1 && !CGGP_DBG(a.dbg & 2)) {
         double* mine = slots_g + ((int64_t)(it % SLOTS) * a.C + rank) * (BM * NB);
 #pragma unroll
         for (int q = 0; q < (BM * NB + 31) / 32; ++q)
@@ -413,7 +312,7 @@ __global__ void __launch_bounds__(WARPS * 32 + 64, 1) kfu_pipe_kernel(const Args
     const int s = (int)(it % XS), par = (int)(it % NBUF);
     mbar_wait(&mbar[s], (unsigned)((it / XS) & 1));  // X tile (TMA or guarded loads) has landed
     const double* xs = xt + s * BM * LDX + lr * LDX + lk;
-    const double* xns = xn + s * BM + lr;
+    const double* xns = xn + (s * BM + lr) * XNW;
     double2* kb = kbuf + (size_t)par * RB * CBW * THREADS + tid;
     double* tr = tred + (par * WARPS + warp) * BM * NB;
 #pragma unroll
@@ -421,14 +320,21 @@ __global__ void __launch_bounds__(WARPS * 32 + 64, 1) kfu_pipe_kernel(const Args
       double af[KS];
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) af[ks] = xs[rb * 8 * LDX + ks * 4];
-      const double xa = Fam<KIND>::alpha * xns[rb * 8];
       double c[CBW][2];
+      if constexpr (DUP) {
+        // one LDS.128 delivers the accumulator pair (alpha |x|^2 twice): no FP64 multiply, no register moves
+        const double2 xa2 = *reinterpret_cast<const double2*>(xns + rb * 8 * 2);
 #pragma unroll
-      for (int cb = 0; cb < CBW; ++cb) {
-        c[cb][0] = c[cb][1] = xa;
+        for (int cb = 0; cb < CBW; ++cb) c[cb][0] = xa2.x, c[cb][1] = xa2.y;
+      } else {
+        const double xa = Fam<KIND>::alpha * xns[rb * 8];
+#pragma unroll
+        for (int cb = 0; cb < CBW; ++cb) c[cb][0] = c[cb][1] = xa;
+      }
+#pragma unroll
+      for (int cb = 0; cb < CBW; ++cb)
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) dmma884(c[cb][0], c[cb][1], af[ks], bf[cb][ks]);
-      }
       double tp[NB];
 #pragma unroll
       for (int b = 0; b < NB; ++b) tp[b] = 0.0;
@@ -452,9 +358,9 @@ __global__ void __launch_bounds__(WARPS * 32 + 64, 1) kfu_pipe_kernel(const Args
     __threadfence_block();
     bar_arrive(BAR_T + par, ALL);  // hand the partials (and the X stage) to the exchange warp; do not wait
     // ------------------------------- phase 2 of block `it - 1` -------------------------------
-    if (it >= LAG && !(a.dbg & 1)) phase2(it - LAG);
+    if (it >= LAG && !CGGP_DBG(a.dbg & 1)) phase2(it - LAG);
   }
-  if (!(a.dbg & 1))
+  if (!CGGP_DBG(a.dbg & 1))
     for (int64_t jt = nit > LAG ? nit - LAG : 0; jt < nit; ++jt) phase2(jt);
 
   // reduce the 8 row-lanes of every column, write this group's partial
@@ -484,17 +390,59 @@ __global__ void reduce_groups_kernel(const double* __restrict__ Wp, int G, int N
   W[(int64_t)b * ldw + c] = v;
 }
 
+}  // namespace kpipe
+
+// (alpha |x_i|^2, alpha |x_i|^2): the initial DMMA accumulator pair of row i, read by the kernels with one LDS.128.
+__global__ void scale_dup_kernel(const double* __restrict__ nX, int64_t n, double alpha, double2* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double v = alpha * nX[i];
+    out[i] = make_double2(v, v);
+  }
+}
+// Built per launch, or once per cggp_cg_solve (the operator's points cannot change inside a solve: the buffer is
+// keyed on pointer, row count, family and the solve epoch).
+int kpipe::dup_scaled_norms(cggp_ctx* ctx, int kind, const double* nX, int64_t n, const int* active,
+                            const double2** out) {
+  const double alpha = kind == CGGP_SE ? Fam<CGGP_SE>::alpha : kind == CGGP_MATERN12 ? Fam<CGGP_MATERN12>::alpha
+                       : kind == CGGP_MATERN32 ? Fam<CGGP_MATERN32>::alpha : Fam<CGGP_MATERN52>::alpha;
+  const size_t need = sizeof(double2) * (size_t)(n > 0 ? n : 1);
+  const bool hit = ctx->solve_epoch > 0 && ctx->xa2_epoch == ctx->solve_epoch && ctx->xa2_key == (const void*)nX &&
+                   ctx->xa2_n == n && ctx->xa2_alpha == alpha && ctx->xa2;
+  if (!hit) {
+    if (need > ctx->xa2_bytes) {
+      CGGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if (ctx->xa2) cudaFree(ctx->xa2);
+      ctx->xa2 = nullptr;
+      ctx->xa2_bytes = 0;
+      CGGP_CUDA(ctx, cudaMalloc(&ctx->xa2, need + need / 8));
+      ctx->xa2_bytes = need + need / 8;
+    }
+    (void)active;  // built unconditionally: a later launch of the same solve may reuse it
+    scale_dup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(nX, n, alpha, (double2*)ctx->xa2);
+    CGGP_LAUNCH_CHECK(ctx);
+    ctx->xa2_key = nX;
+    ctx->xa2_n = n;
+    ctx->xa2_alpha = alpha;
+    ctx->xa2_epoch = ctx->solve_epoch;
+  }
+  *out = (const double2*)ctx->xa2;
+  return CGGP_OK;
+}
+
+namespace kpipe {
 struct Plan {
   const void* fn;
-  int threads, BM, BN, NB;
+  int threads, BM, BN, NB, dup;
   size_t smem;
 };
 
-template <int KIND, int KS, int WARPS, int RB, int CBW, int NB, int NBUF, int ET = 0, int SQ = 0>
+template <int KIND, int KS, int WARPS, int RB, int CBW, int NB, int NBUF, int ET = 0, int SQ = 0, int DUP = 0>
 static Plan make_plan() {
-  using L = Layout<WARPS, RB, CBW, NB, KS, NBUF, ET>;
+  using L = Layout<WARPS, RB, CBW, NB, KS, NBUF, ET, DUP>;
   Plan p;
-  p.fn = (const void*)kfu_pipe_kernel<KIND, KS, WARPS, RB, CBW, NB, NBUF, ET, SQ>;
+  p.fn = (const void*)kfu_pipe_kernel<KIND, KS, WARPS, RB, CBW, NB, NBUF, ET, SQ, DUP>;
+  p.dup = DUP;
   p.threads = L::THREADS + 64;  // + the two exchange warps
   p.BM = L::BM;
   p.BN = L::BN;
@@ -506,34 +454,41 @@ static Plan make_plan() {
 // `deep`: three K buffers of 32 rows instead of two of 48, i.e. the group exchange of a block has TWO phase-1 periods
 // to complete.  Chosen where the group is large (M = 16384: 64 CTAs to wait for) or phase 1 is cheap (D <= 3).
 template <int KIND, int KS>
-static bool plan_for_nb(int nb, bool deep, int et, Plan& p) {
-  // et = 10 (default for one right-hand side): 1024-entry shared-memory exp table (degree-3 polynomial) + third-order
-  // sqrt step; et = 0: 32-entry shuffle table (degree 5) + two Newton steps.  Measured at c3: 20.58 vs 21.14 ms.
-  switch (nb) {
-    case 1:
-      if (et == 10) p = deep ? make_plan<KIND, KS, 16, 4, 2, 1, 3, 10, 1>() : make_plan<KIND, KS, 16, 6, 2, 1, 2, 10, 1>();
-      else p = deep ? make_plan<KIND, KS, 16, 4, 2, 1, 3>() : make_plan<KIND, KS, 16, 6, 2, 1, 2>();
-      return true;
-    case 2: p = deep ? make_plan<KIND, KS, 16, 3, 2, 2, 3>() : make_plan<KIND, KS, 16, 5, 2, 2, 2>(); return true;
-    default: return false;
+static bool plan_for_nb(int nb, bool deep, Plan& p) {
+  // one right-hand side: 1024-entry shared-memory exp table (degree-3 polynomial) + third-order sqrt step + the
+  // pre-scaled accumulator pair per row; two: 32-entry shuffle table (degree 5) + two Newton steps (no room for the table)
+  if (nb == 1) {
+    p = deep ? make_plan<KIND, KS, 16, 4, 2, 1, 3, 10, 1, 1>() : make_plan<KIND, KS, 16, 6, 2, 1, 2, 10, 1, 1>();
+    return true;
   }
+  if constexpr (KS <= 4) {  // 16 <= D <= 31: two and more right-hand sides go through the 8-wide kernel (matvec_pipe8.cu)
+    if (nb == 2) {
+      p = deep ? make_plan<KIND, KS, 16, 3, 2, 2, 3>() : make_plan<KIND, KS, 16, 5, 2, 2, 2>();
+      return true;
+    }
+  }
+  return false;
 }
 template <int KIND>
-static bool plan_for_ks(int ks, int nb, bool deep, int et, Plan& p) {
+static bool plan_for_ks(int ks, int nb, bool deep, Plan& p) {
   switch (ks) {
-    case 1: return plan_for_nb<KIND, 1>(nb, deep, et, p);
-    case 2: return plan_for_nb<KIND, 2>(nb, deep, et, p);
-    case 3: return plan_for_nb<KIND, 3>(nb, deep, et, p);
-    case 4: return plan_for_nb<KIND, 4>(nb, deep, et, p);
+    case 1: return plan_for_nb<KIND, 1>(nb, deep, p);
+    case 2: return plan_for_nb<KIND, 2>(nb, deep, p);
+    case 3: return plan_for_nb<KIND, 3>(nb, deep, p);
+    case 4: return plan_for_nb<KIND, 4>(nb, deep, p);
+    case 5: return plan_for_nb<KIND, 5>(nb, deep, p);
+    case 6: return plan_for_nb<KIND, 6>(nb, deep, p);
+    case 7: return plan_for_nb<KIND, 7>(nb, deep, p);
+    case 8: return plan_for_nb<KIND, 8>(nb, deep, p);
     default: return false;
   }
 }
-static bool plan_for(int kind, int ks, int nb, bool deep, int et, Plan& p) {
+static bool plan_for(int kind, int ks, int nb, bool deep, Plan& p) {
   switch (kind) {
-    case CGGP_SE: return plan_for_ks<CGGP_SE>(ks, nb, deep, et, p);
-    case CGGP_MATERN12: return plan_for_ks<CGGP_MATERN12>(ks, nb, deep, et, p);
-    case CGGP_MATERN32: return plan_for_ks<CGGP_MATERN32>(ks, nb, deep, et, p);
-    case CGGP_MATERN52: return plan_for_ks<CGGP_MATERN52>(ks, nb, deep, et, p);
+    case CGGP_SE: return plan_for_ks<CGGP_SE>(ks, nb, deep, p);
+    case CGGP_MATERN12: return plan_for_ks<CGGP_MATERN12>(ks, nb, deep, p);
+    case CGGP_MATERN32: return plan_for_ks<CGGP_MATERN32>(ks, nb, deep, p);
+    case CGGP_MATERN52: return plan_for_ks<CGGP_MATERN52>(ks, nb, deep, p);
     default: return false;
   }
 }
@@ -542,7 +497,7 @@ static bool plan_for(int kind, int ks, int nb, bool deep, int et, Plan& p) {
 bool cggp_matvec_pipe_supported(cggp_ctx* ctx, int dtype, int64_t m, int D, int B) {
   if (dtype != CGGP_F64 || B < 1) return false;
   const int ks = (D + 1 + 3) / 4;
-  if (ks > 4) return false;
+  if (ks > 8) return false;  // D <= 31
   const int64_t C = (m + 255) / 256;  // one co-resident CTA per 256 columns
   return C <= ctx->sm_count;
 }
@@ -550,6 +505,9 @@ bool cggp_matvec_pipe_supported(cggp_ctx* ctx, int dtype, int64_t m, int D, int 
 static int pipe_launch(cggp_ctx* ctx, int kind, double variance, const double* PX, const double* nX, int64_t n,
                        const double* PZ, const double* nZ, int64_t m, int D, int64_t ldp, const double* V, int64_t ldv,
                        int B, double* W, int64_t ldw, const int* active, const double* Tin, int64_t ldt);
+int cggp_pipe8_launch(cggp_ctx* ctx, int kind, double variance, const double* PX, const double* nX, int64_t n,
+                      const double* PZ, const double* nZ, int64_t m, int D, int64_t ldp, const double* V, int64_t ldv,
+                      int B, double* W, int64_t ldw, const int* active, const double* Tin, int64_t ldt);
 
 int cggp_matvec_pipe(cggp_ctx* ctx, int kind, double variance, const double* PX, const double* nX, int64_t n,
                      const double* PZ, const double* nZ, int64_t m, int D, int64_t ldp, const double* V, int64_t ldv,
@@ -567,7 +525,7 @@ int cggp_kuf_times_pipe(cggp_ctx* ctx, int kind, double variance, const double* 
 
 // 2^(j / 1024), j < 1024, correctly rounded from long double on the host; the high word of entry j is pre-decremented
 // by j << (20 - TBITS) (kmath.cuh).  Built once per ctx.
-static int cggp_exp_tables(cggp_ctx* ctx, const int2** out) {
+int kpipe::exp_table_device(cggp_ctx* ctx, const int2** out) {
   if (!ctx->exp_tab) {
     std::vector<int2> h(1024);
     auto fill = [&](int off, int bits) {
@@ -592,7 +550,18 @@ static int pipe_launch(cggp_ctx* ctx, int kind, double variance, const double* P
   using namespace kpipe;
   const int ks = (D + 1 + 3) / 4;
   int b0 = 0;
+  // from 3 right-hand sides on, sweeps of up to 8 with both contractions on DMMA (matvec_pipe8.cu): one sweep costs
+  // ~1.4 x a single-RHS sweep; below that the FMA-contraction kernels of this file (1 or 2 per sweep)
+  static const int p8_min = getenv("CGGP_PIPE8_MIN") ? atoi(getenv("CGGP_PIPE8_MIN")) : 3;  // tuning knob
   while (b0 < B) {
+    if (B - b0 >= (ks > 4 ? 2 : p8_min)) {
+      const int nb8 = (B - b0) >= 8 ? 8 : (B - b0);
+      int rc8 = cggp_pipe8_launch(ctx, kind, variance, PX, nX, n, PZ, nZ, m, D, ldp, V ? V + (int64_t)b0 * ldv : nullptr,
+                                  ldv, nb8, W + (int64_t)b0 * ldw, ldw, active, Tin ? Tin + b0 : nullptr, ldt);
+      if (rc8) return rc8;
+      b0 += nb8;
+      continue;
+    }
     const int nb = (B - b0) >= 2 ? 2 : 1;
     Plan p;
     static const int deep_env = getenv("CGGP_PIPE_DEEP") ? atoi(getenv("CGGP_PIPE_DEEP")) : -1;  // tuning knob
@@ -600,9 +569,8 @@ static int pipe_launch(cggp_ctx* ctx, int kind, double variance, const double* P
     // (M = 16384) wins big; c3 (D = 11) 20.39 / 20.40 at N = 2M but 2.600 / 2.562 at an 8-GPU shard of 250k rows:
     // three buffers where phase 1 is cheap (one DMMA k-step) or the group is large, two otherwise
     const bool deep = deep_env >= 0 ? deep_env != 0 : ((nb == 1 && ks <= 1) || m > 8192);
-    static const int et_env = getenv("CGGP_PIPE_ET") ? atoi(getenv("CGGP_PIPE_ET")) : 10;  // tuning knob
-    const int et = (nb == 1 && et_env == 10) ? 10 : 0;
-    if (!plan_for(kind, ks, nb, deep, et, p)) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "pipelined matvec: no plan for D=%d", D);
+    const int et = nb == 1 ? 10 : 0;
+    if (!plan_for(kind, ks, nb, deep, p)) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "pipelined matvec: no plan for D=%d", D);
     CGGP_CUDA(ctx, cudaFuncSetAttribute(p.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     int occ = 0;
     CGGP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p.fn, p.threads, p.smem));
@@ -629,11 +597,20 @@ static int pipe_launch(cggp_ctx* ctx, int kind, double variance, const double* P
     a.part = (double*)(base + wp_bytes);
     a.counters = (int*)(base + wp_bytes + part_bytes);
     a.C = C; a.G = G; a.nblocks = nblocks; a.active = active;
+#ifdef CGGP_DEBUG_KNOBS
     static const int dbg_env = getenv("CGGP_PIPE_DBG") ? atoi(getenv("CGGP_PIPE_DBG")) : 0;  // timing experiments
     a.dbg = dbg_env;
+#else
+    a.dbg = 0;
+#endif
+    a.xa2 = nullptr;
+    if (p.dup) {
+      rc = dup_scaled_norms(ctx, kind, nX, n, active, &a.xa2);
+      if (rc) return rc;
+    }
     a.etab = nullptr;
     if (et == 10) {
-      rc = cggp_exp_tables(ctx, &a.etab);
+      rc = exp_table_device(ctx, &a.etab);
       if (rc) return rc;
     }
     a.tma_ok = (ldp == ks * 4) && (((uintptr_t)PX | (uintptr_t)nX) % 16 == 0) ? 1 : 0;

@@ -2,7 +2,7 @@
 // 256-thread CTA owns a 4x4 micro-tile of pairwise quantities between 64 A-rows and 64 B-rows, accumulated over
 // the feature axis in chunks of 16 staged (transposed) through shared memory.  Used by the general-purpose
 // kernels (kernel matrix, distances, nearest centre, the simple two-sweep matvec, large-B dense products); the
-// headline fused matvec has its own DMMA pipeline (matvec_fused.cu).
+// headline fused matvec has its own DMMA pipeline (matvec_pipe.cu, matvec_pipe8.cu).
 #pragma once
 #include "common.cuh"
 

@@ -111,6 +111,34 @@ def kernel_matrix(kind, variance, A: PreparedPoints, B: PreparedPoints, *, outpu
     return out
 
 
+def kuf_gram(kind, variance, PZ: PreparedPoints, PX: PreparedPoints, out=None, accumulate=False) -> torch.Tensor:
+    """``Kuf Kfu`` ``[M, M]`` over the rows of ``PX`` (``cggp_kuf_gram``: ``Kuf`` evaluated in L2-sized row chunks,
+    contracted by the library's FP64 DMMA GEMM as a symmetric rank-k update).  Not all-reduced."""
+    ctx = _lib.context(PZ.P.device)
+    ctx.use_current_stream()
+    M = PZ.n
+    if out is None:
+        out = torch.empty((M, M), dtype=PZ.P.dtype, device=PZ.P.device)
+        accumulate = False
+    ctx.check(ctx.lib.cggp_kuf_gram(
+        ctx.handle, _lib.dtype_code(PZ.P.dtype), int(kind), float(variance), _lib.ptr(PX.P), _lib.ptr(PX.norms), PX.n,
+        _lib.ptr(PZ.P), _lib.ptr(PZ.norms), M, PZ.D, PZ.ldp, _lib.ptr(out), out.stride(0), 1 if accumulate else 0))
+    return out
+
+
+def symm_matmul(A: torch.Tensor, V: torch.Tensor) -> torch.Tensor:
+    """``V @ A`` for a symmetric ``A`` through ``cggp_symm_matmul`` (HBM-bound GEMV for few rows of V, FP64 DMMA GEMM
+    for many)."""
+    A, V = _lib.row_major(A), _lib.row_major(V)
+    ctx = _lib.context(A.device)
+    ctx.use_current_stream()
+    Y = torch.empty_like(V)
+    if V.shape[0] and A.shape[0]:
+        ctx.check(ctx.lib.cggp_symm_matmul(ctx.handle, _lib.dtype_code(A.dtype), _lib.ptr(A), A.stride(0), A.shape[0],
+                                           _lib.ptr(V), V.stride(0), V.shape[0], _lib.ptr(Y), Y.stride(0)))
+    return Y
+
+
 def kernel_matrix_param_grads(kind, variance, lengthscales, A: PreparedPoints, B: PreparedPoints, G) -> torch.Tensor:
     """``[dL/dvariance, dL/dlengthscales (D)]`` of ``K(A, B)`` from ``G = dL/dK`` in one fused, deterministic sweep
     (``cggp_kernel_matrix_backward``)."""
@@ -177,14 +205,12 @@ class _SGPRTermsFn(torch.autograd.Function):
         PX = prepare_points(X, ls, PZ.P.dtype)
         M = PZ.n
         Kzz = kernel_matrix(kind, var, PZ, PZ)
-        G = torch.zeros((M, M), dtype=PZ.P.dtype, device=PZ.P.device)
+        G = kuf_gram(kind, var, PZ, PX)  # symmetric rank-k updates on the library's DMMA GEMM
         W = torch.zeros((M, Y.shape[1]), dtype=PZ.P.dtype, device=PZ.P.device)
-        step = max(1, (1 << 27) // max(M, 1))
+        step = max(1, (1 << 24) // max(M, 1))
         for s in range(0, PX.n, step):
             e = min(PX.n, s + step)
-            Kzx = kernel_matrix(kind, var, PZ, PX.rows(s, e))
-            G.addmm_(Kzx, Kzx.t())
-            W.addmm_(Kzx, Y[s:e])
+            W.addmm_(kernel_matrix(kind, var, PZ, PX.rows(s, e)), Y[s:e])  # [M, nc] @ [nc, P]: P columns, HBM-bound
         c = _lib.context(PZ.P.device)
         if c.world > 1:
             c.allreduce_sum_(G)
@@ -217,12 +243,14 @@ class _SGPRTermsFn(torch.autograd.Function):
         for s in range(0, PX.n, step):
             e = min(PX.n, s + step)
             rows = PX.rows(s, e)
-            dK = torch.zeros((PZ.n, e - s), dtype=PZp.dtype, device=PZp.device)
+            # dL/dKfu [nc, M] = Kfu (dG + dG^T) + Y dW^T: the N M^2 part on the library's DMMA GEMM (sym is symmetric)
             if sym is not None:
-                dK.addmm_(sym, kernel_matrix(kind, var, PZ, rows))
+                dKt = symm_matmul(sym, kernel_matrix(kind, var, rows, PZ))
+            else:
+                dKt = torch.zeros((e - s, PZ.n), dtype=PZp.dtype, device=PZp.device)
             if dW is not None:
-                dK.addmm_(dW, Y[s:e].t())
-            shard += kmb(PZ, rows, dK)
+                dKt.addmm_(Y[s:e], dW.t())  # rank-P update
+            shard += kmb(rows, PZ, dKt)
         if c.world > 1:
             c.allreduce_sum_(shard)
         g = shard

@@ -10,7 +10,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .kernels import PreparedPoints, Stationary, kernel_matrix, kernel_matrix_param_grads, prepare_tf32
+from .kernels import (PreparedPoints, Stationary, kernel_matrix, kernel_matrix_param_grads, kuf_gram, prepare_tf32,
+                      symm_matmul)
 
 
 class LinearOperator:
@@ -65,7 +66,7 @@ class SGPROperator(LinearOperator):
 
     def __init__(self, kernel: Stationary, X, Z, noise_variance: float, jitter: float = 1e-6, variant: int = 0,
                  tf32_nsplit: int = 16):
-        """``variant``: 0 auto, 1 two-sweep kernels, 2 / 3 float64 fused kernels, 4 float32 tensor-core (tcgen05 TF32)
+        """``variant``: 0 auto, 1 two-sweep kernels, 3 float64 fused pipelined kernels, 4 float32 tensor-core (tcgen05 TF32)
         kernels - the default for float32 on sm_100 where the tiles fit (D <= 128).
         ``tf32_nsplit`` selects the tensor-core arithmetic: 16 (default) = 3xFP16 with a per-row power-of-two scale
         (float32-accurate distances at twice the TF32 rate), 3 = 3xTF32 (same accuracy), 1 = one TF32 pass (~1e-3
@@ -186,7 +187,7 @@ class SGPROperator(LinearOperator):
         Computed in row batches so that nothing of size N x M is ever resident."""
         Y = _lib.row_major(_lib.as_device_tensor(Y, self.dtype))
         ctx = _lib.context(self.device)
-        if self.dtype == torch.float64 and self.PZ.D <= 15 and self.n <= 256 * 148 and self.variant in (0, 3):
+        if self.dtype == torch.float64 and self.PZ.D <= 31 and self.n <= 256 * 148 and self.variant in (0, 3):
             # fused: phase 2 of the pipelined kernel with the row weights given (cggp_kuf_times)
             ctx.use_current_stream()
             W = torch.empty((Y.shape[1], self.n), dtype=self.dtype, device=self.device)
@@ -228,13 +229,9 @@ class SGPROperator(LinearOperator):
         """``Kuf Kfu`` as a dense ``[M, M]`` matrix over the local shard (+ all-reduce when ``rows`` is None): the
         materialised form GPflow's SGPR builds (``A A^T``), needed where a log-determinant or a trace is required
         (``SGPR.elbo``).  Row chunks of ``Kuf`` are evaluated on the fly by ``cggp_kernel_matrix``; the rank-k updates
-        are plain library GEMMs (cuBLAS DGEMM: ``N M^2`` flop, not on the per-iteration path)."""
+        run on the library's own FP64 DMMA GEMM, lower tiles only (``cggp_kuf_gram``)."""
         src = self.PX if rows is None else rows
-        G = torch.zeros((self.n, self.n), dtype=self.dtype, device=self.device)
-        step = max(1, (1 << 27) // max(self.n, 1))
-        for s in range(0, src.n, step):
-            Kzx = kernel_matrix(self.kernel.kind, self.kernel.variance, self.PZ, src.rows(s, min(src.n, s + step)))
-            G.addmm_(Kzx, Kzx.t())
+        G = kuf_gram(self.kernel.kind, self.kernel.variance, self.PZ, src)
         ctx = _lib.context(self.device)
         if rows is None and ctx.world > 1:
             ctx.allreduce_sum_(G)

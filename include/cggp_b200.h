@@ -127,10 +127,11 @@ int cggp_cluster_stats(cggp_ctx* ctx, int dtype, const int64_t* dev_idx, const v
 /* ---------------------------------------------------------------------------------------------------------
  * Matrix-free product with Kuf Kfu  (the north-star operator's data term)
  *   W[b, :] = V[b, :] @ (Kuf Kfu),  Kfu[i, j] = k(x_i, z_j) never materialised; X is this rank's shard.
- *   variant: 0 = auto, 1 = simple two-sweep kernels (any dtype / D), 2 = fused register-tile kernel, 3 = fused
- *   software-pipelined kernel (TMA-staged X tiles, K parked in shared memory; the default where supported:
- *   float64, D <= 15).  Variants 2 and 3 evaluate every Gram entry once per application.  float32 has its own
- *   tensor-core entry point, cggp_kuf_kfu_matvec_tf32 below.
+ *   variant: 0 = auto, 1 = simple two-sweep kernels (any dtype / D), 3 = fused software-pipelined kernels (TMA-staged
+ *   X tiles, K parked in shared memory; the default where supported: float64, D <= 31): every Gram entry is evaluated
+ *   once per application; B <= 2 right-hand sides per sweep with FMA contractions, from B = 3 on eight per sweep with
+ *   both tile contractions on DMMA (csrc/matvec_pipe8.cu).  (2 was a register-tile kernel of round 1, removed.)
+ *   float32 has its own tensor-core entry point, cggp_kuf_kfu_matvec_tf32 below.
  *   The result is NOT all-reduced; call cggp_allreduce_sum (cggp_cg_solve does it per iteration).
  * ------------------------------------------------------------------------------------------------------- */
 int cggp_kuf_kfu_matvec(cggp_ctx* ctx, int dtype, int kind, double variance,
@@ -176,12 +177,22 @@ int cggp_kuf_times_tf32(cggp_ctx* ctx, int kind, double variance,
 
 /* W[p, j] = sum_i k(z_j, x_i) Y[i, p]   (Kuf @ Y over this rank's shard, the right-hand side `Kuf y` of the SGPR
  * system and GPflow's `A @ err`): fused, Kuf never materialised (the second contraction of the pipelined kernel with
- * the row weights given).  Y is [n, ldy] row-major with P columns, W is [P, ldw].  float64, D <= 15; CGGP_ERR_UNSUPPORTED
+ * the row weights given).  Y is [n, ldy] row-major with P columns, W is [P, ldw].  float64, D <= 31; CGGP_ERR_UNSUPPORTED
  * otherwise (the Python layer then forms Kuf in row chunks with cggp_kernel_matrix).  Not all-reduced. */
 int cggp_kuf_times(cggp_ctx* ctx, int dtype, int kind, double variance,
                    const void* dev_PX, const void* dev_normsX, int64_t n,
                    const void* dev_PZ, const void* dev_normsZ, int64_t m, int D, int64_t ldp,
                    const void* dev_Y, int64_t ldy, int P, void* dev_W, int64_t ldw);
+
+/* G[m, m] (+)= Kuf Kfu over this rank's n rows (G[a, b] = sum_i k(z_a, x_i) k(x_i, z_b)): the Gram matrix GPflow's
+ * SGPR materialises as A A^T (cggp/cli_utils.py:444-446 -> gpflow.models.SGPR), needed where a
+ * log-determinant or a trace is (SGPR.elbo) and for Nystrom-style preconditioners.  Kuf is evaluated in L2-sized row
+ * chunks and contracted by the library's own FP64 DMMA GEMM as a symmetric rank-k update (lower tiles only, mirrored
+ * at the end); float32 uses the FFMA tile GEMM.  accumulate != 0 adds to the G passed in (symmetric).  Not all-reduced. */
+int cggp_kuf_gram(cggp_ctx* ctx, int dtype, int kind, double variance,
+                  const void* dev_PX, const void* dev_normsX, int64_t n,
+                  const void* dev_PZ, const void* dev_normsZ, int64_t m, int D, int64_t ldp,
+                  void* dev_G, int64_t ldg, int accumulate);
 
 /* Y[B, n] = V[B, n] @ A[n, n] for SYMMETRIC A (CG's `state.p @ A`, cggp/conjugate_gradient.py:65,74,87). */
 int cggp_symm_matmul(cggp_ctx* ctx, int dtype, const void* dev_A, int64_t lda, int64_t n,

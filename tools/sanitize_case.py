@@ -20,7 +20,7 @@ def main():
         y = torch.randn(N, 2, dtype=torch.float64, device="cuda", generator=g)
         k = cb.kernels.KERNELS[kern](1.1, [1.3] * D)
         op = cb.SGPROperator(k, X, Z, 0.1)
-        ws = [op.kuf_kfu_matmul(V, variant=v) for v in (1, 2, 3)]
+        ws = [op.kuf_kfu_matmul(V, variant=v) for v in (1, 3)]
         assert float((ws[2] - ws[0]).abs().max() / ws[0].abs().max()) < 1e-10
         op.kuf_times(y)
         rhs = torch.randn(2, M, dtype=torch.float64, device="cuda", generator=g)
