@@ -195,9 +195,10 @@ class Context:
         idbuf = (C.c_char * 128).from_buffer_copy(ident[0])
         self.check(self.lib.cggp_ctx_comm_init(self.handle, C.cast(idbuf, C.c_void_p), rank, world))
         self.world, self.rank = world, rank
-        # opt-in (CGGP_PEER_ALLREDUCE=1): measured on 2 B200 at 31 us per call against ncclAllReduce's 24 us, both
-        # dominated by waiting for the slower rank's product - no gain, so NCCL stays the default
-        if world > 1 and os.environ.get("CGGP_PEER_ALLREDUCE", "0") == "1":
+        # NVLink peer buffers (ranks of one node): the CG loop's fused tail kernel all-reduces the partial product
+        # straight out of peer memory (csrc/cg.cu cg_tail_kernel).  CGGP_PEER_ALLREDUCE=0 keeps everything on NCCL;
+        # if the IPC mapping fails on any rank, all ranks agree to stay on NCCL.
+        if world > 1 and os.environ.get("CGGP_PEER_ALLREDUCE", "1") == "1":
             self._init_peers(group, world)
 
     def _init_peers(self, group, world, slot_bytes: int = 1 << 20):

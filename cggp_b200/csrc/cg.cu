@@ -9,6 +9,7 @@
 //
 // Rounding follows the reference op by op where it is cheap to do so (separate multiply and add, (p*rz')/rz with a
 // true division, guards `<= 1e-16 -> 0`), so trajectories differ from the TF path only through summation order.
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -89,10 +90,7 @@ __device__ void block_precond_apply(const StepArgs<T>& a, const T* __restrict__ 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(512) cg_step_kernel(const StepArgs<T> a) {
-  if (a.state && a.state[0] == 0) return;
-  __shared__ T red[33];
-  __shared__ int s_last;
+__device__ __forceinline__ void cg_step_body(const StepArgs<T>& a, T* red, int& s_last) {
   const int b = blockIdx.x;
   const int64_t n = a.n;
   const T* q = a.q + (int64_t)b * n;
@@ -185,6 +183,99 @@ __global__ void __launch_bounds__(512) cg_step_kernel(const StepArgs<T> a) {
     a.state[2] = 0;
     a.state[0] = (over && it < a.max_iterations) ? 1 : 0;
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) cg_step_kernel(const StepArgs<T> a) {
+  if (a.state && a.state[0] == 0) return;
+  __shared__ T red[33];
+  __shared__ int s_last;
+  cg_step_body(a, red, s_last);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused tail of an iteration on the matrix-free operator (Eye preconditioner, B <= 8): ONE kernel does
+//   (1) the all-reduce of this rank's partial product over NVLink peer memory: every rank copies its vector into its
+//       own IPC-shared slot, publishes a sequence number, waits for the other ranks' numbers and sums all slots in
+//       RANK ORDER straight out of peer memory (bit-identical on all ranks; the protocol of peer_allreduce_kernel),
+//   (2) q = p Kuu + scale * w   (p Kuu was computed on a side stream while the product ran), and
+//   (3) the CG vector update with its dot products, stopping condition and history row (cg_step_body).
+// Per iteration this replaces ncclAllReduce + the Kuu product (now overlapped) + the step kernel: the serial tail
+// after the product drops from ~130 us to one short kernel (profiles/r02_tail.md).
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+struct TailArgs {
+  const T* w;       // [B, n] this rank's partial Kuf Kfu product (already all-reduced when world == 1 or by NCCL)
+  T* q;             // [B, n] in: p @ Kuu, out: p @ Sigma
+  T scale;
+  // peer exchange (world > 1)
+  char* const* peers;
+  int rank, world;
+  unsigned seq;
+  int64_t slot_bytes;
+  int* counter;
+};
+
+__device__ __forceinline__ unsigned tail_ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tail_st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) cg_tail_kernel(const StepArgs<T> a, const TailArgs<T> t) {
+  if (a.state && a.state[0] == 0) return;  // identical on every rank: all ranks skip together
+  __shared__ T red[33];
+  __shared__ int s_last;
+  const int b = blockIdx.x;
+  const int64_t n = a.n;
+  const T* w = t.w + (int64_t)b * n;
+  T* q = t.q + (int64_t)b * n;
+  if (t.world > 1) {
+    const int slot = (int)(t.seq & 1u);
+    T* mine = reinterpret_cast<T*>(t.peers[t.rank] + slot * t.slot_bytes) + (int64_t)b * n;
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) mine[k] = w[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      if (atomicAdd(t.counter, 1) == (int)gridDim.x - 1) {  // the last CTA of this rank: all rows are in the slot
+        *t.counter = 0;
+        __threadfence_system();
+        tail_st_release_sys(reinterpret_cast<unsigned*>(t.peers[t.rank] + 2 * t.slot_bytes) + slot, t.seq);
+      }
+      const long long t0 = clock64();
+      for (int r = 0; r < t.world; ++r) {
+        const unsigned* flag = reinterpret_cast<const unsigned*>(t.peers[r] + 2 * t.slot_bytes) + slot;
+        while ((int)(tail_ld_acquire_sys(flag) - t.seq) < 0) {
+          if (clock64() - t0 > (1ll << 34)) {  // ~8 s: a peer died; report instead of hanging the device
+            if (a.state) a.state[3] = 1;
+            break;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) {
+      T part[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r)
+        part[r] = r < t.world
+                      ? __ldcv(reinterpret_cast<const T*>(t.peers[r] + slot * t.slot_bytes) + (int64_t)b * n + k)
+                      : T(0);
+      T v = T(0);
+#pragma unroll
+      for (int r = 0; r < 16; ++r)
+        if (r < t.world) v += part[r];
+      q[k] = fma(t.scale, v, q[k]);
+    }
+  } else {
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) q[k] = fma(t.scale, w[k], q[k]);
+  }
+  __syncthreads();  // q of this row is complete (written by this CTA)
+  cg_step_body(a, red, s_last);
 }
 
 // Second half of an iteration with the dense preconditioner: given z = r @ Pinv, rz' = sum z*r (:157-style),
@@ -382,6 +473,21 @@ extern "C" int cggp_cg_fused_step(cggp_ctx* ctx, int dtype, int B, int64_t n, co
 // ---------------------------------------------------------------------------------------------------------
 // Operator application  Y = V @ A  for the two operator forms
 // ---------------------------------------------------------------------------------------------------------
+// W = V @ (Kuf_r Kfu_r) on this rank's shard (not all-reduced)
+static int apply_kuf_kfu(cggp_ctx* ctx, const cggp_operator* op, const void* V, int B, void* wbuf, const int* active) {
+  const int64_t n = op->n;
+  if (op->dtype == CGGP_F32 && op->dev_X32_big) {
+    ProfScope prof(ctx, 0);
+    return cggp_matvec_tf32(ctx, op->kind, op->variance, (const float*)op->dev_X32_big, (const float*)op->dev_X32_small,
+                            (const float*)op->dev_x32_norms, op->n_local, (const float*)op->dev_Z32_big,
+                            (const float*)op->dev_Z32_small, (const float*)op->dev_z32_norms, n, op->D, (const float*)V,
+                            n, B, (float*)wbuf, n, (op->tf32_nsplit == 1 || op->tf32_nsplit == 16) ? op->tf32_nsplit : 3,
+                            active);
+  }
+  return cggp_matvec_dispatch(ctx, op->dtype, op->kind, op->variance, op->dev_PX, op->dev_normsX, op->n_local,
+                              op->dev_PZ, op->dev_normsZ, n, op->D, op->ldp, V, n, B, wbuf, n, op->variant, active);
+}
+
 static int apply_operator(cggp_ctx* ctx, const cggp_operator* op, const void* V, int B, void* Y, void* wbuf,
                           const int* active) {
   const int64_t n = op->n;
@@ -404,6 +510,50 @@ static int apply_operator(cggp_ctx* ctx, const cggp_operator* op, const void* V,
   if (rc) return rc;
   // Y = V @ Kuu + scale * W
   return cggp_symm_matmul_ex(ctx, op->dtype, op->dev_A, op->lda, n, V, n, B, Y, n, wbuf, n, op->scale, active);
+}
+
+extern "C" int cggp_peer_enabled(cggp_ctx* ctx);
+
+// One non-refresh iteration on the matrix-free operator with the fused tail (see cg_tail_kernel): p @ Kuu runs on the
+// side stream WHILE the Kuf Kfu product runs on the main stream; the tail kernel then all-reduces over peer memory (or
+// takes the NCCL result), combines and does the vector update.
+template <typename T>
+static int fused_tail_iteration(cggp_ctx* ctx, const cggp_operator* op, StepArgs<T>& a, T* q, T* w, bool peer) {
+  const int64_t n = op->n;
+  const int B = a.B;
+  cudaStream_t main_stream = ctx->stream;
+  CGGP_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main_stream));  // p of this iteration is final
+  CGGP_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+  int rc = apply_kuf_kfu(ctx, op, a.p, B, w, a.state);  // enqueued first: its persistent CTAs take the SMs, the
+  if (rc) return rc;                                    // HBM-bound product below fills in next to them
+  ctx->stream = ctx->side_stream;
+  rc = cggp_symm_matmul_ex(ctx, op->dtype, op->dev_A, op->lda, n, a.p, n, B, q, n, nullptr, 0, 0.0, a.state);
+  ctx->stream = main_stream;
+  if (rc) return rc;
+  CGGP_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
+  if (ctx->world > 1 && !peer) {
+    rc = cggp_allreduce_sum(ctx, op->dtype, w, (int64_t)B * n);
+    if (rc) return rc;
+  }
+  CGGP_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
+  TailArgs<T> t{};
+  t.w = w;
+  t.q = q;
+  t.scale = (T)op->scale;
+  t.world = peer ? ctx->world : 1;
+  t.rank = ctx->rank;
+  if (peer) {
+    t.peers = (char* const*)ctx->peer_ptrs_dev;
+    t.seq = ++ctx->peer_seq;
+    t.slot_bytes = ctx->peer_slot_bytes;
+    t.counter = ctx->peer_counter;
+  }
+  a.mode = MODE_STEP;
+  a.q = q;
+  ProfScope prof(ctx, 2);
+  cg_tail_kernel<T><<<B, 512, 0, main_stream>>>(a, t);
+  CGGP_LAUNCH_CHECK(ctx);
+  return CGGP_OK;
 }
 
 template <typename T>
@@ -433,11 +583,24 @@ static int cg_solve_impl(cggp_ctx* ctx, const cggp_operator* op, const void* rhs
   T* v = (T*)solution;
   T* hrz = half_rz ? (T*)half_rz : half_rz_int;
 
+  // fused tail: matrix-free operator, Eye preconditioner, few right-hand sides; over NVLink peer memory when the
+  // peer buffers are mapped and the vector fits a slot, else after ncclAllReduce (CGGP_FUSED_TAIL=0 switches it off)
+  static const int tail_env = getenv("CGGP_FUSED_TAIL") ? atoi(getenv("CGGP_FUSED_TAIL")) : 1;  // tuning knob
+  const bool eye = !pc || pc->type == CGGP_PRECOND_EYE;
+  const bool fused_tail = tail_env && sgpr && eye && B <= 8;
+  const bool peer_tail = fused_tail && ctx->world > 1 && cggp_peer_enabled(ctx) && (int64_t)vec <= ctx->peer_slot_bytes;
+  if (fused_tail && !ctx->side_stream) {
+    CGGP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    CGGP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CGGP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  }
+
   int* st = ctx->cg_state;
   ctx->cg_state_host[0] = 1;
   ctx->cg_state_host[1] = 0;
   ctx->cg_state_host[2] = 0;
-  CGGP_CUDA(ctx, cudaMemcpyAsync(st, ctx->cg_state_host, 3 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->cg_state_host[3] = 0;
+  CGGP_CUDA(ctx, cudaMemcpyAsync(st, ctx->cg_state_host, 4 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CGGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the pinned staging buffer is reused below
 
   StepArgs<T> a{};
@@ -487,6 +650,11 @@ static int cg_solve_impl(cggp_ctx* ctx, const cggp_operator* op, const void* rhs
     // enqueue one chunk of iterations (skipped on the device once inactive)
     for (int c = 0; c < check_every && enq < max_iterations; ++c, ++enq) {
       const bool reset = (enq % max_steps_cycle) == (max_steps_cycle - 1);  // :71, pre-increment i
+      if (fused_tail && !reset) {
+        rc = fused_tail_iteration<T>(ctx, op, a, q, w, peer_tail);
+        if (rc) goto fail;
+        continue;
+      }
       rc = apply_operator(ctx, op, p, B, q, w, st);
       if (rc) goto fail;
       a.q = q;
@@ -523,10 +691,15 @@ static int cg_solve_impl(cggp_ctx* ctx, const cggp_operator* op, const void* rhs
     ++chunk;
   }
   {
-    cudaError_t e = cudaMemcpyAsync(hstage, st, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(hstage, st, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = CGGP_ERR_CUDA; goto fail; }
     if (host_steps) *host_steps = hstage[1];
+    if (hstage[3] != 0) {
+      ctx->err = "fused CG tail: a peer rank did not publish its partial product in time (NVLink peer all-reduce)";
+      rc = CGGP_ERR_COMM;
+      goto fail;
+    }
   }
   rc = CGGP_OK;
 fail:

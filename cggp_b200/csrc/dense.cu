@@ -73,7 +73,7 @@ symm_gemv_kernel(const T* __restrict__ A, int64_t lda, int64_t n, const T* __res
     for (int b = 0; b < BB; ++b) {
       T s = warp_sum(acc[r][b]);
       if (lane == 0 && j0 + r < n) {
-        if (addend) s += scale * addend[b * ldadd + j0 + r];
+        if (addend) s = fma(scale, addend[b * ldadd + j0 + r], s);
         Y[b * ldy + j0 + r] = s;
       }
     }

@@ -440,6 +440,7 @@ struct Plan {
 template <int KIND, int KS, int WARPS, int RB, int CBW, int NB, int NBUF, int ET = 0, int SQ = 0, int DUP = 0>
 static Plan make_plan() {
   using L = Layout<WARPS, RB, CBW, NB, KS, NBUF, ET, DUP>;
+  static_assert(L::total <= 227 * 1024, "plan exceeds the shared memory of an SM");
   Plan p;
   p.fn = (const void*)kfu_pipe_kernel<KIND, KS, WARPS, RB, CBW, NB, NBUF, ET, SQ, DUP>;
   p.dup = DUP;
@@ -458,7 +459,10 @@ static bool plan_for_nb(int nb, bool deep, Plan& p) {
   // one right-hand side: 1024-entry shared-memory exp table (degree-3 polynomial) + third-order sqrt step + the
   // pre-scaled accumulator pair per row; two: 32-entry shuffle table (degree 5) + two Newton steps (no room for the table)
   if (nb == 1) {
-    p = deep ? make_plan<KIND, KS, 16, 4, 2, 1, 3, 10, 1, 1>() : make_plan<KIND, KS, 16, 6, 2, 1, 2, 10, 1, 1>();
+    if constexpr (KS <= 4)
+      p = deep ? make_plan<KIND, KS, 16, 4, 2, 1, 3, 10, 1, 1>() : make_plan<KIND, KS, 16, 6, 2, 1, 2, 10, 1, 1>();
+    else  // wider X tiles: smaller row blocks keep the kernel inside the 227 KB of shared memory
+      p = deep ? make_plan<KIND, KS, 16, 3, 2, 1, 3, 10, 1, 1>() : make_plan<KIND, KS, 16, 5, 2, 1, 2, 10, 1, 1>();
     return true;
   }
   if constexpr (KS <= 4) {  // 16 <= D <= 31: two and more right-hand sides go through the 8-wide kernel (matvec_pipe8.cu)

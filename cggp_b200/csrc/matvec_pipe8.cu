@@ -360,6 +360,7 @@ struct Plan {
 template <int KIND, int KS, int RB, int NBUF>
 static Plan make_plan() {
   using L = Layout<RB, KS, NBUF>;
+  static_assert(L::total <= 227 * 1024, "plan exceeds the shared memory of an SM");
   Plan p;
   p.fn = (const void*)kfu_pipe8_kernel<KIND, KS, RB, NBUF>;
   p.threads = (WARPS + EWARPS) * 32;

@@ -278,7 +278,18 @@ class SGPR:
         self.dense_threshold = 16
         self._sigma_dense = None
 
+    def _sync(self):
+        """The operator and the cached solves are valid for ONE value of (kernel parameters, likelihood variance):
+        after an in-place optimiser step they are re-prepared / dropped here instead of being reused silently."""
+        s2 = self.likelihood.variance
+        nv = float(s2.detach()) if isinstance(s2, torch.Tensor) else float(s2)
+        if self.operator.stale or nv != self.operator.noise_variance:
+            self.operator.refresh(s2)
+            self._c = None
+            self._sigma_dense = None
+
     def _posterior_weights(self):
+        self._sync()
         if self._c is None:
             rhs = self.operator.kuf_times(self.Y) / self.likelihood.variance  # s^-2 Kuf y  [M, P]
             self._c = self.conjugate_gradient(self.operator, rhs)
@@ -291,6 +302,7 @@ class SGPR:
         factorisations (library calls; this is the reference's own algorithm for this quantity)."""
         import math
 
+        self._sync()
         op, ctx = self.operator, _lib.context(self.operator.device)
         s2 = self.likelihood.variance
         P = self.Y.shape[1]
@@ -334,6 +346,7 @@ class SGPR:
 
     def predict_f(self, Xnew, full_cov: bool = False, full_output_cov: bool = False) -> Moments:
         assert not full_output_cov and not full_cov
+        self._sync()
         Xnew = _lib.as_device_tensor(Xnew, self.X.dtype)
         Kus = Kuf(self.inducing_variable, self.kernel, Xnew)  # [M, B]
         c = self._posterior_weights()

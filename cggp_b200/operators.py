@@ -10,8 +10,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .kernels import (PreparedPoints, Stationary, kernel_matrix, kernel_matrix_param_grads, kuf_gram, prepare_tf32,
-                      symm_matmul)
+from .kernels import (PreparedPoints, Stationary, kernel_matrix, kernel_matrix_param_grads, kuf_gram, prepare_points,
+                      prepare_tf32, symm_matmul)
 
 
 class LinearOperator:
@@ -72,8 +72,10 @@ class SGPROperator(LinearOperator):
         (float32-accurate distances at twice the TF32 rate), 3 = 3xTF32 (same accuracy), 1 = one TF32 pass (~1e-3
         relative on the distances)."""
         self.kernel = kernel
-        self.PZ = kernel.prepare(Z)
-        self.PX = kernel.prepare(X, self.PZ.P.dtype)
+        self._X, self._Z = X, Z
+        self._snapshot()
+        self.PZ = Z if isinstance(Z, PreparedPoints) else prepare_points(Z, self._lengthscales)
+        self.PX = X if isinstance(X, PreparedPoints) else prepare_points(X, self._lengthscales, self.PZ.P.dtype)
         # a tensor that requires grad makes the solve differentiable in the likelihood variance (_SGPRSolveFn)
         self._noise_t = noise_variance if isinstance(noise_variance, torch.Tensor) and noise_variance.requires_grad \
             else None
@@ -84,8 +86,45 @@ class SGPROperator(LinearOperator):
         self.n = self.PZ.n
         self.dtype = self.PZ.P.dtype
         self.device = self.PZ.P.device
-        self.Kuu = kernel_matrix(kernel.kind, kernel.variance, self.PZ, self.PZ, jitter=self.jitter)
         self.tf32_nsplit = int(tf32_nsplit)
+        self._prepare_derived()
+
+    # An operator is valid for ONE value of the kernel hyper-parameters: the scaled points, Kuu and the tensor-core
+    # arrays are prepared from a snapshot taken at construction (or at the last `refresh()`), and every product /
+    # gradient uses that snapshot.  After an in-place optimiser step on the kernel's parameters the operator is
+    # `stale`; using it raises instead of silently mixing old points with new variances.
+    def _snapshot(self):
+        self._variance = float(self.kernel.variance)
+        self._lengthscales = self.kernel.lengthscales.clone()
+
+    @property
+    def stale(self) -> bool:
+        return self._variance != float(self.kernel.variance) or \
+            not torch.equal(self._lengthscales, self.kernel.lengthscales)
+
+    def _check_fresh(self):
+        if self.stale:
+            raise _lib.CggpError("SGPROperator is stale: the kernel hyper-parameters changed since it was prepared; "
+                                 "call operator.refresh() (an operator is valid for one parameter value)")
+
+    def refresh(self, noise_variance=None):
+        """Re-prepare the scaled points, Kuu and the tensor-core arrays from the kernel's CURRENT hyper-parameters
+        (and optionally a new likelihood variance)."""
+        self._snapshot()
+        if noise_variance is not None:
+            self._noise_t = noise_variance if isinstance(noise_variance, torch.Tensor) and \
+                noise_variance.requires_grad else None
+            self.noise_variance = float(noise_variance.detach()) if isinstance(noise_variance, torch.Tensor) \
+                else float(noise_variance)
+        if isinstance(self._Z, PreparedPoints) or isinstance(self._X, PreparedPoints):
+            raise _lib.CggpError("an operator built from prepared points cannot be refreshed: rebuild it")
+        self.PZ = prepare_points(self._Z, self._lengthscales)
+        self.PX = prepare_points(self._X, self._lengthscales, self.PZ.P.dtype)
+        self._prepare_derived()
+        return self
+
+    def _prepare_derived(self):
+        self.Kuu = kernel_matrix(self.kernel.kind, self._variance, self.PZ, self.PZ, jitter=self.jitter)
         self.X32 = self.Z32 = None
         if self.dtype == torch.float32 and self.variant in (0, 4):
             ctx = _lib.context(self.device)
@@ -96,6 +135,7 @@ class SGPROperator(LinearOperator):
                 raise _lib.CggpError("the tcgen05 path needs sm_100 and D <= 128 (3xFP16, 3xTF32) / 256 (1xTF32)")
 
     def c_struct(self):
+        self._check_fresh()
         op = _lib.Operator()
         op.type = _lib.OP_SGPR
         op.dtype = _lib.dtype_code(self.dtype)
@@ -104,7 +144,7 @@ class SGPROperator(LinearOperator):
         op.lda = self.Kuu.stride(0)
         op.kind = self.kernel.kind
         op.D = self.PZ.D
-        op.variance = self.kernel.variance
+        op.variance = self._variance
         op.scale = 1.0 / self.noise_variance
         op.dev_PX = self.PX.P.data_ptr()
         op.dev_normsX = self.PX.norms.data_ptr()
@@ -123,6 +163,7 @@ class SGPROperator(LinearOperator):
 
     def kuf_kfu_matmul(self, V, variant=None, allreduce=True):
         """``V @ (Kuf Kfu)`` over the local shard (+ all-reduce)."""
+        self._check_fresh()
         V = _lib.row_major(V)
         ctx = _lib.context(self.device)
         ctx.use_current_stream()
@@ -130,7 +171,7 @@ class SGPROperator(LinearOperator):
         use = self.variant if variant is None else int(variant)
         if self.X32 is not None and use in (0, 4):
             ctx.check(ctx.lib.cggp_kuf_kfu_matvec_tf32(
-                ctx.handle, self.kernel.kind, self.kernel.variance, _lib.ptr(self.X32.big), _lib.ptr(self.X32.small),
+                ctx.handle, self.kernel.kind, self._variance, _lib.ptr(self.X32.big), _lib.ptr(self.X32.small),
                 _lib.ptr(self.X32.norms), self.PX.n, _lib.ptr(self.Z32.big), _lib.ptr(self.Z32.small),
                 _lib.ptr(self.Z32.norms), self.n, self.PZ.D, _lib.ptr(V), V.stride(0), V.shape[0], _lib.ptr(W),
                 W.stride(0), self.tf32_nsplit))
@@ -140,7 +181,7 @@ class SGPROperator(LinearOperator):
         if use == 4:
             raise _lib.CggpError("variant 4 (tcgen05 TF32) is not available for this operator")
         ctx.check(ctx.lib.cggp_kuf_kfu_matvec(
-            ctx.handle, _lib.dtype_code(self.dtype), self.kernel.kind, self.kernel.variance,
+            ctx.handle, _lib.dtype_code(self.dtype), self.kernel.kind, self._variance,
             _lib.ptr(self.PX.P), _lib.ptr(self.PX.norms), self.PX.n, _lib.ptr(self.PZ.P), _lib.ptr(self.PZ.norms),
             self.n, self.PZ.D, self.PZ.ldp, _lib.ptr(V), V.stride(0), V.shape[0], _lib.ptr(W), W.stride(0),
             use))
@@ -163,7 +204,8 @@ class SGPROperator(LinearOperator):
         ``dL/dKuf = -(sol^T (lam Kuf) + lam^T (sol Kuf)) / s2`` chunk by chunk into ``cggp_kernel_matrix_backward``,
         ``dL/ds2 = sum_b <sol_b Kuf, lam_b Kuf> / s2^2``.  The shard terms are all-reduced.  Returns
         ``(dL/dvariance [1], dL/dlengthscales [D], dL/ds2 [1])``."""
-        kind, var, ls = self.kernel.kind, self.kernel.variance, self.kernel.lengthscales
+        self._check_fresh()
+        kind, var, ls = self.kernel.kind, self._variance, self._lengthscales
         D, M = self.PZ.D, self.n
         g = kernel_matrix_param_grads(kind, var, ls, self.PZ, self.PZ, -(sol.t() @ lam))  # replicated Kuu term
         shard = torch.zeros((2 + D,), dtype=self.dtype, device=self.device)
@@ -185,6 +227,7 @@ class SGPROperator(LinearOperator):
     def kuf_times(self, Y):
         """``Kuf @ Y`` for the local shard ``Y [n_local, P]`` (+ all-reduce): the right-hand side ``Kuf y``.
         Computed in row batches so that nothing of size N x M is ever resident."""
+        self._check_fresh()
         Y = _lib.row_major(_lib.as_device_tensor(Y, self.dtype))
         ctx = _lib.context(self.device)
         if self.dtype == torch.float64 and self.PZ.D <= 31 and self.n <= 256 * 148 and self.variant in (0, 3):
@@ -192,7 +235,7 @@ class SGPROperator(LinearOperator):
             ctx.use_current_stream()
             W = torch.empty((Y.shape[1], self.n), dtype=self.dtype, device=self.device)
             ctx.check(ctx.lib.cggp_kuf_times(
-                ctx.handle, _lib.dtype_code(self.dtype), self.kernel.kind, self.kernel.variance, _lib.ptr(self.PX.P),
+                ctx.handle, _lib.dtype_code(self.dtype), self.kernel.kind, self._variance, _lib.ptr(self.PX.P),
                 _lib.ptr(self.PX.norms), self.PX.n, _lib.ptr(self.PZ.P), _lib.ptr(self.PZ.norms), self.n, self.PZ.D,
                 self.PZ.ldp, _lib.ptr(Y), Y.stride(0), Y.shape[1], _lib.ptr(W), W.stride(0)))
             out = W.t().contiguous()
@@ -205,7 +248,7 @@ class SGPROperator(LinearOperator):
             Yt = Y.t().contiguous()
             W = torch.empty((Y.shape[1], self.n), dtype=self.dtype, device=self.device)
             ctx.check(ctx.lib.cggp_kuf_times_tf32(
-                ctx.handle, self.kernel.kind, self.kernel.variance, _lib.ptr(self.X32.big), _lib.ptr(self.X32.small),
+                ctx.handle, self.kernel.kind, self._variance, _lib.ptr(self.X32.big), _lib.ptr(self.X32.small),
                 _lib.ptr(self.X32.norms), self.PX.n, _lib.ptr(self.Z32.big), _lib.ptr(self.Z32.small),
                 _lib.ptr(self.Z32.norms), self.n, self.PZ.D, _lib.ptr(Yt), Yt.stride(0), Yt.shape[0], _lib.ptr(W),
                 W.stride(0), self.tf32_nsplit))
@@ -217,7 +260,7 @@ class SGPROperator(LinearOperator):
         step = max(1, (1 << 27) // max(self.n, 1))
         for s in range(0, self.PX.n, step):
             e = min(self.PX.n, s + step)
-            Kzx = kernel_matrix(self.kernel.kind, self.kernel.variance, self.PZ, self.PX.rows(s, e))
+            Kzx = kernel_matrix(self.kernel.kind, self._variance, self.PZ, self.PX.rows(s, e))
             out += Kzx @ Y[s:e]
         ctx = _lib.context(self.device)
         if ctx.world > 1:
@@ -230,8 +273,9 @@ class SGPROperator(LinearOperator):
         materialised form GPflow's SGPR builds (``A A^T``), needed where a log-determinant or a trace is required
         (``SGPR.elbo``).  Row chunks of ``Kuf`` are evaluated on the fly by ``cggp_kernel_matrix``; the rank-k updates
         run on the library's own FP64 DMMA GEMM, lower tiles only (``cggp_kuf_gram``)."""
+        self._check_fresh()
         src = self.PX if rows is None else rows
-        G = kuf_gram(self.kernel.kind, self.kernel.variance, self.PZ, src)
+        G = kuf_gram(self.kernel.kind, self._variance, self.PZ, src)
         ctx = _lib.context(self.device)
         if rows is None and ctx.world > 1:
             ctx.allreduce_sum_(G)

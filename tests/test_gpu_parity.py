@@ -1010,6 +1010,43 @@ def test_batched_prediction_and_metrics(cb, models_golden):
     np.testing.assert_allclose(met["test/nlpd"], -lpd.sum() / X.shape[0], rtol=1e-9)
 
 
+def test_operator_is_valid_for_one_parameter_value(cb):
+    """An in-place optimiser step on the kernel's parameters makes a prepared operator stale: it raises instead of
+    mixing old scaled points with the new variance; refresh() re-prepares it, and the SGPR model re-syncs itself."""
+    rng = np.random.default_rng(3)
+    N, M, D = 600, 48, 3
+    X, Z, Y = rng.standard_normal((N, D)), rng.standard_normal((M, D)), rng.standard_normal((N, 1))
+    var = torch.tensor(1.3, dtype=torch.float64, device="cuda", requires_grad=True)
+    ls = torch.full((D,), 1.1, dtype=torch.float64, device="cuda", requires_grad=True)
+    k = cb.Matern32(var, ls)
+    op = cb.SGPROperator(k, dev(X), dev(Z), 0.2)
+    V = dev(rng.standard_normal((1, M)))
+    with torch.no_grad():
+        W0 = op.kuf_kfu_matmul(V)
+        var.mul_(1.5)
+        ls.mul_(0.9)
+    assert op.stale
+    with pytest.raises(cb._lib.CggpError):
+        op.kuf_kfu_matmul(V)
+    with pytest.raises(cb._lib.CggpError):
+        cb.conjugate_gradient(op, V, None, 1e-6, None, 5, 6)
+    with torch.no_grad():
+        W1 = op.refresh().kuf_kfu_matmul(V)
+    ok = g.Matern32(variance=float(var), lengthscales=ls.detach().cpu().numpy())
+    np.testing.assert_allclose(cpu(W1), om.kuf_kfu_matmul(ok, X, Z, cpu(V)), rtol=1e-11)
+    assert not torch.allclose(W0, W1)
+    # the model drops its cached posterior weights / dense Sigma when the parameters move
+    cg = cb.ConjugateGradient(1e-12, max_iterations=400)
+    with torch.no_grad():
+        model = cb.sgpr_class((dev(X), dev(Y)), k, cb.Gaussian(0.2), dev(Z), conjugate_gradient=cg)
+        mu0, _ = model.predict_f(dev(X[:20]))
+        var.mul_(0.5)
+        mu1, _ = model.predict_f(dev(X[:20]))
+        fresh = cb.sgpr_class((dev(X), dev(Y)), k, cb.Gaussian(0.2), dev(Z), conjugate_gradient=cg)
+        mu2, _ = fresh.predict_f(dev(X[:20]))
+    assert torch.equal(mu1, mu2) and not torch.allclose(mu0, mu1)
+
+
 def test_dlpack_zero_copy_import(cb):
     """Foreign device tensors come in through __dlpack__ without a copy (TF: tf.experimental.dlpack)."""
 

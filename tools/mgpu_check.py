@@ -34,6 +34,10 @@ def main():
     op1s = cb.SGPROperator(k, X.to(dev), Z.to(dev), 0.1, variant=1)
     _, (_, _, hist1s) = cb.conjugate_gradient(op1s, rhs1, None, 0.0, None, its, its + 1, return_history=True)
     floor = torch.cummax(((hist1s - hist1).abs() / hist1).max(dim=1).values, dim=0).values
+    # five right-hand sides (the probe solves of cggp/models.py:308-314): 8-wide DMMA-contraction sweeps
+    g5 = torch.Generator().manual_seed(11)
+    rhs5 = torch.randn(5, M, dtype=torch.float64, generator=g5).to(dev)
+    sol5_1, (_, _, hist5_1) = cb.conjugate_gradient(op1, rhs5, None, 0.0, None, 6, 7, return_history=True)
     del op1, op1s
     # sharded solve: this rank's rows, one NCCL all-reduce per operator application
     ctx.init_comm()
@@ -49,6 +53,12 @@ def main():
     early = float(dh[:4].max())
     within = bool((dh <= torch.clamp(50.0 * floor, min=2e-9)).all())
     ok = same and early < 2e-9 and within and int(steps) == its
+    sol5, (_, _, hist5) = cb.conjugate_gradient(op, rhs5, None, 0.0, None, 6, 7, return_history=True)
+    g5l = [torch.empty_like(sol5) for _ in range(world)]
+    dist.all_gather(g5l, sol5)
+    same5 = all(torch.equal(g5l[0], t) for t in g5l)
+    early5 = float(((hist5 - hist5_1).abs() / hist5_1)[:3].max())
+    ok = ok and same5 and early5 < 2e-9
     # float32 leg: the tcgen05 TF32 kernels on the shards + the same all-reduce, against one GPU over all rows
     N32, M32, D32 = 60_000, 512, 40
     g32 = torch.Generator().manual_seed(9)
@@ -64,7 +74,8 @@ def main():
     dev32 = float((w_sh - w_all).abs().max() / w_all.abs().max())
     ok = ok and op_sh.X32 is not None and dev32 < 1e-5
     if rank == 0:
-        msg = (f"world={world} identical_on_ranks={same} early_dev={early:.2e} max_dev={float(dh.max()):.2e} "
+        msg = (f"world={world} peer_tail={ctx.peer_allreduce} identical_on_ranks={same} early_dev={early:.2e} "
+               f"max_dev={float(dh.max()):.2e} rhs5_identical={same5} rhs5_early_dev={early5:.2e} "
                f"tf32_sharded_vs_single={dev32:.2e}")
         print(("MGPU_CHECK ok " if ok else "MGPU_CHECK FAIL ") + msg, flush=True)
     dist.barrier()
