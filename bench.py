@@ -189,6 +189,120 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# roofline denominators measured in the same run (MEASURED_PEAKS.json has HBM + BF16 only)
+# ----------------------------------------------------------------------------------------------------------------
+def fp64_peaks(ctx, device):
+    """FP64 DMMA / DFMA issue rates, the throughput of the exp and sqrt routines the pipelined kernels use
+    (cggp_microbench) and a cuBLAS DGEMM (torch.matmul float64, the denominator BASELINE.md 2 names) - library GEMM
+    used ONLY as a yardstick."""
+    import ctypes as C
+
+    import torch
+
+    out = {}
+    for key, which in (("dmma_tflops", 1), ("dfma_tflops", 0), ("exp_gevals", 5), ("sqrt_gevals", 6)):
+        g = C.c_double(0.0)
+        try:
+            ctx.check(ctx.lib.cggp_microbench(ctx.handle, which, 4096, C.byref(g)))
+            out[key] = g.value / 1e3 if key.endswith("tflops") else g.value
+        except Exception as exc:  # pragma: no cover
+            out[key] = None
+            out[key + "_error"] = str(exc)
+    try:
+        n = 6144
+        A = torch.randn(n, n, device=device, dtype=torch.float64)
+        B = torch.randn(n, n, device=device, dtype=torch.float64)
+        for _ in range(2):
+            A @ B
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(5):
+            A @ B
+        t1.record()
+        torch.cuda.synchronize()
+        out["dgemm_cublas_tflops"] = 5 * 2.0 * n ** 3 / (t0.elapsed_time(t1) * 1e-3) / 1e12
+        del A, B
+    except Exception as exc:  # pragma: no cover
+        out["dgemm_cublas_tflops"] = None
+        out["dgemm_error"] = str(exc)
+    return out
+
+
+def parity_single_rank(cb, device, its=12):
+    """First half of the N > 1 parity check, run BEFORE the communicator exists: every rank solves the same 200k-row
+    problem on its own GPU (no all-reduce) and keeps the residual history."""
+    import torch
+
+    N, M, D = 200_003, 1024, 11
+    g = torch.Generator().manual_seed(5)
+    X = torch.randn(N, D, dtype=torch.float64, generator=g)
+    y = torch.sin(X.sum(-1, keepdim=True))
+    Z = X[torch.randperm(N, generator=g)[:M]].clone() + 0.05
+    k = cb.Matern52(variance=1.0, lengthscales=[1.5] * D)
+    op1 = cb.SGPROperator(k, X.to(device), Z.to(device), 0.1)
+    rhs1 = (op1.kuf_times(y.to(device)) / 0.1).t().contiguous()
+    _, (_, _, h1) = cb.conjugate_gradient(op1, rhs1, None, 0.0, None, its, its + 1, return_history=True)
+    # the same solve through the independent two-sweep kernels: rounding-noise floor of this ill-conditioned system
+    op1s = cb.SGPROperator(k, X.to(device), Z.to(device), 0.1, variant=1)
+    _, (_, _, h1s) = cb.conjugate_gradient(op1s, rhs1, None, 0.0, None, its, its + 1, return_history=True)
+    floor = torch.cummax(((h1s - h1).abs() / h1).max(dim=1).values, dim=0).values
+    return {"X": X, "y": y, "Z": Z, "kernel": k, "hist": h1, "floor": floor, "its": its}
+
+
+def parity_sharded(cb, device, st, rank, world):
+    """Second half (communicator initialised): the same problem with its rows sharded over the ranks through the code
+    path the benchmark times; all ranks must hold bit-identical iterates, and the residual history must follow the
+    1-rank solve (2e-9 on 0.5|r|^2 for the first iterations, then the measured rounding-noise floor x 50)."""
+    import torch
+    import torch.distributed as dist
+
+    from cggp_b200.sharding import shard_rows
+
+    s, e = shard_rows(st["X"].shape[0], rank, world)
+    op = cb.SGPROperator(st["kernel"], st["X"][s:e].to(device), st["Z"].to(device), 0.1)
+    rhs = (op.kuf_times(st["y"][s:e].to(device)) / 0.1).t().contiguous()
+    its = st["its"]
+    sol, (steps, _, h) = cb.conjugate_gradient(op, rhs, None, 0.0, None, its, its + 1, return_history=True)
+    gathered = [torch.empty_like(sol) for _ in range(world)]
+    dist.all_gather(gathered, sol)
+    same = all(torch.equal(gathered[0], t) for t in gathered)
+    dh = ((h - st["hist"]).abs() / st["hist"]).max(dim=1).values
+    early = float(dh[:4].max())
+    within = bool((dh <= torch.clamp(50.0 * st["floor"], min=2e-9)).all())
+    return {"problem": "N=200003, M=1024, D=11, matern52, 12 iterations, rows sharded as in the timed run",
+            "rank_identical_iterates": bool(same), "early_rel_dev_vs_1rank": early,
+            "max_rel_dev_vs_1rank": float(dh.max()), "noise_floor_last": float(st["floor"][-1]),
+            "within_tolerance": bool(within and early < 2e-9), "steps": int(steps),
+            "tolerance": "0.5|r|^2: 2e-9 relative on iterations 0-3, then max(2e-9, 50 x oracle-style noise floor)"}
+
+
+def quick_its(cb, device, workload, steps=5):
+    """CG iterations/s of another BASELINE config on this GPU (secondary figures of the c3 line)."""
+    import torch
+
+    N, M, D, kern, _ = WORKLOADS[workload]
+    dt = torch.float32 if workload in FLOAT32 else torch.float64
+    g = torch.Generator(device=device).manual_seed(99)
+    X = torch.randn(N, D, dtype=dt, device=device, generator=g)
+    Z = X[torch.randperm(N, device=device, generator=g)[:M]].clone()
+    kernel = cb.kernels.KERNELS[kern](variance=1.0, lengthscales=[math.sqrt(D) if workload in FLOAT32 else 1.0] * D)
+    op = cb.SGPROperator(kernel, X, Z, NOISE)
+    rhs = torch.randn(1, M, dtype=dt, device=device, generator=g)
+    cb.conjugate_gradient(op, rhs, None, 0.0, None, 3, 4)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    cb.conjugate_gradient(op, rhs, None, 0.0, None, steps, steps + 1)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    del op, X, Z
+    torch.cuda.empty_cache()
+    return {"value": steps / (ms * 1e-3), "unit": "CG iterations/s", "steps": steps, "ms_per_step": ms / steps,
+            "workload": f"{workload}: N={N}, M={M}, D={D}, {kern}, {'f32' if workload in FLOAT32 else 'f64'}, B=1, 1 GPU"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # native arm
 # ----------------------------------------------------------------------------------------------------------------
 def run_native(args):
@@ -208,9 +322,15 @@ def run_native(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     ctx = _lib.context(device)
+    parity = None
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+        pst = parity_single_rank(cb, device) if not args.no_parity_check else None
         ctx.init_comm()
+        if pst is not None:
+            parity = parity_sharded(cb, device, pst, rank, world)
+            del pst
+            torch.cuda.empty_cache()
 
     N, M, D, kern, desc = WORKLOADS[args.workload]
     from cggp_b200.sharding import shard_rows
@@ -305,40 +425,36 @@ def run_native(args):
 
     # ---- roofline of the dominant kernel (the fused Kuf Kfu product), timed live with CUDA events ---------------
     mv_ms, mv_cnt = prof["kuf_kfu_matvec"]
-    peak_tflops, peak_src = None, None
-    try:
-        if f32w:
-            # the float32 product runs 3xFP16 tcgen05 MMAs: the peak is the dense 16-bit tensor rate, sustained
-            # (driver-measured in MEASURED_PEAKS.json; else a library GEMM timed here only as the denominator)
-            try:
-                mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-                peak_tflops = float(mp["bf16_tflops_sustained"])
-                peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (dense 16-bit tensor rate inside a long step)"
-            except Exception:
-                A_ = torch.randn(8192, 8192, device=device, dtype=torch.float16)
-                B_ = torch.randn(8192, 8192, device=device, dtype=torch.float16)
-                for _ in range(2):
-                    A_ @ B_
-                t0_, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                t0_.record()
-                for _ in range(10):
-                    A_ @ B_
-                t1_.record()
-                torch.cuda.synchronize()
-                peak_tflops = 10 * 2 * 8192 ** 3 / (t0_.elapsed_time(t1_) * 1e-3) / 1e12
-                del A_, B_
-                peak_src = "measured in this run: cuBLAS FP16 GEMM 8192^3 (torch.matmul); MEASURED_PEAKS.json absent"
-        else:
-            import ctypes as C
-
-            gops = C.c_double(0.0)
-            ctx.check(ctx.lib.cggp_microbench(ctx.handle, 1, 4096, C.byref(gops)))
-            peak_tflops = gops.value / 1e3
-            peak_src = ("measured in this run: FP64 DMMA m8n8k4 issue-rate micro-benchmark (cggp_microbench); "
-                        "MEASURED_PEAKS.json has no FP64 figure")
-    except Exception as exc:  # pragma: no cover
-        peak_src = f"unavailable: {exc}"
-    achieved = f_alg_matvec(n_local, M, D) / (mv_ms / max(mv_cnt, 1) * 1e-3) / 1e12 if mv_cnt else None
+    t_launch = (mv_ms / mv_cnt * 1e-3) if mv_cnt else None
+    peak_tflops, peak_src, peaks = None, None, {}
+    if f32w:
+        # the float32 product runs 3xFP16 tcgen05 MMAs: the peak is the dense 16-bit tensor rate, sustained
+        # (driver-measured in MEASURED_PEAKS.json; else a library GEMM timed here only as the denominator)
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak_tflops = float(mp["bf16_tflops_sustained"])
+            peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (dense 16-bit tensor rate inside a long step)"
+        except Exception:
+            A_ = torch.randn(8192, 8192, device=device, dtype=torch.float16)
+            B_ = torch.randn(8192, 8192, device=device, dtype=torch.float16)
+            for _ in range(2):
+                A_ @ B_
+            t0_, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0_.record()
+            for _ in range(10):
+                A_ @ B_
+            t1_.record()
+            torch.cuda.synchronize()
+            peak_tflops = 10 * 2 * 8192 ** 3 / (t0_.elapsed_time(t1_) * 1e-3) / 1e12
+            del A_, B_
+            peak_src = "measured in this run: cuBLAS FP16 GEMM 8192^3 (torch.matmul); MEASURED_PEAKS.json absent"
+    else:
+        peaks = fp64_peaks(ctx, device)
+        peak_tflops = peaks.get("dmma_tflops")
+        peak_src = ("measured in this run: FP64 DMMA m8n8k4 issue-rate micro-benchmark (cggp_microbench; DFMA shares the "
+                    "pipe at the same rate); cuBLAS DGEMM of the same run in peak_dgemm_cublas; MEASURED_PEAKS.json "
+                    "has no FP64 figure")
+    achieved = f_alg_matvec(n_local, M, D) / t_launch / 1e12 if t_launch else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath) and world == 1:
@@ -346,6 +462,7 @@ def run_native(args):
             traffic = json.load(open(tpath)).get(args.workload, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    matern = kern.startswith("matern")
     roofline = {
         "kernel": ("tf32::gram_contract_kernel x2 (tcgen05 3xFP16 gram contraction, FP32 accumulate, two sweeps)" if f32w else
                    "kpipe::kfu_pipe_kernel (fused, software-pipelined Kuf Kfu product)"),
@@ -355,16 +472,76 @@ def run_native(args):
         "launches_timed": mv_cnt, "avg_launch_ms": (mv_ms / mv_cnt) if mv_cnt else None,
         "share_of_step": (mv_ms / ms) if ms > 0 else None,
         "sections_ms": {k: round(v[0], 4) for k, v in prof.items()},
-        "gentries_per_s": (n_local * M / (mv_ms / mv_cnt * 1e-3) / 1e9) if mv_cnt else None,
+        "gentries_per_s": (n_local * M / t_launch / 1e9) if t_launch else None,
     }
-    if not f32w and achieved and peak_tflops:
-        # what the FP64 pipe actually executes per Gram entry (SASS count of the tile loop): the DMMA
-        # distance (4 ceil((D+1)/4) FMA) + sqrt / exp / polynomial / contractions - the algorithmic D + 2 FMA of
-        # `achieved` leave the transcendental work out
-        slots = 4 * ((D + 4) // 4) + (17.75 if kern.startswith("matern") else 9.75)
+    if not f32w and t_launch:
+        # report achieved_fp64 AND achieved_exp; the FP64 pipe is shared by the DMMA distance, the
+        # exp / sqrt of every entry and the two contractions, so the bound is the SUM of their times at the measured
+        # rates of each part running alone (composite), not any one of them
+        E = float(n_local) * M
+        pe, psq, pf = peaks.get("exp_gevals"), peaks.get("sqrt_gevals"), peaks.get("dfma_tflops")
+        roofline["bound_detail"] = ("FP64 pipe, shared by the DMMA distance contraction and the FP64 exp"
+                                    + (" + sqrt" if matern else "") + " of every Gram entry"
+                                    + ("; exp dominates (one DMMA k-step)" if D <= 3 else ""))
+        roofline["achieved_exp"] = E / t_launch / 1e9
+        roofline["peak_exp"] = pe
+        roofline["unit_exp"] = "G exp evaluations/s (the kernel's own routine, micro-benchmarked alone)"
+        roofline["frac_exp"] = (E / t_launch / 1e9 / pe) if pe else None
+        if matern:
+            roofline["achieved_sqrt"] = E / t_launch / 1e9
+            roofline["peak_sqrt"] = psq
+            roofline["frac_sqrt"] = (E / t_launch / 1e9 / psq) if psq else None
+        roofline["peak_dgemm_cublas"] = peaks.get("dgemm_cublas_tflops")
+        roofline["frac_vs_dgemm_cublas"] = (achieved / peaks["dgemm_cublas_tflops"]) \
+            if peaks.get("dgemm_cublas_tflops") else None
+        roofline["peak_dfma"] = pf
+        if peak_tflops and pe and pf and (psq or not matern):
+            ks4 = 4 * ((D + 4) // 4)
+            t_min = (2.0 * E * ks4 / (peak_tflops * 1e12) + E / (pe * 1e9) + (E / (psq * 1e9) if matern else 0.0)
+                     + 2.0 * 2.0 * E / (pf * 1e12) + (3.0 if matern else 0.0) * 2.0 * E / (pf * 1e12) / 2.0)
+            roofline["composite_fp64_pipe"] = {
+                "t_min_ms": t_min * 1e3, "frac": t_min / t_launch,
+                "note": "lower bound of one launch with every part at its stand-alone rate on the shared FP64 pipe: "
+                        "padded distance DMMA + exp" + (" + sqrt + Matern polynomial" if matern else "")
+                        + " + two contractions; frac = t_min / measured launch time"}
+        # what the FP64 pipe actually executes per Gram entry (SASS count of the tile loop)
+        slots = 4 * ((D + 4) // 4) + (17.5 if matern else 9.5)
         roofline["executed"] = {"fp64_fma_slots_per_entry": slots,
-                                "frac_of_peak": achieved / peak_tflops * slots / (D + 2),
+                                "frac_of_peak": achieved / peak_tflops * slots / (D + 2) if peak_tflops else None,
                                 "note": "FP64-pipe occupancy by executed FMA slots; `frac` counts algorithmic flop only"}
+
+    secondary = None
+    if args.workload == "c3" and world == 1 and not args.no_secondary:
+        secondary = {}
+        for wl in ("c2", "c5"):
+            try:
+                secondary[wl] = quick_its(cb, device, wl)
+            except Exception as exc:  # pragma: no cover
+                secondary[wl] = {"error": str(exc)}
+        # the multi-RHS form of the headline product: 8 right-hand sides per sweep, both contractions on DMMA
+        try:
+            g8 = torch.Generator(device=device).manual_seed(3)
+            X8 = torch.randn(min(N, 500_000), D, dtype=f64, device=device, generator=g8)
+            op8 = cb.SGPROperator(kernel, X8, Zd, NOISE)
+            V8 = torch.randn(8, M, dtype=f64, device=device, generator=g8)
+            for _ in range(2):
+                op8.kuf_kfu_matmul(V8)
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for _ in range(3):
+                op8.kuf_kfu_matmul(V8)
+            b1.record()
+            torch.cuda.synchronize()
+            t8 = b0.elapsed_time(b1) / 3 * 1e-3
+            a8 = f_alg_matvec(X8.shape[0], M, D, 8) / t8 / 1e12
+            secondary["c3_b8_product"] = {
+                "kernel": "kpipe8::kfu_pipe8_kernel (8 right-hand sides per sweep, t = K V^T and w = K^T t on DMMA)",
+                "rows": int(X8.shape[0]), "ms_per_launch": t8 * 1e3, "achieved": a8, "unit": "TFLOP/s",
+                "frac": a8 / peak_tflops if peak_tflops else None, "f_alg": "2 N M (D + 2 B), B = 8"}
+            del op8, X8, V8
+            torch.cuda.empty_cache()
+        except Exception as exc:  # pragma: no cover
+            secondary["c3_b8_product"] = {"error": str(exc)}
 
     hbm = None
     try:
@@ -398,6 +575,8 @@ def run_native(args):
                 "hbm_gbs_measured": hbm,
             },
             "roofline": roofline,
+            "secondary": secondary,
+            "parity_check": parity,
             "cpu_baseline": cpu,
             "e2e": {"value": args.steps / (e2e_ms * 1e-3), "unit": "CG iterations/s",
                     "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
@@ -420,9 +599,18 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the c2 / c5 / 8-RHS secondary figures (N = 1, c3)")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the sharded-vs-1-rank parity check (N > 1)")
+    ap.add_argument("--mode", default="cg", choices=["cg", "predict"],
+                    help="cg: CG iterations/s (the headline); predict: SGPR vs CDGP predict_f (BASELINE configs[3])")
+    ap.add_argument("--predict-points", type=int, default=100_000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "predict":
+        from tools.predict_bench import run_predict
+
+        run_predict(args)
     else:
         run_native(args)
 

@@ -8,6 +8,7 @@ from .conjugate_gradient import (BlockPreconditioner, CGPreconditioner, Conjugat
 from .distance import create_distance_fn, euclid_distance  # noqa: F401
 from .kernels import (Gaussian, InducingPoints, Kuf, Kuu, Matern12, Matern32, Matern52, SquaredExponential,  # noqa: F401
                       prepare_points)
+from .gpflow_adapter import from_gpflow  # noqa: F401
 from .models import CGGP, SGPR, ClusterGP, LpSVGP, eval_logdet  # noqa: F401
 from .operators import DenseOperator, SGPROperator  # noqa: F401
 from .prediction import batch_posterior_computation, test_metrics  # noqa: F401
@@ -21,4 +22,6 @@ def cdgp_class(kernel, likelihood, iv, error_threshold: float = 1e-6, **kwargs):
 
 def sgpr_class(train_data, kernel, likelihood, iv, **kwargs):
     """cggp/cli_utils.py:444-446."""
-    return SGPR(train_data, kernel, iv, noise_variance=likelihood.variance, **kwargs)
+    from .gpflow_adapter import likelihood_from_gpflow
+
+    return SGPR(train_data, kernel, iv, noise_variance=likelihood_from_gpflow(likelihood).variance, **kwargs)

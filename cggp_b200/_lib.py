@@ -33,16 +33,19 @@ class Operator(C.Structure):
     """struct cggp_operator (include/cggp_b200.h)."""
 
     _fields_ = [
-        ("type", C.c_int32), ("dtype", C.c_int32), ("n", C.c_int64),
-        ("dev_A", C.c_void_p), ("lda", C.c_int64),
-        ("kind", C.c_int32), ("D", C.c_int32), ("variance", C.c_double), ("scale", C.c_double),
+        ("struct_size", C.c_uint32), ("type", C.c_int32), ("dtype", C.c_int32), ("kind", C.c_int32),
+        ("n", C.c_int64), ("dev_A", C.c_void_p), ("lda", C.c_int64),
+        ("D", C.c_int32), ("variant", C.c_int32), ("variance", C.c_double), ("scale", C.c_double),
         ("dev_PX", C.c_void_p), ("dev_normsX", C.c_void_p), ("n_local", C.c_int64),
         ("dev_PZ", C.c_void_p), ("dev_normsZ", C.c_void_p), ("ldp", C.c_int64),
-        ("variant", C.c_int32), ("_pad", C.c_int32),
         ("dev_X32_big", C.c_void_p), ("dev_X32_small", C.c_void_p), ("dev_x32_norms", C.c_void_p),
         ("dev_Z32_big", C.c_void_p), ("dev_Z32_small", C.c_void_p), ("dev_z32_norms", C.c_void_p),
-        ("tf32_nsplit", C.c_int32), ("_pad2", C.c_int32),
+        ("tf32_nsplit", C.c_int32), ("_pad", C.c_int32),
     ]
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.struct_size = C.sizeof(Operator)
 
 
 class Precond(C.Structure):
@@ -101,6 +104,9 @@ SIGNATURES = {
     "cggp_cg_fused_step": (_i, [_vp, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(Precond)]),
     "cggp_cg_solve": (_i, [_vp, C.POINTER(Operator), _vp, _vp, _i, _d, _i, _i, C.POINTER(Precond), _i, _vp,
                             C.POINTER(C.c_int32), _vp, _vp, _i64]),
+    "cggp_predict_f": (_i, [_vp, _i, _i, _d, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i64, _vp, _i64, _vp, _d, _i, _i,
+                            _vp, _vp, _vp, _vp, C.POINTER(C.c_int32)]),
+    "cggp_elbo_terms": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _d, _vp]),
     "cggp_microbench": (_i, [_vp, _i, _i, C.POINTER(_d)]),
 }
 

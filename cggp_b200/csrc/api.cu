@@ -3,8 +3,7 @@
 
 #include <cstring>
 
-#include "common.cuh"
-#include "kmath.cuh"
+#include "pipe_common.cuh"
 
 int cggp_matvec_simple(cggp_ctx* ctx, int dtype, int kind, double variance, const void* PX, const void* nX, int64_t n,
                        const void* PZ, const void* nZ, int64_t m, int D, int64_t ldp, const void* V, int64_t ldv,
@@ -444,8 +443,13 @@ __device__ __forceinline__ void mb_dmma884(double& c0, double& c1, double a, dou
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-__global__ void mb_kernel(int which, double* out, int iters, double s) {
+__global__ void mb_kernel(int which, double* out, int iters, double s, const int2* etab_g) {
   double acc = 0;
+  __shared__ int2 etab_s[1024];
+  if (which == 5) {
+    for (int j = threadIdx.x; j < 1024; j += blockDim.x) etab_s[j] = etab_g[j];
+    __syncthreads();
+  }
   if (which == 0) {
     double a[8];
     for (int i = 0; i < 8; ++i) a[i] = threadIdx.x * 1e-3 + i;
@@ -468,18 +472,35 @@ __global__ void mb_kernel(int which, double* out, int iters, double s) {
     for (int it = 0; it < iters; ++it)
 #pragma unroll
       for (int i = 0; i < 4; ++i) { acc += fast_exp(a[i], tab); a[i] += s; }
-  } else {
+  } else if (which == 3) {
     double a[4];
     for (int i = 0; i < 4; ++i) a[i] = threadIdx.x * 1e-2 + i + 1;
     for (int it = 0; it < iters; ++it)
 #pragma unroll
       for (int i = 0; i < 4; ++i) { acc += fast_sqrt_pos(a[i]); a[i] += s; }
+  } else if (which == 5) {  // the exp of the pipelined kernels: 1024-entry shared-memory table, degree-3 polynomial
+    double a[4];
+    for (int i = 0; i < 4; ++i) a[i] = threadIdx.x * 1e-2 + i;
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc += fast_exp_neg_core_smem<10>(a[i], etab_s); a[i] += s; }
+  } else {  // 6: the sqrt of the pipelined kernels: MUFU.RSQ64H seed + one third-order step
+    double a[4];
+    for (int i = 0; i < 4; ++i) a[i] = threadIdx.x * 1e-2 + i + 1;
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc += fast_sqrt_pos_cubic(a[i]); a[i] += s; }
   }
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
 extern "C" int cggp_microbench(cggp_ctx* ctx, int which, int iters, double* host_gops) {
-  if (!ctx || !host_gops || which < 0 || which > 4 || iters < 1) return CGGP_ERR_INVALID;
+  if (!ctx || !host_gops || which < 0 || which > 6 || iters < 1) return CGGP_ERR_INVALID;
+  const int2* etab = nullptr;
+  if (which == 5) {
+    int rce = kpipe::exp_table_device(ctx, &etab);
+    if (rce) return rce;
+  }
   const int nb = ctx->sm_count * 8, nt = 256;
   int rc = cggp_ws_reserve(ctx, sizeof(double) * nb * nt);
   if (rc) return rc;
@@ -490,7 +511,7 @@ extern "C" int cggp_microbench(cggp_ctx* ctx, int which, int iters, double* host
   float best = 1e30f;
   for (int rep = 0; rep < 4; ++rep) {
     cudaEventRecord(e0, ctx->stream);
-    mb_kernel<<<nb, nt, 0, ctx->stream>>>(which, (double*)ctx->ws, iters, s);
+    mb_kernel<<<nb, nt, 0, ctx->stream>>>(which, (double*)ctx->ws, iters, s, etab);
     cudaEventRecord(e1, ctx->stream);
     cudaEventSynchronize(e1);
     float ms = 0;

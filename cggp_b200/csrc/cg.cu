@@ -714,6 +714,10 @@ extern "C" int cggp_cg_solve(cggp_ctx* ctx, const cggp_operator* op, const void*
                              int64_t history_cap) {
   if (!ctx) return CGGP_ERR_INVALID;
   if (!op || !rhs || !solution) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "null operator / rhs / solution");
+  if (op->struct_size != (uint32_t)sizeof(cggp_operator))
+    CGGP_FAIL(ctx, CGGP_ERR_INVALID, "cggp_operator.struct_size is %u, this library expects %u (set it to sizeof of the "
+              "header you compiled against; a shorter struct would be read past its end)", op->struct_size,
+              (unsigned)sizeof(cggp_operator));
   if (B <= 0 || op->n <= 0) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "empty system (B=%d, n=%lld)", B, (long long)op->n);
   if (max_steps_cycle < 1) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "max_steps_cycle must be >= 1");
   if (max_iterations < 0) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "max_iterations must be >= 0");

@@ -419,8 +419,10 @@ int kpipe::dup_scaled_norms(cggp_ctx* ctx, int kind, const double* nX, int64_t n
       ctx->xa2_bytes = need + need / 8;
     }
     (void)active;  // built unconditionally: a later launch of the same solve may reuse it
-    scale_dup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(nX, n, alpha, (double2*)ctx->xa2);
-    CGGP_LAUNCH_CHECK(ctx);
+    if (n > 0) {
+      scale_dup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(nX, n, alpha, (double2*)ctx->xa2);
+      CGGP_LAUNCH_CHECK(ctx);
+    }
     ctx->xa2_key = nX;
     ctx->xa2_n = n;
     ctx->xa2_alpha = alpha;

@@ -15,7 +15,8 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from .conjugate_gradient import ConjugateGradient
+from .conjugate_gradient import ConjugateGradient, EyePreconditioner
+from .gpflow_adapter import inducing_from_gpflow, kernel_from_gpflow, likelihood_from_gpflow
 from .kernels import Gaussian, InducingPoints, Kuf, Kuu, Stationary, inducingpoint_wrapper
 from .operators import SGPROperator
 from .utils import add_diagonal
@@ -58,12 +59,14 @@ class LpSVGP:
     def __init__(self, kernel: Stationary, likelihood: Gaussian, inducing_variable, *, mean_function=None,
                  num_latent_gps: int = 1, nu=None, diag_variance=None, num_data=None):
         assert num_latent_gps == 1, "One latent GP is allowed"
-        self.kernel = kernel
-        self.likelihood = likelihood
+        # GPflow objects (gpflow.kernels.*, gpflow.likelihoods.Gaussian, InducingPoints) are accepted as in the
+        # reference (models.py:279-291) and converted by duck typing; objects of this package pass through
+        self.kernel = kernel_from_gpflow(kernel)
+        self.likelihood = likelihood_from_gpflow(likelihood)
         self.mean_function = mean_function
         self.num_latent_gps = num_latent_gps
         self.num_data = num_data
-        self.inducing_variable: InducingPoints = inducingpoint_wrapper(inducing_variable)
+        self.inducing_variable: InducingPoints = inducing_from_gpflow(inducing_variable)
         Z = self.inducing_variable.Z
         m = Z.shape[0]
         self._nu = torch.zeros((m, 1), dtype=Z.dtype, device=Z.device) if nu is None else \
@@ -103,9 +106,26 @@ class LpSVGP:
         y = _lib.as_device_tensor(y, x.dtype)
         kl = self.prior_kl()
         f_mean, f_var = self.predict_f(x, full_cov=False, full_output_cov=False)
-        var_exp = self.likelihood.variational_expectations(x, f_mean, f_var, y)
         scale = self.scale(x.shape[0], kl.dtype)
+        if not self._needs_grad() and y.shape[1] == 1:
+            # forward value only: the Gaussian expectation sum as ONE deterministic device reduction (cggp_elbo_terms)
+            ctx = _lib.context(x.device)
+            ctx.use_current_stream()
+            out = torch.empty((1,), dtype=x.dtype, device=x.device)
+            yc, mc, vc = y.contiguous(), f_mean.contiguous(), f_var.contiguous()
+            ctx.check(ctx.lib.cggp_elbo_terms(ctx.handle, _lib.dtype_code(x.dtype), _lib.ptr(yc), _lib.ptr(mc),
+                                              _lib.ptr(vc), yc.shape[0], float(self.likelihood.variance), _lib.ptr(out)))
+            return out[0] * scale - kl
+        var_exp = self.likelihood.variational_expectations(x, f_mean, f_var, y)
         return var_exp.sum() * scale - kl
+
+    def _needs_grad(self) -> bool:
+        """True when a differentiable evaluation is wanted (trainable kernel / likelihood parameters under grad mode):
+        the fused forward-only C entry points (cggp_predict_f, cggp_elbo_terms) are used otherwise."""
+        if not torch.is_grad_enabled():
+            return False
+        v = self.likelihood.variance
+        return bool(self.kernel.trainable or (isinstance(v, torch.Tensor) and v.requires_grad))
 
     def predict_f(self, Xnew, full_cov: bool = False, full_output_cov: bool = False) -> Moments:  # :136-161
         assert not full_output_cov
@@ -235,11 +255,14 @@ class CGGP(ClusterGP):
         Xnew = _lib.as_device_tensor(Xnew)
         var = self.diag_variance
         Kmm = Kuu(self.inducing_variable, self.kernel, jitter=0.0)  # :333
-        Kmn = Kuf(self.inducing_variable, self.kernel, Xnew)  # :334
         Knn = self.kernel.K(Xnew) if full_cov else self.kernel.K_diag(Xnew)  # :335
         KmmLambda = add_diagonal(Kmm, var[:, 0])  # :337
         cg = self.conjugate_gradient
         a = cg(KmmLambda, self.pseudo_u)  # :339
+        if not full_cov and not self._needs_grad() and isinstance(cg.preconditioner, EyePreconditioner) \
+                and not cg.record_history and self.mean_function is None and Xnew.shape[0] > 0:
+            return self._predict_f_fused(Xnew, KmmLambda, a)
+        Kmn = Kuf(self.inducing_variable, self.kernel, Xnew)  # :334
         S = cg(KmmLambda, Kmn)  # :340
         if not full_cov:
             fvar = (Knn - (Kmn * S).sum(0))[:, None]  # :343-345
@@ -247,6 +270,37 @@ class CGGP(ClusterGP):
             fvar = (Knn - Kmn.t() @ S)[None, ...]  # :347-349
         fmu = Kmn.t() @ a  # :351
         return fmu + self._mean(Xnew, fmu), fvar
+
+
+    def _predict_f_fused(self, Xnew, KmmLambda, a) -> Moments:
+        """models.py:334-352 as ONE call of the C ABI (``cggp_predict_f``): Kmn, the B-RHS solve with the reference's
+        stopping rule, ``fvar = Knn - sum_m Kmn * S`` and ``fmu = Kmn^T a`` - forward values, nothing leaves the
+        device.  The differentiable path above is kept for training."""
+        import ctypes as C
+
+        cg = self.conjugate_gradient
+        Z = self.inducing_variable.Z
+        PZ = self.kernel.prepare(Z)
+        PN = self.kernel.prepare(Xnew, PZ.P.dtype)
+        ctx = _lib.context(Z.device)
+        ctx.use_current_stream()
+        nb, m = PN.n, PZ.n
+        Knm = torch.empty((nb, m), dtype=PZ.P.dtype, device=Z.device)
+        S = torch.empty_like(Knm)
+        mean = torch.empty((nb,), dtype=PZ.P.dtype, device=Z.device)
+        var = torch.empty_like(mean)
+        max_it = cg.max_iterations if cg.max_iterations is not None else m
+        cycle = cg.max_steps_cycle if cg.max_steps_cycle is not None else max_it + 1
+        A = _lib.row_major(KmmLambda)
+        av = a.reshape(-1).contiguous()
+        steps = C.c_int32(0)
+        ctx.check(ctx.lib.cggp_predict_f(
+            ctx.handle, _lib.dtype_code(PZ.P.dtype), self.kernel.kind, self.kernel.variance, _lib.ptr(PZ.P),
+            _lib.ptr(PZ.norms), m, _lib.ptr(PN.P), _lib.ptr(PN.norms), nb, PZ.D, PZ.ldp, _lib.ptr(A), A.stride(0),
+            _lib.ptr(av), float(cg.error_threshold), int(max_it), int(cycle), _lib.ptr(Knm), _lib.ptr(S), _lib.ptr(mean),
+            _lib.ptr(var), C.byref(steps)))
+        self.last_predict_steps = int(steps.value)
+        return mean[:, None], var[:, None]
 
 
 class SGPR:
@@ -263,8 +317,9 @@ class SGPR:
         X, Y = data
         self.X = _lib.as_device_tensor(X)
         self.Y = _lib.as_device_tensor(Y, self.X.dtype)
-        self.kernel = kernel
-        self.inducing_variable = inducingpoint_wrapper(inducing_variable)
+        self.kernel = kernel_from_gpflow(kernel)
+        kernel = self.kernel
+        self.inducing_variable = inducing_from_gpflow(inducing_variable, self.X.dtype)
         self.likelihood = Gaussian(noise_variance)
         self.jitter = jitter
         self.conjugate_gradient = conjugate_gradient or ConjugateGradient(1e-6)

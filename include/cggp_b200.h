@@ -207,15 +207,18 @@ enum cggp_operator_type {
 };
 
 typedef struct cggp_operator {
+  uint32_t struct_size; /* sizeof(cggp_operator) of the header the caller was built against: the library rejects any
+                           other value instead of reading past a shorter struct (zero-initialise, then set this) */
   int32_t type;
   int32_t dtype;
+  int32_t kind;         /* CGGP_OP_SGPR only */
   int64_t n;            /* system size (= M) */
   /* dense part: A (CGGP_OP_DENSE) or Kuu incl. jitter (CGGP_OP_SGPR); symmetric, row-major */
   const void* dev_A;
   int64_t lda;
   /* CGGP_OP_SGPR only */
-  int32_t kind;
   int32_t D;
+  int32_t variant;      /* as cggp_kuf_kfu_matvec */
   double variance;
   double scale;         /* 1 / noise_variance */
   const void* dev_PX;   /* prepared X shard [n_local, ldp] */
@@ -224,8 +227,6 @@ typedef struct cggp_operator {
   const void* dev_PZ;   /* prepared Z [n, ldp] */
   const void* dev_normsZ;
   int64_t ldp;
-  int32_t variant;      /* as cggp_kuf_kfu_matvec */
-  int32_t _pad;
   /* float32 tensor-core path (optional, CGGP_OP_SGPR with dtype CGGP_F32): arrays from cggp_tf32_prepare; when
    * dev_X32_big is non-NULL every application of the operator goes through cggp_kuf_kfu_matvec_tf32 */
   const void* dev_X32_big;
@@ -235,7 +236,7 @@ typedef struct cggp_operator {
   const void* dev_Z32_small;
   const void* dev_z32_norms;
   int32_t tf32_nsplit;  /* 3, 1 or 16: what the arrays were prepared with */
-  int32_t _pad2;
+  int32_t _pad;
 } cggp_operator;
 
 enum cggp_precond_type {
@@ -283,9 +284,37 @@ int cggp_cg_solve(cggp_ctx* ctx, const cggp_operator* op, const void* dev_rhs, c
                   void* dev_history, int64_t history_cap);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Model-level chains  (cggp/models.py objective + prediction as single calls; forward values only - the Python
+ * mirror keeps the differentiable path for training)
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* CGGP.predict_f, cggp/models.py:333-352, for one batch of nb test points given the dense system
+ * A = Kuu + Lambda [m, m] (models.py:337) and a = A^-1 pseudo_u [m] (models.py:339):
+ *   Knm = K(Xnew, Z) [nb, m] (the reference's Kmn transposed: rows = right-hand sides)     models.py:334
+ *   S   = cg(A, Knm), nb right-hand sides, the reference's stopping rule                   models.py:340
+ *   var[b]  = variance - sum_m Knm[b, m] S[b, m]                                           models.py:343-345
+ *   mean[b] = sum_m Knm[b, m] a[m]                                                         models.py:351
+ * Workspaces dev_Knm_work / dev_S_work are caller-owned [nb, m] buffers (nothing is allocated per call beyond the CG
+ * state).  host_steps receives the iteration count of the nb-RHS solve; the call synchronises the stream. */
+int cggp_predict_f(cggp_ctx* ctx, int dtype, int kind, double variance,
+                   const void* dev_PZ, const void* dev_normsZ, int64_t m,
+                   const void* dev_Pnew, const void* dev_normsNew, int64_t nb, int D, int64_t ldp,
+                   const void* dev_A, int64_t lda, const void* dev_a,
+                   double error_threshold, int max_iterations, int max_steps_cycle,
+                   void* dev_Knm_work, void* dev_S_work, void* dev_mean, void* dev_var, int32_t* host_steps);
+
+/* Data term of the ELBO, cggp/models.py:131-133 with GPflow's Gaussian likelihood:
+ *   out[0] = sum_i [ -1/2 log(2 pi) - 1/2 log(s2) - 1/2 ((y_i - mean_i)^2 + var_i) / s2 ]
+ * (the caller scales by num_data / batch and subtracts the KL, models.py:133-134).  Deterministic two-stage sum. */
+int cggp_elbo_terms(cggp_ctx* ctx, int dtype, const void* dev_y, const void* dev_mean, const void* dev_var, int64_t n,
+                    double noise_variance, void* dev_out);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Micro-benchmarks for the roofline denominators that MEASURED_PEAKS.json lacks:
- * which: 0 = FP64 DFMA, 1 = FP64 DMMA m8n8k4, 2 = the library's FP64 exp, 3 = FP64 sqrt (rsqrt seed + Newton),
- *        4 = DMMA m16n8k4.  Returns giga-ops/s in *host_gops (FMA counted as 2 flop; exp/sqrt as 1 evaluation). */
+ * which: 0 = FP64 DFMA, 1 = FP64 DMMA m8n8k4, 2 = FP64 exp with the 32-entry shuffle table (two-RHS kernels),
+ *        3 = FP64 sqrt (rsqrt seed + two Newton steps), 4 = DMMA m16n8k4, 5 = the exp of the pipelined kernels
+ *        (1024-entry shared-memory table + degree-3 polynomial), 6 = their sqrt (rsqrt seed + one third-order step).
+ * Returns giga-ops/s in *host_gops (FMA counted as 2 flop; exp/sqrt as 1 evaluation). */
 int cggp_microbench(cggp_ctx* ctx, int which, int iters, double* host_gops);
 
 #ifdef __cplusplus

@@ -49,7 +49,29 @@ def test_struct_layout_matches_header():
 
     assert ctypes.sizeof(_lib.Operator) == 168
     assert ctypes.sizeof(_lib.Precond) == 48
-    assert _lib.Operator.dev_PZ.offset == 80 and _lib.Operator.variant.offset == 104
+    assert _lib.Operator.struct_size.offset == 0 and _lib.Operator.n.offset == 16
+    assert _lib.Operator.dev_PZ.offset == 88 and _lib.Operator.variant.offset == 44
+    assert _lib.Operator().struct_size == 168  # the constructor stamps it; cggp_cg_solve rejects any other value
+
+
+def test_header_struct_fields_match_ctypes_and_integration_doc():
+    """Field names and order of struct cggp_operator: header == cggp_b200._lib.Operator == the ctypes stub published
+    in INTEGRATION.md (a maintainer copying a stale stub would make the library read past the struct)."""
+    from cggp_b200 import _lib
+
+    src = open(HEADER).read()
+    body = src[src.index("typedef struct cggp_operator {"):src.index("} cggp_operator;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    header_fields = re.findall(r"\b(\w+)\s*;", body)
+    lib_fields = [f[0] for f in _lib.Operator._fields_]
+    assert header_fields == lib_fields
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    stub = doc[doc.index("class Operator(C.Structure):"):]
+    stub = stub[:stub.index("op = Operator(")]
+    doc_fields = re.findall(r'\("(\w+)",\s*C\.(\w+)\)', stub)
+    assert [f for f, _ in doc_fields] == lib_fields
+    alias = {"c_uint": "c_uint32", "c_int": "c_int32", "c_long": "c_int64"}  # ctypes names on LP64
+    assert [t for _, t in doc_fields] == [alias.get(f[1].__name__, f[1].__name__) for f in _lib.Operator._fields_]
 
 
 def test_prepared_ld_and_version(lib):

@@ -1010,6 +1010,66 @@ def test_batched_prediction_and_metrics(cb, models_golden):
     np.testing.assert_allclose(met["test/nlpd"], -lpd.sum() / X.shape[0], rtol=1e-9)
 
 
+def test_fused_predict_f_and_elbo_entry_points(cb):
+    """cggp_predict_f / cggp_elbo_terms (the model chains of cggp/models.py:333-352 and :131-133 as single C calls,
+    used when no gradient is wanted) against the step-by-step differentiable path and the oracle."""
+    rng = np.random.default_rng(21)
+    N, M, D = 900, 96, 3
+    X = rng.uniform(-2, 2, (N, D))
+    y = np.sin(X.sum(-1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
+    Z = X[rng.choice(N, M, replace=False)] + 0.01
+    _, u, counts = om.kmeans_update_inducing_parameters(Z, X, y)
+    u, counts = np.nan_to_num(u), np.maximum(counts, 1.0)
+    ls = np.array([1.1, 0.8, 1.4])
+    ok = g.Matern32(variance=1.2, lengthscales=ls)
+    mo = om.CGGP(ok, g.Gaussian(0.15), Z, ocg.ConjugateGradient(1e-22), num_probes=None, cluster_counts=counts,
+                 pseudo_u=u, num_data=N)
+    k = cb.Matern32(1.2, ls)
+    fused = cb.CGGP(k, cb.Gaussian(0.15), dev(Z), cb.ConjugateGradient(1e-22), num_probes=None,
+                    cluster_counts=dev(counts), pseudo_u=dev(u), num_data=N)
+    plain = cb.CGGP(k, cb.Gaussian(0.15), dev(Z), cb.ConjugateGradient(1e-22, record_history=True), num_probes=None,
+                    cluster_counts=dev(counts), pseudo_u=dev(u), num_data=N)  # history wanted => step-by-step path
+    with torch.no_grad():
+        mu_f, var_f = fused.predict_f(dev(X[:257]))
+        mu_p, var_p = plain.predict_f(dev(X[:257]))
+        e_f, e_p = fused.elbo((dev(X[:300]), dev(y[:300]))), plain.elbo((dev(X[:300]), dev(y[:300])))
+    assert fused.last_predict_steps > 0 and tuple(mu_f.shape) == (257, 1) and tuple(var_f.shape) == (257, 1)
+    omu, ovar = mo.predict_f(X[:257])
+    for got, ref in ((mu_f, omu), (var_f, ovar), (mu_p, omu), (var_p, ovar)):
+        np.testing.assert_allclose(cpu(got), ref, rtol=1e-8, atol=1e-8 * np.abs(ref).max())
+    np.testing.assert_allclose(cpu(mu_f), cpu(mu_p), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(float(e_f), float(mo.elbo((X[:300], y[:300]))), rtol=1e-8)
+    np.testing.assert_allclose(float(e_f), float(e_p), rtol=1e-12)
+    # the Gaussian expectation sum alone, float32 as well
+    ctx = cb._lib.context()
+    for dt in (torch.float64, torch.float32):
+        yy, mm = dev(y[:500]).to(dt), dev(rng.standard_normal((500, 1))).to(dt)
+        vv = dev(rng.random((500, 1))).to(dt)
+        out = torch.empty(1, dtype=dt, device="cuda")
+        ctx.use_current_stream()
+        ctx.check(ctx.lib.cggp_elbo_terms(ctx.handle, cb._lib.dtype_code(dt), cb._lib.ptr(yy), cb._lib.ptr(mm),
+                                          cb._lib.ptr(vv), 500, 0.3, cb._lib.ptr(out)))
+        ref = float(cb.Gaussian(0.3).variational_expectations(None, mm.double(), vv.double(), yy.double()).sum())
+        np.testing.assert_allclose(float(out), ref, rtol=1e-12 if dt == torch.float64 else 1e-5)
+
+
+def test_short_operator_struct_is_rejected(cb):
+    """A caller built against an older / shorter struct cggp_operator is refused (struct_size), not read past its end."""
+    import ctypes as C
+
+    ctx = cb._lib.context()
+    A = torch.eye(8, dtype=torch.float64, device="cuda")
+    b = torch.ones(1, 8, dtype=torch.float64, device="cuda")
+    x = torch.empty_like(b)
+    op = cb._lib.Operator(type=cb._lib.OP_DENSE, dtype=cb._lib.F64, n=8, dev_A=A.data_ptr(), lda=8)
+    steps = C.c_int32(0)
+    args = (ctx.handle, C.byref(op), cb._lib.ptr(b), None, 1, 1e-12, 8, 9, None, 16, cb._lib.ptr(x), C.byref(steps),
+            None, None, 0)
+    assert ctx.lib.cggp_cg_solve(*args) == 0 and float((x - b).abs().max()) < 1e-12
+    op.struct_size = 112  # the size of the stub INTEGRATION.md published in round 1
+    assert ctx.lib.cggp_cg_solve(*args) == -1 and b"struct_size" in ctx.lib.cggp_last_error(ctx.handle)
+
+
 def test_operator_is_valid_for_one_parameter_value(cb):
     """An in-place optimiser step on the kernel's parameters makes a prepared operator stale: it raises instead of
     mixing old scaled points with the new variance; refresh() re-prepares it, and the SGPR model re-syncs itself."""
