@@ -603,7 +603,10 @@ def main():
     ap.add_argument("--no-parity-check", action="store_true", help="skip the sharded-vs-1-rank parity check (N > 1)")
     ap.add_argument("--mode", default="cg", choices=["cg", "predict"],
                     help="cg: CG iterations/s (the headline); predict: SGPR vs CDGP predict_f (BASELINE configs[3])")
-    ap.add_argument("--predict-points", type=int, default=100_000)
+    ap.add_argument("--predict-points", type=int, default=100_000, help="held-out test points (all ranks together)")
+    ap.add_argument("--predict-batch", type=int, default=4096, help="test points per predict_f call")
+    ap.add_argument("--predict-rows", type=int, default=0, help="override N (reduced replicas of c4)")
+    ap.add_argument("--predict-inducing", type=int, default=0, help="override M (rounded down to a square)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

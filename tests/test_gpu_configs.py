@@ -175,6 +175,41 @@ def test_config4_sgpr_vs_cdgp_predict_replica(cb):
     assert float(np.abs(cpu(cmu) - ref_mean).mean()) < 0.2  # two approximations of the same posterior
 
 
+def test_config4_predict_bench_code_path_vs_oracle(cb):
+    """The code path `bench.py --workload c4 --mode predict` times at N = 8M / M = 16384 (tools/predict_bench.py:
+    assignment -> cggp_predict_f batches; Kuf y + cggp_kuf_gram -> Sigma -> mean / variance; matrix-free preconditioned
+    CG for the mean weights) on the reduced replica SURVEY.md 8(d) prescribes, against the oracle's CGGP and GPflow-SGPR
+    restatements on the same inputs."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from tools.predict_bench import predict_compare
+
+    res = predict_compare(cb, torch.device("cuda", 0), 0, 1, N=100_000, M=1024, T=600, batch=256, threshold=1e-14)
+    X, y, Z, Xs = cpu(res["X"]), cpu(res["y"]), cpu(res["Z"]), cpu(res["Xs"])
+    u, cnt = cpu(res["u"])[:, None], cpu(res["counts"])[:, None]
+    ok = g.Matern32(1.0, [1.0, 1.0])
+    # assignment: same clusters as the oracle's (optimize.py:50-78 semantics)
+    _, omeans, ocounts = om.oips_style_assignment(Z, X, y)
+    np.testing.assert_array_equal(cnt[:, 0], ocounts.astype(np.float64))
+    np.testing.assert_allclose(u[:, 0], np.nan_to_num(omeans), rtol=1e-10, atol=1e-12)
+    # CDGP
+    mo = om.CGGP(ok, g.Gaussian(0.1), Z, ocg.ConjugateGradient(1e-14), cluster_counts=cnt, pseudo_u=u)
+    omu, ovar = mo.predict_f(Xs)
+    alt = [om.CGGP(ok, g.Gaussian(0.1), Z, nz.PermutedCG(s, 1e-14), cluster_counts=cnt, pseudo_u=u).predict_f(Xs)
+           for s in (0, 1)]
+    nz.assert_close_with_noise(cpu(res["mu_cdgp"]), omu, [a[0] for a in alt], 1e-8, "cdgp mean")
+    nz.assert_close_with_noise(cpu(res["var_cdgp"]), ovar, [a[1] for a in alt], 1e-8, "cdgp var")
+    # SGPR (GPflow's Cholesky formulas)
+    ref_mean, ref_var = g.SGPR((X, y), ok, Z, noise_variance=0.1).predict_f(Xs)
+    np.testing.assert_allclose(cpu(res["mu_sgpr"]), ref_mean, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(cpu(res["var_sgpr"]), ref_var, rtol=1e-5, atol=1e-6)
+    # the matrix-free preconditioned CG reaches the same mean weights
+    assert float((res["mu_sgpr_matrix_free"] - res["mu_sgpr"]).abs().max()) < 1e-5
+    assert float((res["mu_sgpr"] - res["mu_cdgp"]).abs().mean()) < 0.2  # two approximations of one posterior
+
+
 def test_config5_float32_replica(cb):
     rng = np.random.default_rng(4)
     N, M, D = 6000, 192, 90
