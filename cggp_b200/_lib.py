@@ -101,6 +101,7 @@ SIGNATURES = {
     "cggp_kuf_gram": (_i, [_vp, _i, _i, _d, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i64, _vp, _i64, _i]),
     "cggp_symm_matmul": (_i, [_vp, _i, _vp, _i64, _i64, _vp, _i64, _i, _vp, _i64]),
     "cggp_block_cholesky": (_i, [_vp, _i, _vp, _i64, _i64, _vp, _i, _i, _vp]),
+    "cggp_block_precond_apply": (_i, [_vp, _i, _i, _i64, _vp, C.POINTER(Precond), _vp]),
     "cggp_cg_fused_step": (_i, [_vp, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(Precond)]),
     "cggp_cg_solve": (_i, [_vp, C.POINTER(Operator), _vp, _vp, _i, _d, _i, _i, C.POINTER(Precond), _i, _vp,
                             C.POINTER(C.c_int32), _vp, _vp, _i64]),

@@ -49,7 +49,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         for lg in logs:
             sys.stderr.write(lg)
     if jobs or not os.path.exists(OUT):
-        run([nvcc, "-shared", "-o", OUT] + objs + ["-lcudart", "-ldl"])
+        # link next to the target and swap it in atomically: a snapshot of the tree (gpurun) taken while a build runs
+        # must never see a half-written library
+        tmp = OUT + ".tmp.%d" % os.getpid()
+        run([nvcc, "-shared", "-o", tmp] + objs + ["-lcudart", "-ldl"])
+        os.replace(tmp, OUT)
     return OUT
 
 

@@ -89,10 +89,14 @@ class BlockPreconditioner(CGPreconditioner):
         return pc, (idx, chol)
 
     def __call__(self, vec, mat):
-        idx, chol = self.factorise(as_operator(mat))
+        pc, keep = self.c_struct(as_operator(mat))
+        vec = _lib.row_major(_lib.as_device_tensor(vec)).contiguous()
         z = torch.empty_like(vec)
-        for b in range(idx.shape[0]):
-            z[:, idx[b]] = torch.cholesky_solve(vec[:, idx[b]].t(), chol[b]).t()
+        ctx = _lib.context(vec.device)
+        ctx.use_current_stream()
+        ctx.check(ctx.lib.cggp_block_precond_apply(ctx.handle, _lib.dtype_code(vec.dtype), vec.shape[0], vec.shape[1],
+                                                   _lib.ptr(vec), C.byref(pc), _lib.ptr(z)))
+        del keep
         return z, (z * vec).sum(-1, keepdim=True)
 
 

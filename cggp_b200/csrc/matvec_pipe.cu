@@ -457,7 +457,16 @@ static Plan make_plan() {
 // `deep`: three K buffers of 32 rows instead of two of 48, i.e. the group exchange of a block has TWO phase-1 periods
 // to complete.  Chosen where the group is large (M = 16384: 64 CTAs to wait for) or phase 1 is cheap (D <= 3).
 template <int KIND, int KS>
-static bool plan_for_nb(int nb, bool deep, Plan& p) {
+static bool plan_for_nb(int nb, bool deep, bool wide, Plan& p) {
+  // `wide` (M > 8192, D <= 7, one right-hand side): 32 columns per warp = 512 per CTA, 16-row blocks, three buffers.
+  // At M = 16384 the group shrinks from 64 to 32 CTAs: the exchange of a block gathers half as many partials of half as
+  // many rows (4 x fewer L2 loads, half the arrivals to poll for) for the same 8192 Gram entries of phase 1.
+  if constexpr (KS <= 2) {
+    if (nb == 1 && wide) {
+      p = make_plan<KIND, KS, 16, 2, 4, 1, 3, 10, 1, 1>();
+      return true;
+    }
+  }
   // one right-hand side: 1024-entry shared-memory exp table (degree-3 polynomial) + third-order sqrt step + the
   // pre-scaled accumulator pair per row; two: 32-entry shuffle table (degree 5) + two Newton steps (no room for the table)
   if (nb == 1) {
@@ -476,25 +485,25 @@ static bool plan_for_nb(int nb, bool deep, Plan& p) {
   return false;
 }
 template <int KIND>
-static bool plan_for_ks(int ks, int nb, bool deep, Plan& p) {
+static bool plan_for_ks(int ks, int nb, bool deep, bool wide, Plan& p) {
   switch (ks) {
-    case 1: return plan_for_nb<KIND, 1>(nb, deep, p);
-    case 2: return plan_for_nb<KIND, 2>(nb, deep, p);
-    case 3: return plan_for_nb<KIND, 3>(nb, deep, p);
-    case 4: return plan_for_nb<KIND, 4>(nb, deep, p);
-    case 5: return plan_for_nb<KIND, 5>(nb, deep, p);
-    case 6: return plan_for_nb<KIND, 6>(nb, deep, p);
-    case 7: return plan_for_nb<KIND, 7>(nb, deep, p);
-    case 8: return plan_for_nb<KIND, 8>(nb, deep, p);
+    case 1: return plan_for_nb<KIND, 1>(nb, deep, wide, p);
+    case 2: return plan_for_nb<KIND, 2>(nb, deep, wide, p);
+    case 3: return plan_for_nb<KIND, 3>(nb, deep, wide, p);
+    case 4: return plan_for_nb<KIND, 4>(nb, deep, wide, p);
+    case 5: return plan_for_nb<KIND, 5>(nb, deep, wide, p);
+    case 6: return plan_for_nb<KIND, 6>(nb, deep, wide, p);
+    case 7: return plan_for_nb<KIND, 7>(nb, deep, wide, p);
+    case 8: return plan_for_nb<KIND, 8>(nb, deep, wide, p);
     default: return false;
   }
 }
-static bool plan_for(int kind, int ks, int nb, bool deep, Plan& p) {
+static bool plan_for(int kind, int ks, int nb, bool deep, bool wide, Plan& p) {
   switch (kind) {
-    case CGGP_SE: return plan_for_ks<CGGP_SE>(ks, nb, deep, p);
-    case CGGP_MATERN12: return plan_for_ks<CGGP_MATERN12>(ks, nb, deep, p);
-    case CGGP_MATERN32: return plan_for_ks<CGGP_MATERN32>(ks, nb, deep, p);
-    case CGGP_MATERN52: return plan_for_ks<CGGP_MATERN52>(ks, nb, deep, p);
+    case CGGP_SE: return plan_for_ks<CGGP_SE>(ks, nb, deep, wide, p);
+    case CGGP_MATERN12: return plan_for_ks<CGGP_MATERN12>(ks, nb, deep, wide, p);
+    case CGGP_MATERN32: return plan_for_ks<CGGP_MATERN32>(ks, nb, deep, wide, p);
+    case CGGP_MATERN52: return plan_for_ks<CGGP_MATERN52>(ks, nb, deep, wide, p);
     default: return false;
   }
 }
@@ -576,7 +585,9 @@ static int pipe_launch(cggp_ctx* ctx, int kind, double variance, const double* P
     // three buffers where phase 1 is cheap (one DMMA k-step) or the group is large, two otherwise
     const bool deep = deep_env >= 0 ? deep_env != 0 : ((nb == 1 && ks <= 1) || m > 8192);
     const int et = nb == 1 ? 10 : 0;
-    if (!plan_for(kind, ks, nb, deep, p)) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "pipelined matvec: no plan for D=%d", D);
+    static const int wide_env = getenv("CGGP_PIPE_WIDE") ? atoi(getenv("CGGP_PIPE_WIDE")) : -1;  // tuning knob
+    const bool wide = wide_env >= 0 ? wide_env != 0 : m > 8192;
+    if (!plan_for(kind, ks, nb, deep, wide, p)) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "pipelined matvec: no plan for D=%d", D);
     CGGP_CUDA(ctx, cudaFuncSetAttribute(p.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     int occ = 0;
     CGGP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p.fn, p.threads, p.smem));

@@ -263,6 +263,13 @@ typedef struct cggp_precond {
 int cggp_block_cholesky(cggp_ctx* ctx, int dtype, const void* dev_A, int64_t lda, int64_t n,
                         const int64_t* dev_block_indices, int num_blocks, int block_size, void* dev_chol);
 
+/* z[b, blk] = A[blk, blk]^-1 r[b, blk] for every row b and block: the batched triangular solves of the block-Jacobi
+ * preconditioner (one warp per block, lane-parallel forward / backward substitution with the factors of
+ * cggp_block_cholesky) - the reference's protocol `__call__(vec, mat) -> (z, rz)`, cggp/conjugate_gradient.py:125-128,
+ * outside the solve loop (inside cggp_cg_solve the same routine runs in the fused step kernel). */
+int cggp_block_precond_apply(cggp_ctx* ctx, int dtype, int B, int64_t n, const void* dev_r,
+                             const cggp_precond* precond, void* dev_z);
+
 /* One fused CG update on [B, n] row-major state given pA = p @ A  (cggp/conjugate_gradient.py:66-84, non-reset branch;
  * with `reset` != 0 the caller passes fresh_r = b - v_new @ A ... see cggp_cg_solve).  Exported for unit tests / ncu.
  *   denom = sum p*pA; gamma = rz/denom (0 where denom <= 1e-16); v += gamma p; r -= gamma pA;

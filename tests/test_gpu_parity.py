@@ -331,6 +331,18 @@ def test_block_preconditioner(cb):
     np.testing.assert_allclose(cpu(sol) @ A, rhs, atol=1e-4)
     with pytest.raises(ValueError):
         cb.conjugate_gradient(dev(A), dev(rhs), None, 1e-10, cb.BlockPreconditioner(blocks[:-1]), 10, 100)
+    # the preconditioner protocol `__call__(vec, mat) -> (z, rz)` (conjugate_gradient.py:125-128) on the device:
+    # the batched triangular solves of cggp_block_precond_apply, block sizes up to 64 (two entries per lane)
+    for bs2 in (12, 32, 48, 64):
+        n2 = 4 * bs2
+        X2 = np.sort(rng.uniform(0, 10, size=(n2, 1)), axis=0)
+        A2 = np.exp(-0.5 * (X2 - X2.T) ** 2) + 1e-2 * np.eye(n2)
+        blocks2 = rng.permutation(n2).reshape(n2 // bs2, bs2)
+        r2 = rng.standard_normal((3, n2))
+        z, rz = cb.BlockPreconditioner(blocks2)(dev(r2), dev(A2))
+        oz, orz = ocg.BlockPreconditioner(blocks2)(r2, A2)
+        np.testing.assert_allclose(cpu(z), oz, rtol=1e-9, atol=1e-9 * np.abs(oz).max())
+        np.testing.assert_allclose(cpu(rz), orz, rtol=1e-9)
 
 
 def test_dense_preconditioner_matches_oracle(cb):
