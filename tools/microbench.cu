@@ -1,5 +1,5 @@
 // FP64 pipe micro-benchmarks for B200 (sm_100a): what bounds the fused Kuf*Kfu matvec kernel.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench tools/microbench.cu
+// Build: nvcc --cudart shared -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench tools/microbench.cu
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>

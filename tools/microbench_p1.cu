@@ -1,6 +1,6 @@
 // Micro-benchmark of phase 1 of the pipelined Kuf*Kfu kernel (DMMA distance tile + Matern-5/2 epilogue) in isolation:
 // no shared-memory parking, no exchange, no phase 2.  Which part of the FP64-pipe budget is lost where?
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/microbench_p1 tools/microbench_p1.cu
+// Build: nvcc --cudart shared -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/microbench_p1 tools/microbench_p1.cu
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>

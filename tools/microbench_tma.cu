@@ -1,7 +1,7 @@
 // Micro-benchmark: how fast can every SM pull L2-resident data into shared memory with 1-D TMA bulk copies
 // (cp.async.bulk + mbarrier), the feed of the tcgen05 gram kernel?  One producer thread per CTA keeps `stages` copies
 // of `chunk` bytes in flight from a `footprint`-byte buffer that all CTAs read (optionally each from its own offset).
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/microbench_tma tools/microbench_tma.cu
+// Build: nvcc --cudart shared -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/microbench_tma tools/microbench_tma.cu
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>

@@ -1,7 +1,7 @@
 // Probe for the float32 path: one 128 x 128 x K TF32 tile through tcgen05.mma (A, B K-major in shared memory with the
 // canonical no-swizzle "interleave" layout, accumulator in TMEM, read back with tcgen05.ld) against a CPU reference.
 // Validates the shared-memory / instruction descriptors that csrc/matvec_tf32.cu builds on.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/tf32_probe tools/tf32_probe.cu
+// Build: nvcc --cudart shared -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/tf32_probe tools/tf32_probe.cu
 #include <cmath>
 #include <cstdint>
 #include <cstring>
