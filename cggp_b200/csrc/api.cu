@@ -73,9 +73,6 @@ extern "C" int cggp_ctx_destroy(cggp_ctx* ctx) {
   if (w.p) { cudaFree(w.p); w.p = nullptr; w.bytes = 0; }
   if (ctx->exp_tab) cudaFree(ctx->exp_tab);
   if (ctx->xa2) cudaFree(ctx->xa2);
-  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->cg_state) cudaFree(ctx->cg_state);
   if (ctx->cg_state_host) cudaFreeHost(ctx->cg_state_host);
   for (int s = 0; s < CGGP_PROF_SECTIONS; ++s)

@@ -208,20 +208,22 @@ __global__ void __launch_bounds__(512) cg_step_kernel(const StepArgs<T> a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+extern "C" int cggp_peer_enabled(cggp_ctx* ctx);
+
 // Fused tail of an iteration on the matrix-free operator (Eye preconditioner, B <= 8): ONE kernel does
 //   (1) the all-reduce of this rank's partial product over NVLink peer memory: every rank copies its vector into its
 //       own IPC-shared slot, publishes a sequence number, waits for the other ranks' numbers and sums all slots in
 //       RANK ORDER straight out of peer memory (bit-identical on all ranks; the protocol of peer_allreduce_kernel),
-//   (2) q = p Kuu + scale * w   (p Kuu was computed on a side stream while the product ran), and
+//   (2) q = p Kuu + scale * w   (the ranks' shares of p Kuu ride in the same sum), and
 //   (3) the CG vector update with its dot products, stopping condition and history row (cg_step_body).
-// Per iteration this replaces ncclAllReduce + the Kuu product (now overlapped) + the step kernel: the serial tail
-// after the product drops from ~130 us to one short kernel (profiles/r02_tail.md).
+// Per iteration this replaces ncclAllReduce + the replicated Kuu product + the step kernel (profiles/README.md).
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
 struct TailArgs {
   const T* w;       // [B, n] this rank's partial Kuf Kfu product (already all-reduced when world == 1 or by NCCL)
-  T* q;             // [B, n] in: p @ Kuu, out: p @ Sigma
-  T scale;
+  T* q;             // [B, n] in: p @ Kuu (world == 1: all columns; else this rank's columns [col_lo, col_hi)), out: p Sigma
+  T scale, inv_scale;
+  int64_t col_lo, col_hi;  // world > 1: the slice of p @ Kuu this rank computed and contributes to the sum
   // peer exchange (world > 1)
   char* const* peers;
   int rank, world;
@@ -251,7 +253,9 @@ __global__ void __launch_bounds__(512) cg_tail_kernel(const StepArgs<T> a, const
   if (t.world > 1) {
     const int slot = (int)(t.seq & 1u);
     T* mine = reinterpret_cast<T*>(t.peers[t.rank] + slot * t.slot_bytes) + (int64_t)b * n;
-    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) mine[k] = w[k];
+    // this rank's share of the replicated term rides in the same sum: every rank computes 1 / world of p @ Kuu
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x)
+      mine[k] = (k >= t.col_lo && k < t.col_hi) ? fma(t.inv_scale, q[k], w[k]) : w[k];
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence_system();
@@ -283,7 +287,7 @@ __global__ void __launch_bounds__(512) cg_tail_kernel(const StepArgs<T> a, const
 #pragma unroll
       for (int r = 0; r < 16; ++r)
         if (r < t.world) v += part[r];
-      q[k] = fma(t.scale, v, q[k]);
+      q[k] = t.scale * v;
     }
   } else {
     for (int64_t k = threadIdx.x; k < n; k += blockDim.x) q[k] = fma(t.scale, w[k], q[k]);
@@ -556,34 +560,39 @@ static int apply_operator(cggp_ctx* ctx, const cggp_operator* op, const void* V,
   return cggp_symm_matmul_ex(ctx, op->dtype, op->dev_A, op->lda, n, V, n, B, Y, n, wbuf, n, op->scale, active);
 }
 
-extern "C" int cggp_peer_enabled(cggp_ctx* ctx);
 
-// One non-refresh iteration on the matrix-free operator with the fused tail (see cg_tail_kernel): p @ Kuu runs on the
-// side stream WHILE the Kuf Kfu product runs on the main stream; the tail kernel then all-reduces over peer memory (or
-// takes the NCCL result), combines and does the vector update.
+// One non-refresh iteration on the matrix-free operator with the fused tail (see cg_tail_kernel).  The replicated term
+// p @ Kuu is SHARDED over the ranks when the tail all-reduces over peer memory: rank r computes the columns
+// [r n / W, (r + 1) n / W) only (1 / W of the HBM traffic of Kuu) and adds them, divided by sigma^-2, to its partial
+// product before the exchange, so the one sum over ranks delivers p @ Sigma / sigma^-2.  (Overlapping the full product
+// with the Kuf Kfu kernel on a side stream was measured first: it slowed that kernel by as much as it hid, 2.636 vs
+// 2.607 ms at 8 GPUs.)
+int cggp_symm_matmul_rows(cggp_ctx* ctx, int dtype, const void* A, int64_t lda, int64_t n, const void* V, int64_t ldv,
+                          int B, void* Y, int64_t ldy, int64_t row_lo, int64_t row_hi, const int* active);
+
 template <typename T>
 static int fused_tail_iteration(cggp_ctx* ctx, const cggp_operator* op, StepArgs<T>& a, T* q, T* w, bool peer) {
   const int64_t n = op->n;
   const int B = a.B;
-  cudaStream_t main_stream = ctx->stream;
-  CGGP_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main_stream));  // p of this iteration is final
-  CGGP_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
-  int rc = apply_kuf_kfu(ctx, op, a.p, B, w, a.state);  // enqueued first: its persistent CTAs take the SMs, the
-  if (rc) return rc;                                    // HBM-bound product below fills in next to them
-  ctx->stream = ctx->side_stream;
-  rc = cggp_symm_matmul_ex(ctx, op->dtype, op->dev_A, op->lda, n, a.p, n, B, q, n, nullptr, 0, 0.0, a.state);
-  ctx->stream = main_stream;
+  TailArgs<T> t{};
+  t.col_lo = 0;
+  t.col_hi = n;
+  if (peer) {
+    t.col_lo = n * ctx->rank / ctx->world;
+    t.col_hi = n * (ctx->rank + 1) / ctx->world;
+  }
+  int rc = cggp_symm_matmul_rows(ctx, op->dtype, op->dev_A, op->lda, n, a.p, n, B, q, n, t.col_lo, t.col_hi, a.state);
   if (rc) return rc;
-  CGGP_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
+  rc = apply_kuf_kfu(ctx, op, a.p, B, w, a.state);
+  if (rc) return rc;
   if (ctx->world > 1 && !peer) {
     rc = cggp_allreduce_sum(ctx, op->dtype, w, (int64_t)B * n);
     if (rc) return rc;
   }
-  CGGP_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
-  TailArgs<T> t{};
   t.w = w;
   t.q = q;
   t.scale = (T)op->scale;
+  t.inv_scale = (T)(1.0 / op->scale);
   t.world = peer ? ctx->world : 1;
   t.rank = ctx->rank;
   if (peer) {
@@ -595,7 +604,7 @@ static int fused_tail_iteration(cggp_ctx* ctx, const cggp_operator* op, StepArgs
   a.mode = MODE_STEP;
   a.q = q;
   ProfScope prof(ctx, 2);
-  cg_tail_kernel<T><<<B, 512, 0, main_stream>>>(a, t);
+  cg_tail_kernel<T><<<B, 512, 0, ctx->stream>>>(a, t);
   CGGP_LAUNCH_CHECK(ctx);
   return CGGP_OK;
 }
@@ -633,11 +642,6 @@ static int cg_solve_impl(cggp_ctx* ctx, const cggp_operator* op, const void* rhs
   const bool eye = !pc || pc->type == CGGP_PRECOND_EYE;
   const bool fused_tail = tail_env && sgpr && eye && B <= 8;
   const bool peer_tail = fused_tail && ctx->world > 1 && cggp_peer_enabled(ctx) && (int64_t)vec <= ctx->peer_slot_bytes;
-  if (fused_tail && !ctx->side_stream) {
-    CGGP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
-    CGGP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-    CGGP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-  }
 
   int* st = ctx->cg_state;
   ctx->cg_state_host[0] = 1;

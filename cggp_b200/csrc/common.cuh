@@ -44,9 +44,6 @@ struct cggp_ctx {
   int64_t peer_slot_bytes = 0;
   unsigned peer_seq = 0;
   int* peer_counter = nullptr;
-  // side stream + events for work that overlaps the product inside a CG iteration (cg.cu: p @ Kuu)
-  cudaStream_t side_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // optional per-section device timing (cggp_profile_*): event pairs recorded on the ctx stream
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev[CGGP_PROF_SECTIONS];  // start, stop, start, stop, ...

@@ -18,16 +18,18 @@ struct Vec2<float> { using type = float2; };
 // are latency-bound otherwise.
 template <typename T, int BB, int ROWS>
 __global__ void __launch_bounds__(256)
-symm_gemv_kernel(const T* __restrict__ A, int64_t lda, int64_t n, const T* __restrict__ V, int64_t ldv,
+symm_gemv_kernel(const T* __restrict__ A, int64_t lda, int64_t n, int64_t nrows, const T* __restrict__ V, int64_t ldv,
                  T* __restrict__ Y, int64_t ldy, const T* __restrict__ addend, int64_t ldadd, T scale,
                  const int* __restrict__ active) {
+  // A points at the first of `nrows` rows (all n columns of each are contracted); Y / addend at their first column
   if (cg_inactive(active)) return;
   const int lane = threadIdx.x & 31;
   const int64_t j0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
-  if (j0 >= n) return;
+  if (j0 >= nrows) return;
   const T* __restrict__ row[ROWS];
 #pragma unroll
-  for (int r = 0; r < ROWS; ++r) row[r] = A + (j0 + r < n ? j0 + r : n - 1) * lda;  // clamp: tail rows recompute n-1
+  for (int r = 0; r < ROWS; ++r)
+    row[r] = A + (j0 + r < nrows ? j0 + r : nrows - 1) * lda;  // clamp: tail rows recompute the last one
   T acc[ROWS][BB];
 #pragma unroll
   for (int r = 0; r < ROWS; ++r)
@@ -72,7 +74,7 @@ symm_gemv_kernel(const T* __restrict__ A, int64_t lda, int64_t n, const T* __res
 #pragma unroll
     for (int b = 0; b < BB; ++b) {
       T s = warp_sum(acc[r][b]);
-      if (lane == 0 && j0 + r < n) {
+      if (lane == 0 && j0 + r < nrows) {
         if (addend) s = fma(scale, addend[b * ldadd + j0 + r], s);
         Y[b * ldy + j0 + r] = s;
       }
@@ -81,9 +83,18 @@ symm_gemv_kernel(const T* __restrict__ A, int64_t lda, int64_t n, const T* __res
 
 template <typename T>
 static int symm_matmul_impl(cggp_ctx* ctx, const T* A, int64_t lda, int64_t n, const T* V, int64_t ldv, int B, T* Y,
-                            int64_t ldy, const T* addend, int64_t ldadd, T scale, const int* active) {
+                            int64_t ldy, const T* addend, int64_t ldadd, T scale, const int* active,
+                            int64_t row_lo = 0, int64_t row_hi = -1) {
+  // [row_lo, row_hi): only these output columns Y[:, j] (= rows j of the symmetric A) are computed (B <= 8 path)
+  if (row_hi < 0) row_hi = n;
+  const int64_t nrows = row_hi - row_lo;
+  if (nrows <= 0) return CGGP_OK;
+  A += row_lo * lda;
+  Y += row_lo;
+  if (addend) addend += row_lo;
   int b0 = 0;
   if (B > 8) {
+    if (nrows != n) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "row-range symmetric product needs B <= 8");
     // DMMA tile GEMM, NT form: C[b, j] = sum_k V[b, k] A[j, k]
     int rc = dmma_gemm_nt<T>(ctx, V, ldv, B, A, lda, n, n, Y, ldy, addend, ldadd, scale, active);
     return rc;
@@ -95,14 +106,14 @@ static int symm_matmul_impl(cggp_ctx* ctx, const T* A, int64_t lda, int64_t n, c
     // measured on B200 (tools/bench_dense.py): one right-hand side streams best with 1 row per warp once there are
     // enough rows to fill the machine; several right-hand sides want their reads of V amortised over 2-4 rows
     const int rows = bb == 1 ? ((n >= 2048 && n < 8192) ? 2 : 1) : ((n >= 8192 && bb <= 4) ? 4 : (n >= 2048 ? 2 : 1));
-    const int64_t nw = (n + rows - 1) / rows;
+    const int64_t nw = (nrows + rows - 1) / rows;
     const unsigned grid = (unsigned)((nw + warps - 1) / warps);
     const T* Vb = V + (int64_t)b0 * ldv;
     T* Yb = Y + (int64_t)b0 * ldy;
     const T* Ab = addend ? addend + (int64_t)b0 * ldadd : nullptr;
 #define GEMV_R(BBV, R)                                                                                          \
-  symm_gemv_kernel<T, BBV, R><<<grid, warps * 32, 0, ctx->stream>>>(A, lda, n, Vb, ldv, Yb, ldy, Ab, ldadd, scale, \
-                                                                    active)
+  symm_gemv_kernel<T, BBV, R><<<grid, warps * 32, 0, ctx->stream>>>(A, lda, n, nrows, Vb, ldv, Yb, ldy, Ab, ldadd,  \
+                                                                    scale, active)
 #define GEMV(BBV)                         \
   do {                                    \
     if (rows == 4 && BBV <= 4) {          \
@@ -132,6 +143,16 @@ static int symm_matmul_impl(cggp_ctx* ctx, const T* A, int64_t lda, int64_t n, c
 }
 
 // internal entry used by the CG driver (adds the optional scaled addend and the loop-active flag)
+int cggp_symm_matmul_rows(cggp_ctx* ctx, int dtype, const void* A, int64_t lda, int64_t n, const void* V, int64_t ldv,
+                          int B, void* Y, int64_t ldy, int64_t row_lo, int64_t row_hi, const int* active) {
+  ProfScope prof(ctx, 1);
+  if (dtype == CGGP_F64)
+    return symm_matmul_impl<double>(ctx, (const double*)A, lda, n, (const double*)V, ldv, B, (double*)Y, ldy, nullptr,
+                                    0, 0.0, active, row_lo, row_hi);
+  return symm_matmul_impl<float>(ctx, (const float*)A, lda, n, (const float*)V, ldv, B, (float*)Y, ldy, nullptr, 0,
+                                 0.0f, active, row_lo, row_hi);
+}
+
 int cggp_symm_matmul_ex(cggp_ctx* ctx, int dtype, const void* A, int64_t lda, int64_t n, const void* V, int64_t ldv,
                         int B, void* Y, int64_t ldy, const void* addend, int64_t ldadd, double scale,
                         const int* active) {
