@@ -33,10 +33,16 @@ extern "C" int cggp_ctx_create(int device, cggp_ctx** out) {
     g_err = "device index out of range";
     return CGGP_ERR_INVALID;
   }
+  int prev_device = -1;
+  cudaGetDevice(&prev_device);
   if ((e = cudaSetDevice(device)) != cudaSuccess) {
     g_err = cudaGetErrorString(e);
     return CGGP_ERR_CUDA;
   }
+  struct Restore {  // the caller's current device is left as it was
+    int d;
+    ~Restore() { if (d >= 0) cudaSetDevice(d); }
+  } restore{prev_device};
   cggp_ctx* ctx = new cggp_ctx();
   ctx->device = device;
   cudaDeviceProp prop;
@@ -83,6 +89,7 @@ extern "C" int cggp_ctx_destroy(cggp_ctx* ctx) {
 
 extern "C" int cggp_ctx_set_stream(cggp_ctx* ctx, void* stream) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   ctx->stream = (cudaStream_t)stream;
   return CGGP_OK;
 }
@@ -115,6 +122,7 @@ ProfScope::~ProfScope() {
 
 extern "C" int cggp_profile_enable(cggp_ctx* ctx, int on) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   ctx->prof_on = on != 0;
   for (int s = 0; s < CGGP_PROF_SECTIONS; ++s) ctx->prof_used[s] = 0;
   return CGGP_OK;
@@ -122,6 +130,7 @@ extern "C" int cggp_profile_enable(cggp_ctx* ctx, int on) {
 
 extern "C" int cggp_profile_read(cggp_ctx* ctx, int section, double* host_ms_total, int64_t* host_count) {
   if (!ctx || section < 0 || section >= CGGP_PROF_SECTIONS || !host_ms_total || !host_count) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   CGGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   double total = 0.0;
   for (size_t i = 0; i < ctx->prof_used[section]; ++i) {
@@ -211,6 +220,7 @@ extern "C" int cggp_comm_unique_id(void* host_id128) {
 
 extern "C" int cggp_ctx_comm_init(cggp_ctx* ctx, const void* host_id128, int rank, int world) {
   if (!ctx || !host_id128 || world < 1 || rank < 0 || rank >= world) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   cggp_ctx_comm_destroy(ctx);
   ctx->rank = rank;
   ctx->world = world;
@@ -229,6 +239,7 @@ extern "C" int cggp_peer_close(cggp_ctx* ctx);
 extern "C" int cggp_ctx_comm_destroy(cggp_ctx* ctx) {
   cggp_peer_close(ctx);
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   ctx->comm = nullptr;
   ctx->world = 1;
@@ -299,6 +310,7 @@ extern "C" int cggp_peer_close(cggp_ctx* ctx) {
 // step 1 (every rank): allocate this rank's buffer (2 slots of slot_bytes + flags) and export its 64-byte IPC handle
 extern "C" int cggp_peer_alloc(cggp_ctx* ctx, int64_t slot_bytes, void* host_handle64) {
   if (!ctx || !host_handle64 || slot_bytes <= 0) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   cggp_peer_close(ctx);
   slot_bytes = (slot_bytes + 255) / 256 * 256;
@@ -318,6 +330,7 @@ extern "C" int cggp_peer_alloc(cggp_ctx* ctx, int64_t slot_bytes, void* host_han
 // order.  Call only after cggp_ctx_comm_init (rank / world).
 extern "C" int cggp_peer_open(cggp_ctx* ctx, const void* host_handles, int world) {
   if (!ctx || !host_handles) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (!ctx->peer_local) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "cggp_peer_alloc first");
   if (world != ctx->world || world < 2 || world > 16) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "peer table: bad world size %d", world);
   for (int r = 0; r < world; ++r) {
@@ -347,6 +360,7 @@ extern "C" int cggp_peer_enabled(cggp_ctx* ctx) { return ctx && ctx->peer_ptrs_d
 
 extern "C" int cggp_allreduce_sum(cggp_ctx* ctx, int dtype, void* buf, int64_t count) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (ctx->world == 1 || count == 0) return CGGP_OK;
   const int64_t bytes = count * (dtype == CGGP_F64 ? 8 : 4);
   if (cggp_peer_enabled(ctx) && bytes <= ctx->peer_slot_bytes) {
@@ -395,6 +409,7 @@ extern "C" int cggp_kuf_kfu_matvec(cggp_ctx* ctx, int dtype, int kind, double va
                                    const void* nX, int64_t n, const void* PZ, const void* nZ, int64_t m, int D,
                                    int64_t ldp, const void* V, int64_t ldv, int B, void* W, int64_t ldw, int variant) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (B <= 0 || m <= 0) return CGGP_OK;
   if (variant != 0 && variant != 1 && variant != 3) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "variant must be 0, 1 or 3");
   return cggp_matvec_dispatch(ctx, dtype, kind, variance, PX, nX, n, PZ, nZ, m, D, ldp, V, ldv, B, W, ldw, variant,
@@ -410,6 +425,7 @@ extern "C" int cggp_kuf_kfu_matvec_tf32(cggp_ctx* ctx, int kind, double variance
                                         int64_t m, int D, const void* V, int64_t ldv, int B, void* W, int64_t ldw,
                                         int nsplit) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (B <= 0 || m <= 0) return CGGP_OK;
   if (kind < CGGP_SE || kind > CGGP_MATERN52) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "unknown kernel kind %d", kind);
   if (nsplit != 1 && nsplit != 3 && nsplit != 16)
@@ -424,6 +440,7 @@ extern "C" int cggp_kuf_times(cggp_ctx* ctx, int dtype, int kind, double varianc
                               int64_t n, const void* PZ, const void* nZ, int64_t m, int D, int64_t ldp, const void* Y,
                               int64_t ldy, int P, void* W, int64_t ldw) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (P <= 0 || m <= 0) return CGGP_OK;
   if (kind < CGGP_SE || kind > CGGP_MATERN52) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "unknown kernel kind %d", kind);
   if (!cggp_matvec_pipe_supported(ctx, dtype, m, D, P))
@@ -493,6 +510,7 @@ __global__ void mb_kernel(int which, double* out, int iters, double s, const int
 
 extern "C" int cggp_microbench(cggp_ctx* ctx, int which, int iters, double* host_gops) {
   if (!ctx || !host_gops || which < 0 || which > 6 || iters < 1) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   const int2* etab = nullptr;
   if (which == 5) {
     int rce = kpipe::exp_table_device(ctx, &etab);

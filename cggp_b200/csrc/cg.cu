@@ -404,6 +404,7 @@ __global__ void block_cholesky_kernel(const T* __restrict__ A, int64_t lda, cons
 extern "C" int cggp_block_cholesky(cggp_ctx* ctx, int dtype, const void* A, int64_t lda, int64_t n,
                                    const int64_t* idx, int num_blocks, int block_size, void* chol) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (block_size < 1 || block_size > MAX_BS)
     CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "block_size %d outside [1, %d]", block_size, MAX_BS);
   if ((int64_t)num_blocks * block_size != n)
@@ -489,6 +490,7 @@ __global__ void __launch_bounds__(512) block_precond_kernel(StepArgs<T> a) {
 extern "C" int cggp_block_precond_apply(cggp_ctx* ctx, int dtype, int B, int64_t n, const void* r,
                                         const cggp_precond* pc, void* z) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (B <= 0 || n <= 0) return CGGP_OK;
   if (!pc || pc->type != CGGP_PRECOND_BLOCK) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "block preconditioner expected");
   int rc = check_precond(ctx, pc, n);
@@ -511,6 +513,7 @@ extern "C" int cggp_block_precond_apply(cggp_ctx* ctx, int dtype, int B, int64_t
 extern "C" int cggp_cg_fused_step(cggp_ctx* ctx, int dtype, int B, int64_t n, const void* pA, void* v, void* r,
                                   void* p, void* rz, void* half_rr, const cggp_precond* pc) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (B <= 0 || n <= 0) return CGGP_OK;
   int rc = check_precond(ctx, pc, n);
   if (rc) return rc;
@@ -761,6 +764,7 @@ extern "C" int cggp_cg_solve(cggp_ctx* ctx, const cggp_operator* op, const void*
                              int check_every, void* solution, int32_t* host_steps, void* half_rz, void* history,
                              int64_t history_cap) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (!op || !rhs || !solution) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "null operator / rhs / solution");
   if (op->struct_size != (uint32_t)sizeof(cggp_operator))
     CGGP_FAIL(ctx, CGGP_ERR_INVALID, "cggp_operator.struct_size is %u, this library expects %u (set it to sizeof of the "

@@ -59,6 +59,20 @@ struct ProfScope {
   ~ProfScope();
 };
 
+// A process may drive several devices (one ctx each): every ABI entry runs on the device of its ctx and restores the
+// caller's current device on return.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const cggp_ctx* c) {
+    if (c && cudaGetDevice(&prev) == cudaSuccess && prev != c->device) switched = cudaSetDevice(c->device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+#define CGGP_DEVICE_GUARD(ctx) DeviceGuard _cggp_device_guard(ctx)
+
 #define CGGP_FAIL(ctx, code, ...)                       \
   do {                                                  \
     char _buf[512];                                     \

@@ -167,6 +167,7 @@ int cggp_symm_matmul_ex(cggp_ctx* ctx, int dtype, const void* A, int64_t lda, in
 extern "C" int cggp_symm_matmul(cggp_ctx* ctx, int dtype, const void* A, int64_t lda, int64_t n, const void* V,
                                 int64_t ldv, int B, void* Y, int64_t ldy) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (B <= 0 || n <= 0) return CGGP_OK;
   return cggp_symm_matmul_ex(ctx, dtype, A, lda, n, V, ldv, B, Y, ldy, nullptr, 0, 0.0, nullptr);
 }
@@ -203,6 +204,7 @@ extern "C" int cggp_kuf_gram(cggp_ctx* ctx, int dtype, int kind, double variance
                              int64_t n, const void* PZ, const void* nZ, int64_t m, int D, int64_t ldp, void* G,
                              int64_t ldg, int accumulate) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (m <= 0) return CGGP_OK;
   if (!G || ldg < m) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "gram: output must be [m, m] with ldg >= m");
   const size_t es = dtype == CGGP_F64 ? 8 : 4;

@@ -752,6 +752,7 @@ extern "C" int cggp_tf32_sizes(int nsplit, int64_t n, int D, int64_t* stream_flo
 extern "C" int cggp_tf32_prepare(cggp_ctx* ctx, int nsplit, const void* P, const void* norms, int64_t n, int D,
                                  int64_t ldp, void* stream, void* rows_buf, void* norms_pad) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (D < 1 || n < 0) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "bad shape");
   if (nsplit != 1 && nsplit != 3 && nsplit != tf32::F16X3)
     CGGP_FAIL(ctx, CGGP_ERR_INVALID, "nsplit must be 1, 3 (TF32) or 16 (3xFP16)");
@@ -842,8 +843,13 @@ static int gram_sweep(cggp_ctx* ctx, int kind, double variance, int nsplit, int 
     a.stages = ring.stages;
     a.gc = ring.gc;
     a.niss = ring.niss;
-    static const int dbg_env = getenv("CGGP_TF32_DBG") ? atoi(getenv("CGGP_TF32_DBG")) : 0;  // timing experiments
+#ifdef CGGP_DEBUG_KNOBS
+    // timing experiments that switch parts of the product OFF (wrong results): only in builds with -DCGGP_DEBUG_KNOBS
+    static const int dbg_env = getenv("CGGP_TF32_DBG") ? atoi(getenv("CGGP_TF32_DBG")) : 0;
     a.dbg = dbg_env;
+#else
+    a.dbg = 0;  // the shipped library ignores CGGP_TF32_DBG
+#endif
     a.active = active;
     fn<<<dim3((unsigned)p_blocks, (unsigned)splits), 384, smem, ctx->stream>>>(a, KP);
     CGGP_LAUNCH_CHECK(ctx);
@@ -904,6 +910,7 @@ extern "C" int cggp_kuf_times_tf32(cggp_ctx* ctx, int kind, double variance, con
                                    int64_t m, int D, const void* Yt, int64_t ldy, int P, void* W, int64_t ldw,
                                    int nsplit) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (P <= 0 || m <= 0) return CGGP_OK;
   if (kind < CGGP_SE || kind > CGGP_MATERN52) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "unknown kernel kind %d", kind);
   if (nsplit != 1 && nsplit != 3 && nsplit != tf32::F16X3)

@@ -61,6 +61,7 @@ __global__ void gauss_expect_final_kernel(const double* __restrict__ partial, in
 extern "C" int cggp_elbo_terms(cggp_ctx* ctx, int dtype, const void* y, const void* mean, const void* var, int64_t n,
                                double noise_variance, void* out) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (!out || n < 0 || !(noise_variance > 0.0)) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "elbo_terms: bad arguments");
   const int np = 256;
   int rc = cggp_ws_reserve(ctx, sizeof(double) * np);
@@ -89,6 +90,7 @@ extern "C" int cggp_predict_f(cggp_ctx* ctx, int dtype, int kind, double varianc
                               int max_steps_cycle, void* Knm_work, void* S_work, void* mean, void* var,
                               int32_t* host_steps) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (host_steps) *host_steps = 0;
   if (nb <= 0) return CGGP_OK;
   if (!A || !a || !Knm_work || !S_work || !mean || !var || m <= 0)

@@ -340,6 +340,7 @@ extern "C" int64_t cggp_prepared_ld(int D) { return ((int64_t)D + 1 + 3) / 4 * 4
 extern "C" int cggp_prepare_points(cggp_ctx* ctx, int dtype, const void* X, int64_t n, int D, int64_t ldx,
                                    const double* ls, int ls_count, void* P, int64_t ldp, void* norms) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (D < 1 || D > 128) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "D=%d outside [1,128]", D);
   if (ls_count != 1 && ls_count != D) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "lengthscales count %d != 1 or D", ls_count);
   if (ldp < cggp_prepared_ld(D)) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "ldp=%lld < %lld", (long long)ldp,
@@ -384,6 +385,7 @@ extern "C" int cggp_kernel_matrix(cggp_ctx* ctx, int dtype, int kind, double var
                                   const void* PA, const void* nA, int64_t n, const void* PB, const void* nB, int64_t m,
                                   int D, int64_t ldp, double jitter, void* out, int64_t ldo) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (n == 0 || m == 0) return CGGP_OK;
   if (n > 65535LL * TILE) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "n too large for one kernel_matrix call; batch it");
   if (ldo < m) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "ldo < m");
@@ -430,6 +432,7 @@ extern "C" int cggp_nearest_center(cggp_ctx* ctx, int dtype, int kind, double va
                                    const void* nX, int64_t n, const void* PZ, const void* nZ, int64_t m, int D,
                                    int64_t ldp, int64_t* idx, void* dist) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (n == 0) return CGGP_OK;
   if (m == 0) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "nearest_center needs at least one centre");
   if (dtype == CGGP_F64)
@@ -465,6 +468,7 @@ extern "C" int cggp_kernel_matrix_backward(cggp_ctx* ctx, int dtype, int kind, d
                                            const double* host_lengthscales, int ls_count, const void* G, int64_t ldg,
                                            void* g_variance, void* g_ls) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   if (D < 1 || D > 128) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "D=%d outside [1,128]", D);
   if (ls_count != 1 && ls_count != D) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "lengthscales count %d != 1 or D", ls_count);
   if ((int64_t)((n + TILE - 1) / TILE) > 65535) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "too many rows for one call");
@@ -484,6 +488,7 @@ extern "C" int cggp_kernel_matrix_backward(cggp_ctx* ctx, int dtype, int kind, d
 extern "C" int cggp_cluster_stats(cggp_ctx* ctx, int dtype, const int64_t* idx, const void* y, int64_t n, int64_t m,
                                   void* counts, void* sums) {
   if (!ctx) return CGGP_ERR_INVALID;
+  CGGP_DEVICE_GUARD(ctx);
   const size_t es = dtype == CGGP_F64 ? 8 : 4;
   CGGP_CUDA(ctx, cudaMemsetAsync(counts, 0, es * m, ctx->stream));
   CGGP_CUDA(ctx, cudaMemsetAsync(sums, 0, es * m, ctx->stream));
