@@ -39,9 +39,16 @@ def _worker(rank, world, port, N, M, D, out):
     Kuu = g.Kuu(Z, k, 1e-6)
 
     def matmul(V):  # Sigma = Kuu + Kuf Kfu / s2 with the data term all-reduced (the one collective of the path)
-        part = torch.from_numpy(om.kuf_kfu_matmul(k, X[s:e], Z, V))
+        # the fused tail kernel's form (csrc/cg.cu cg_tail_kernel): every rank adds ITS columns [r M / W, (r + 1) M / W)
+        # of the replicated term V Kuu, divided by the scale 1 / s2, to its partial product; the one sum over ranks then
+        # delivers V Sigma / scale
+        scale = 1.0 / 0.1
+        part = om.kuf_kfu_matmul(k, X[s:e], Z, V)
+        lo, hi = M * rank // world, M * (rank + 1) // world
+        part[:, lo:hi] += (V @ Kuu[:, lo:hi]) / scale
+        part = torch.from_numpy(part)
         dist.all_reduce(part)
-        return V @ Kuu + part.numpy() / 0.1
+        return scale * part.numpy()
 
     rhs_part = torch.from_numpy((k.K(Z, X[s:e]) @ y[s:e] / 0.1).T.copy())
     dist.all_reduce(rhs_part)
