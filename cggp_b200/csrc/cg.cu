@@ -224,6 +224,7 @@ struct TailArgs {
   T* q;             // [B, n] in: p @ Kuu (world == 1: all columns; else this rank's columns [col_lo, col_hi)), out: p Sigma
   T scale, inv_scale;
   int64_t col_lo, col_hi;  // world > 1: the slice of p @ Kuu this rank computed and contributes to the sum
+  int shard;               // world > 1: 1 = p @ Kuu sharded over ranks (above), 0 = every rank holds all of it in q
   // peer exchange (world > 1)
   char* const* peers;
   int rank, world;
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(512) cg_tail_kernel(const StepArgs<T> a, const
     T* mine = reinterpret_cast<T*>(t.peers[t.rank] + slot * t.slot_bytes) + (int64_t)b * n;
     // this rank's share of the replicated term rides in the same sum: every rank computes 1 / world of p @ Kuu
     for (int64_t k = threadIdx.x; k < n; k += blockDim.x)
-      mine[k] = (k >= t.col_lo && k < t.col_hi) ? fma(t.inv_scale, q[k], w[k]) : w[k];
+      mine[k] = (t.shard && k >= t.col_lo && k < t.col_hi) ? fma(t.inv_scale, q[k], w[k]) : w[k];
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence_system();
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(512) cg_tail_kernel(const StepArgs<T> a, const
 #pragma unroll
       for (int r = 0; r < 16; ++r)
         if (r < t.world) v += part[r];
-      q[k] = t.scale * v;
+      q[k] = t.shard ? t.scale * v : fma(t.scale, v, q[k]);
     }
   } else {
     for (int64_t k = threadIdx.x; k < n; k += blockDim.x) q[k] = fma(t.scale, w[k], q[k]);
@@ -580,7 +581,9 @@ static int fused_tail_iteration(cggp_ctx* ctx, const cggp_operator* op, StepArgs
   TailArgs<T> t{};
   t.col_lo = 0;
   t.col_hi = n;
-  if (peer) {
+  static const int shard_env = getenv("CGGP_TAIL_SHARD") ? atoi(getenv("CGGP_TAIL_SHARD")) : 1;  // tuning knob
+  t.shard = (peer && shard_env) ? 1 : 0;
+  if (t.shard) {
     t.col_lo = n * ctx->rank / ctx->world;
     t.col_hi = n * (ctx->rank + 1) / ctx->world;
   }
