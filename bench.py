@@ -535,7 +535,7 @@ def run_native(args):
         # the multi-RHS form of the headline product: 8 right-hand sides per sweep, both contractions on DMMA
         try:
             g8 = torch.Generator(device=device).manual_seed(3)
-            X8 = torch.randn(min(N, 500_000), D, dtype=f64, device=device, generator=g8)
+            X8 = torch.randn(min(N, 1_000_000), D, dtype=f64, device=device, generator=g8)
             op8 = cb.SGPROperator(kernel, X8, Zd, NOISE)
             V8 = torch.randn(8, M, dtype=f64, device=device, generator=g8)
             for _ in range(2):
