@@ -3,6 +3,8 @@
 //   Y[b, j] = sum_k V[b, k] * A[j, k].
 // Small B (<= 8, the headline B = 1 and the 5-probe case) is HBM-bound on A: one warp per row of A, 16-byte loads,
 // B accumulators, warp-shuffle reduction.  Larger B goes through the DMMA tile GEMM (dmma_gemm.cuh).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "dmma_gemm.cuh"
 
@@ -210,8 +212,13 @@ extern "C" int cggp_kuf_gram(cggp_ctx* ctx, int dtype, int kind, double variance
   const size_t es = dtype == CGGP_F64 ? 8 : 4;
   if (!accumulate) CGGP_CUDA(ctx, cudaMemset2DAsync(G, (size_t)ldg * es, 0, (size_t)m * es, (size_t)m, ctx->stream));
   if (n <= 0) return CGGP_OK;
-  int64_t nc = (int64_t)((size_t)(1u << 26) / ((size_t)m * es));  // 64 MB chunks
-  nc = nc < 256 ? 256 : nc;
+  // rows per chunk: 64 MB of Kuf, but never fewer than 2048 rows - the rank-k update then runs 64 k-tiles per output
+  // tile and the GEMM's prologue / epilogue is amortised (M = 16384: 268 MB chunks; measured with 512-row chunks:
+  // 23.6 TFLOP/s executed, profiles/r02_c4_predict_g8.json)
+  static const int64_t nc_env = getenv("CGGP_GRAM_ROWS") ? atoll(getenv("CGGP_GRAM_ROWS")) : 0;  // tuning knob
+  int64_t nc = (int64_t)((size_t)(1u << 26) / ((size_t)m * es));
+  nc = nc < 2048 ? 2048 : nc;
+  if (nc_env > 0) nc = nc_env;
   nc = (nc + 31) / 32 * 32;
   if (nc > n) nc = (n + 1) / 2 * 2;
   int rc = cggp_ws2_reserve(ctx, (size_t)m * (size_t)nc * es);
