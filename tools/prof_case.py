@@ -1,5 +1,5 @@
 """Short single-GPU cases for ncu (one kernel family per run, few launches; the same command line must first exit 0
-without ncu - B200_PROFILING.md):  python tools/prof_case.py pipe1 | pipe8 | cg | gram"""
+without ncu - B200_PROFILING.md):  python tools/prof_case.py pipe1 | pipe8 | cg | gram [rows]"""
 import os
 import sys
 
@@ -12,7 +12,7 @@ import cggp_b200 as cb
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "pipe1"
     g = torch.Generator(device="cuda").manual_seed(0)
-    N, M, D = 500_000, 4096, 11
+    N, M, D = (int(sys.argv[2]) if len(sys.argv) > 2 else 500_000), 4096, 11
     X = torch.randn(N, D, dtype=torch.float64, device="cuda", generator=g)
     Z = torch.randn(M, D, dtype=torch.float64, device="cuda", generator=g)
     k = cb.Matern52(variance=1.0, lengthscales=[1.0] * D)
