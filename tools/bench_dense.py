@@ -50,5 +50,33 @@ def main():
           f"{2.0 * B * M * M * its / t / 1e9:.2f} TFLOP/s on the product", flush=True)
 
 
+def step_kernel_bandwidth():
+    """The fused CG vector update alone (cggp_cg_fused_step): reads p, pA, v, r and writes v, r, p = 7 B M sizeof bytes
+    per call against the measured HBM copy bandwidth of MEASURED_PEAKS.json (6551.7 GB/s)."""
+    import ctypes as C
+
+    from cggp_b200 import _lib
+
+    ctx = _lib.context()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for B, M in ((1, 4096), (5, 16384), (2000, 2048), (4096, 4096), (4096, 16384)):
+        bufs = [torch.randn(B, M, dtype=torch.float64, device="cuda", generator=g) for _ in range(4)]
+        pA, v, r, p = bufs
+        rz = torch.ones(B, dtype=torch.float64, device="cuda")
+        hrr = torch.empty(B, dtype=torch.float64, device="cuda")
+
+        def call():
+            ctx.use_current_stream()
+            ctx.check(ctx.lib.cggp_cg_fused_step(ctx.handle, _lib.F64, B, M, _lib.ptr(pA), _lib.ptr(v), _lib.ptr(r),
+                                                 _lib.ptr(p), _lib.ptr(rz), _lib.ptr(hrr), None))
+        t = timeit(call, reps=5, warm=2)
+        byts = 7.0 * B * M * 8
+        print(f"cg_step_kernel B={B:5d} M={M:6d}: {t * 1e3:9.1f} us, {byts / 1e6:9.1f} MB -> {byts / t / 1e6:8.1f} GB/s "
+              f"= {byts / t / 1e6 / 6551.7:.3f} of the measured HBM copy bandwidth", flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if "step" in sys.argv[1:]:
+        step_kernel_bandwidth()
+    else:
+        main()
