@@ -103,7 +103,39 @@ __device__ void block_precond_apply(const StepArgs<T>& a, const T* __restrict__ 
   }
 }
 
+// Loop control by the last CTA of a launch (stopping condition, conjugate_gradient.py:59-62): history row, iteration
+// counter and the device-side `active` flag.
 template <typename T>
+__device__ __forceinline__ void cg_loop_control(const StepArgs<T>& a, int& s_last) {
+  if (!a.state) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&a.state[2], 1) == a.B - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int it = (a.mode == MODE_INIT) ? 0 : a.state[1] + 1;
+  int over = 0;
+  const volatile T* hr = a.half_rr;
+  for (int k = threadIdx.x; k < a.B; k += blockDim.x) {
+    const T h = hr[k];
+    if (h > a.threshold) over = 1;
+    if (a.history && it < a.history_cap) a.history[(int64_t)it * a.B + k] = h;
+  }
+  over = __syncthreads_or(over);
+  if (threadIdx.x == 0) {
+    a.state[1] = it;
+    a.state[2] = 0;
+    a.state[0] = (over && it < a.max_iterations) ? 1 : 0;
+  }
+}
+
+// EPT > 0: the row of the four vectors lives in REGISTERS (EPT elements per thread, n <= EPT * blockDim.x; plain
+// iteration, Eye preconditioner): p, pA, v, r are read from HBM once and v, r, p written once - the algorithmic
+// 7 B n sizeof bytes - instead of the three passes of the general form (11 vector transfers, 4 of them from L2).
+// Same arithmetic in the same order as the general form (element e of thread t is index t + e * blockDim.x, exactly
+// the order of its strided loops), so the results are bit-identical.
+template <typename T, int EPT>
 __device__ __forceinline__ void cg_step_body(const StepArgs<T>& a, T* red, int& s_last) {
   const int b = blockIdx.x;
   const int64_t n = a.n;
@@ -115,6 +147,52 @@ __device__ __forceinline__ void cg_step_body(const StepArgs<T>& a, T* red, int& 
   const T min_float = T(1e-16);  // conjugate_gradient.py:50 (1e-16 also for float32)
   T gamma = T(0);
   const T rz_old = (a.mode == MODE_STEP || a.mode == MODE_PRE) ? a.rz[b] : T(0);
+  if constexpr (EPT > 0) {
+    T pk[EPT], qk[EPT], vk[EPT], rk[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int64_t k = threadIdx.x + (int64_t)e * blockDim.x;
+      const bool ok = k < n;
+      pk[e] = ok ? p[k] : T(0);
+      qk[e] = ok ? q[k] : T(0);
+      vk[e] = ok ? v[k] : T(0);
+      rk[e] = ok ? r[k] : T(0);
+    }
+    T part = T(0);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e)
+      if (threadIdx.x + (int64_t)e * blockDim.x < n) part = add_rn(part, mul_rn(pk[e], qk[e]));
+    const T denom = block_sum(part, red);                       // :66
+    gamma = denom <= min_float ? T(0) : div_rn(rz_old, denom);  // :67-68
+    T rr_part = T(0);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e)
+      if (threadIdx.x + (int64_t)e * blockDim.x < n) {
+        vk[e] = add_rn(vk[e], mul_rn(gamma, pk[e]));   // :69
+        rk[e] = add_rn(rk[e], -mul_rn(gamma, qk[e]));  // :75
+        rr_part = add_rn(rr_part, mul_rn(rk[e], rk[e]));
+      }
+    const T rr = block_sum(rr_part, red);
+    const T rz_new = rr;  // EyePreconditioner: z = r
+    const bool dead = rz_old <= min_float;  // :79
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int64_t k = threadIdx.x + (int64_t)e * blockDim.x;
+      if (k < n) {
+        const T upd = dead ? T(0) : div_rn(mul_rn(pk[e], rz_new), rz_old);  // :78
+        v[k] = vk[e];
+        r[k] = rk[e];
+        p[k] = add_rn(rk[e], upd);  // :83
+      }
+    }
+    if (threadIdx.x == 0) {
+      a.rz[b] = rz_new;
+      a.half_rr[b] = T(0.5) * rr;
+      if (a.half_rz) a.half_rz[b] = T(0.5) * rz_new;  // :97
+    }
+    cg_loop_control(a, s_last);
+    return;
+  }
 
   if (a.mode == MODE_STEP || a.mode == MODE_PRE) {
     T part = T(0);
@@ -175,36 +253,15 @@ __device__ __forceinline__ void cg_step_body(const StepArgs<T>& a, T* red, int& 
     a.half_rr[b] = half;
     if (a.half_rz) a.half_rz[b] = T(0.5) * rz_new;  // :97
   }
-  if (!a.state) return;
-  // ---- loop control by the last CTA of this launch (stopping condition :59-62) ----
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&a.state[2], 1) == a.B - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const int it = (a.mode == MODE_INIT) ? 0 : a.state[1] + 1;
-  int over = 0;
-  const volatile T* hr = a.half_rr;
-  for (int k = threadIdx.x; k < a.B; k += blockDim.x) {
-    const T h = hr[k];
-    if (h > a.threshold) over = 1;
-    if (a.history && it < a.history_cap) a.history[(int64_t)it * a.B + k] = h;
-  }
-  over = __syncthreads_or(over);
-  if (threadIdx.x == 0) {
-    a.state[1] = it;
-    a.state[2] = 0;
-    a.state[0] = (over && it < a.max_iterations) ? 1 : 0;
-  }
+  cg_loop_control(a, s_last);
 }
 
-template <typename T>
+template <typename T, int EPT>
 __global__ void __launch_bounds__(512) cg_step_kernel(const StepArgs<T> a) {
   if (a.state && a.state[0] == 0) return;
   __shared__ T red[33];
   __shared__ int s_last;
-  cg_step_body(a, red, s_last);
+  cg_step_body<T, EPT>(a, red, s_last);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -294,7 +351,7 @@ __global__ void __launch_bounds__(512) cg_tail_kernel(const StepArgs<T> a, const
     for (int64_t k = threadIdx.x; k < n; k += blockDim.x) q[k] = fma(t.scale, w[k], q[k]);
   }
   __syncthreads();  // q of this row is complete (written by this CTA)
-  cg_step_body(a, red, s_last);
+  cg_step_body<T, 0>(a, red, s_last);
 }
 
 // Second half of an iteration with the dense preconditioner: given z = r @ Pinv, rz' = sum z*r (:157-style),
@@ -355,7 +412,13 @@ template <typename T>
 static int launch_step(cggp_ctx* ctx, const StepArgs<T>& a) {
   {
     ProfScope prof(ctx, 2);
-    cg_step_kernel<T><<<a.B, 512, 0, ctx->stream>>>(a);
+    // plain iteration with the Eye preconditioner and a row that fits the registers of one CTA: single-pass form
+    const bool regs = a.mode == MODE_STEP && !a.defer && a.num_blocks == 0 && a.n <= 8 * 512;
+    if (regs && a.n <= 512) cg_step_kernel<T, 1><<<a.B, 512, 0, ctx->stream>>>(a);
+    else if (regs && a.n <= 1024) cg_step_kernel<T, 2><<<a.B, 512, 0, ctx->stream>>>(a);
+    else if (regs && a.n <= 2048) cg_step_kernel<T, 4><<<a.B, 512, 0, ctx->stream>>>(a);
+    else if (regs) cg_step_kernel<T, 8><<<a.B, 512, 0, ctx->stream>>>(a);
+    else cg_step_kernel<T, 0><<<a.B, 512, 0, ctx->stream>>>(a);
     CGGP_LAUNCH_CHECK(ctx);
   }
   if (a.defer && a.mode != MODE_PRE) {

@@ -212,12 +212,12 @@ extern "C" int cggp_kuf_gram(cggp_ctx* ctx, int dtype, int kind, double variance
   const size_t es = dtype == CGGP_F64 ? 8 : 4;
   if (!accumulate) CGGP_CUDA(ctx, cudaMemset2DAsync(G, (size_t)ldg * es, 0, (size_t)m * es, (size_t)m, ctx->stream));
   if (n <= 0) return CGGP_OK;
-  // rows per chunk: 64 MB of Kuf, but never fewer than 2048 rows - the rank-k update then runs 64 k-tiles per output
-  // tile and the GEMM's prologue / epilogue is amortised (M = 16384: 268 MB chunks; measured with 512-row chunks:
-  // 23.6 TFLOP/s executed, profiles/r02_c4_predict_g8.json)
+  // rows per chunk: 64 MB of Kuf, but never fewer than 4096 rows - the rank-k update then runs 128 k-tiles per output
+  // tile and the GEMM's prologue / epilogue is amortised (M = 16384, executed TFLOP/s with 512 / 2048 / 4096-row chunks:
+  // 23.6 / 25.7 / 28.9, gpurun_out/r2_gram10.log; 537 MB of scratch at that size)
   static const int64_t nc_env = getenv("CGGP_GRAM_ROWS") ? atoll(getenv("CGGP_GRAM_ROWS")) : 0;  // tuning knob
   int64_t nc = (int64_t)((size_t)(1u << 26) / ((size_t)m * es));
-  nc = nc < 2048 ? 2048 : nc;
+  nc = nc < 4096 ? 4096 : nc;
   if (nc_env > 0) nc = nc_env;
   nc = (nc + 31) / 32 * 32;
   if (nc > n) nc = (n + 1) / 2 * 2;
