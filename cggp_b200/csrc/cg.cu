@@ -413,11 +413,14 @@ static int launch_step(cggp_ctx* ctx, const StepArgs<T>& a) {
   {
     ProfScope prof(ctx, 2);
     // plain iteration with the Eye preconditioner and a row that fits the registers of one CTA: single-pass form
+    // (256 threads up to n = 2048: two or three CTAs per SM keep more rows in flight than one CTA of 512)
     const bool regs = a.mode == MODE_STEP && !a.defer && a.num_blocks == 0 && a.n <= 8 * 512;
-    if (regs && a.n <= 512) cg_step_kernel<T, 1><<<a.B, 512, 0, ctx->stream>>>(a);
-    else if (regs && a.n <= 1024) cg_step_kernel<T, 2><<<a.B, 512, 0, ctx->stream>>>(a);
-    else if (regs && a.n <= 2048) cg_step_kernel<T, 4><<<a.B, 512, 0, ctx->stream>>>(a);
-    else if (regs) cg_step_kernel<T, 8><<<a.B, 512, 0, ctx->stream>>>(a);
+    const int threads = (regs && a.n <= 2048) ? 256 : 512;
+    const int64_t ept = (a.n + threads - 1) / threads;
+    if (regs && ept <= 1) cg_step_kernel<T, 1><<<a.B, threads, 0, ctx->stream>>>(a);
+    else if (regs && ept <= 2) cg_step_kernel<T, 2><<<a.B, threads, 0, ctx->stream>>>(a);
+    else if (regs && ept <= 4) cg_step_kernel<T, 4><<<a.B, threads, 0, ctx->stream>>>(a);
+    else if (regs) cg_step_kernel<T, 8><<<a.B, threads, 0, ctx->stream>>>(a);
     else cg_step_kernel<T, 0><<<a.B, 512, 0, ctx->stream>>>(a);
     CGGP_LAUNCH_CHECK(ctx);
   }
