@@ -1,4 +1,5 @@
 #!/bin/bash
+# needs a library built with -DCGGP_DEBUG_KNOBS (the shipped build ignores CGGP_TF32_DBG)
 # which part of the tcgen05 gram kernel binds?  (CGGP_TF32_DBG bits: 1 no epilogue math, 2 no MMAs, 4 no TMA copies,
 # 8 no global loads of the column scalars, 16 no tcgen05.ld)
 for d in ${DBGS:-0 1 2 4 7 15 23 31}; do
