@@ -630,7 +630,8 @@ def run_native(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50,
+                    help="timed CG iterations (a full preconditioned solve of c3 takes ~107; see secondary.c3_full_solve)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
