@@ -47,6 +47,15 @@ def workload_string(workload):
     return f"{workload}: N={N}, M={M}, D={D}, {kern}, B=1 right-hand side; {desc}"
 
 
+def l2_string(workload, world):
+    """Timing rule: inputs larger than L2 (identical text in both arms; it describes the GPU arm's working set)."""
+    N, M, D, _, _ = WORKLOADS[workload]
+    esize = 4 if workload in FLOAT32 else 8
+    n_local = (N + world - 1) // world
+    return ("inputs larger than L2, no flush needed: per GPU the prepared X shard %.0f MB + Kuu %.0f MB are streamed "
+            "every iteration (126 MB L2)" % (n_local * (4 * ((D + 4) // 4) + 2) * esize / 1e6, M * M * esize / 1e6))
+
+
 OPERATOR_STRING = "Kuu + jitter I + Kuf Kfu / noise_variance, matrix-free (Kfu never materialised)"
 STEP_STRING = "one CG iteration: Kuf Kfu product (+ all-reduce over ranks) + Kuu product + vector update"
 
@@ -191,10 +200,12 @@ def run_reference(args):
         "ms_per_step_full_workload_scaled": base["ms_per_step_scaled"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32" if args.workload in FLOAT32 else "f64", "data": "synthetic",
+        # `config` is identical in both arms (the driver compares them); arm-specific detail goes to `run`
         "config": {"workload": workload_string(args.workload), "operator": OPERATOR_STRING, "step": STEP_STRING,
-                   "impl_note": "restated reference (torch-CPU port of oracle/, chunked matrix-free product) on the host "
-                                "cores, bounded row sample scaled linearly to the full N; n_gpus is echoed from the "
-                                "command line; TensorFlow / GPflow are not installable in this image"},
+                   "l2": l2_string(args.workload, max(args.gpus, 1))},
+        "run": {"impl_note": "restated reference (torch-CPU port of oracle/, chunked matrix-free product) on the host "
+                             "cores, bounded row sample scaled linearly to the full N; n_gpus is echoed from the "
+                             "command line; TensorFlow / GPflow are not installable in this image"},
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "CG iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -595,15 +606,15 @@ def run_native(args):
             "metric": metric_for(args.workload), "value": its, "unit": "CG iterations/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32" if f32w else "f64", "data": "synthetic",
-            "config": {
-                "workload": workload_string(args.workload), "operator": OPERATOR_STRING, "step": STEP_STRING,
+            # `config` is identical in both arms (the driver compares them); the details of this run are in `run`
+            "config": {"workload": workload_string(args.workload), "operator": OPERATOR_STRING, "step": STEP_STRING,
+                       "l2": l2_string(args.workload, world)},
+            "run": {
                 "sharding": f"rows sharded over {world} GPU(s), {n_local} on rank 0; Z, Kuu and the CG vectors replicated",
                 "allreduce": (("fused tail kernel: rank-ordered sum over NVLink peer memory (incl. each rank's 1/W share "
                                "of p Kuu) + CG vector update in one launch" if ctx.peer_allreduce
                                else "ncclAllReduce, then the fused combine + vector-update kernel")
                               if world > 1 else "none (one rank); combine + vector update fused in one kernel"),
-                "l2": "inputs larger than L2: prepared X shard %.0f MB + Kuu %.0f MB streamed every iteration (126 MB L2)"
-                      % (n_local * (4 * ((D + 4) // 4)) * esize / 1e6, M * M * esize / 1e6),
                 "seconds_per_solve": f"{ms_max * 1e-3:.4f} s for {args.steps} iterations (threshold 0, fixed count)",
                 "f_alg_per_iteration": f_alg_iteration(N, M, D),
                 "fp64_frac_whole_iteration": (f_alg_iteration(N, M, D) * its / world / 1e12 / peak_tflops)
