@@ -586,7 +586,13 @@ static int pipe_launch(cggp_ctx* ctx, int kind, double variance, const double* P
     const bool deep = deep_env >= 0 ? deep_env != 0 : ((nb == 1 && ks <= 1) || m > 8192);
     const int et = nb == 1 ? 10 : 0;
     static const int wide_env = getenv("CGGP_PIPE_WIDE") ? atoi(getenv("CGGP_PIPE_WIDE")) : -1;  // tuning knob
-    const bool wide = wide_env >= 0 ? wide_env != 0 : m > 8192;
+    // default: the wide plan where it keeps at least as many SMs busy as 256 columns per CTA and the problem is not
+    // tiny (measured: c2, M = 2048: 37 groups of 4 CTAs = 148 SMs, 1.345 vs 1.586 ms; c4 share, M = 16384: 33.0 vs
+    // 40.6 ms; c1, M = 500: 0.062 vs 0.055 ms - stays narrow)
+    const int64_t c_narrow = (m + 255) / 256, c_wide = (m + 511) / 512;
+    const int64_t use_narrow = c_narrow <= ctx->sm_count ? (ctx->sm_count / c_narrow) * c_narrow : 0;
+    const int64_t use_wide = c_wide <= ctx->sm_count ? (ctx->sm_count / c_wide) * c_wide : 0;
+    const bool wide = wide_env >= 0 ? wide_env != 0 : (ks <= 2 && m >= 1024 && use_wide >= use_narrow);
     if (!plan_for(kind, ks, nb, deep, wide, p)) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "pipelined matvec: no plan for D=%d", D);
     CGGP_CUDA(ctx, cudaFuncSetAttribute(p.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     int occ = 0;
