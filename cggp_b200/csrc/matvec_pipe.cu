@@ -467,6 +467,12 @@ static bool plan_for_nb(int nb, bool deep, bool wide, Plan& p) {
       return true;
     }
   }
+  if constexpr (KS == 3 && KIND == CGGP_MATERN52) {  // experiment: 32 columns per warp at c3
+    if (nb == 1 && wide) {
+      p = make_plan<KIND, KS, 16, 3, 4, 1, 2, 10, 1, 1>();
+      return true;
+    }
+  }
   // one right-hand side: 1024-entry shared-memory exp table (degree-3 polynomial) + third-order sqrt step + the
   // pre-scaled accumulator pair per row; two: 32-entry shuffle table (degree 5) + two Newton steps (no room for the table)
   if (nb == 1) {
