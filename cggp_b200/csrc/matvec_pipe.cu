@@ -458,18 +458,15 @@ static Plan make_plan() {
 // to complete.  Chosen where the group is large (M = 16384: 64 CTAs to wait for) or phase 1 is cheap (D <= 3).
 template <int KIND, int KS>
 static bool plan_for_nb(int nb, bool deep, bool wide, Plan& p) {
-  // `wide` (M > 8192, D <= 7, one right-hand side): 32 columns per warp = 512 per CTA, 16-row blocks, three buffers.
-  // At M = 16384 the group shrinks from 64 to 32 CTAs: the exchange of a block gathers half as many partials of half as
-  // many rows (4 x fewer L2 loads, half the arrivals to poll for) for the same 8192 Gram entries of phase 1.
-  if constexpr (KS <= 2) {
+  // `wide` (D <= 15, one right-hand side): 32 columns per warp = 512 per CTA.  The X fragments and the cross-lane
+  // reduction of t are amortised over twice the columns, and the group halves (M = 4096: 8 CTAs, M = 16384: 32): the
+  // exchange of a block gathers half as many partials for the same number of Gram entries per block.
+  if constexpr (KS <= 4) {
     if (nb == 1 && wide) {
-      p = make_plan<KIND, KS, 16, 2, 4, 1, 3, 10, 1, 1>();
-      return true;
-    }
-  }
-  if constexpr (KS == 3 && KIND == CGGP_MATERN52) {  // experiment: 32 columns per warp at c3
-    if (nb == 1 && wide) {
-      p = make_plan<KIND, KS, 16, 3, 4, 1, 2, 10, 1, 1>();
+      // KS <= 2: 16-row blocks, three buffers (phase 1 is cheap: the exchange gets two periods); KS = 3, 4: 24-row
+      // blocks, two buffers by default (c3: 19.24 ms against 20.79 ms with 16 columns per warp)
+      if (KS <= 2 || deep) p = make_plan<KIND, KS, 16, 2, 4, 1, 3, 10, 1, 1>();
+      else p = make_plan<KIND, KS, 16, 3, 4, 1, 2, 10, 1, 1>();
       return true;
     }
   }
@@ -598,7 +595,7 @@ static int pipe_launch(cggp_ctx* ctx, int kind, double variance, const double* P
     const int64_t c_narrow = (m + 255) / 256, c_wide = (m + 511) / 512;
     const int64_t use_narrow = c_narrow <= ctx->sm_count ? (ctx->sm_count / c_narrow) * c_narrow : 0;
     const int64_t use_wide = c_wide <= ctx->sm_count ? (ctx->sm_count / c_wide) * c_wide : 0;
-    const bool wide = wide_env >= 0 ? wide_env != 0 : (ks <= 2 && m >= 1024 && use_wide >= use_narrow);
+    const bool wide = wide_env >= 0 ? wide_env != 0 : (ks <= 4 && m >= 1024 && use_wide >= use_narrow);
     if (!plan_for(kind, ks, nb, deep, wide, p)) CGGP_FAIL(ctx, CGGP_ERR_UNSUPPORTED, "pipelined matvec: no plan for D=%d", D);
     CGGP_CUDA(ctx, cudaFuncSetAttribute(p.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     int occ = 0;

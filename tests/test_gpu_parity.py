@@ -513,7 +513,9 @@ def test_fused_matvec_is_deterministic_and_linear(cb, variant):
 
 @pytest.mark.parametrize("N,M,D,name", [(300_007, 2048, 3, "se"), (150_001, 4096, 11, "matern52"),
                                        (120_000, 1500, 7, "matern32"),
-                                       (30_011, 8300, 2, "matern52")])  # M > 8192: the three-buffer ("deep") plan
+                                       (30_011, 8300, 2, "matern52"),  # M > 8192: 16-row blocks, three buffers
+                                       (50_003, 1100, 14, "se"),       # four DMMA k-steps, 32 columns per warp
+                                       (20_011, 1030, 5, "matern12")])  # ragged M just above the wide-plan threshold
 def test_fused_matvec_many_row_blocks_matches_two_sweep(cb, N, M, D, name):
     """Thousands of row blocks per CTA group (the exchange ring wraps many times), ragged last block, ragged M:
     the fused kernel against the independent two-sweep kernels, which were checked against the oracle above."""
