@@ -461,15 +461,6 @@ static bool plan_for_nb(int nb, bool deep, bool wide, Plan& p) {
   // `wide` (D <= 15, one right-hand side): 32 columns per warp = 512 per CTA.  The X fragments and the cross-lane
   // reduction of t are amortised over twice the columns, and the group halves (M = 4096: 8 CTAs, M = 16384: 32): the
   // exchange of a block gathers half as many partials for the same number of Gram entries per block.
-  if constexpr (KS == 3 && KIND == CGGP_MATERN52) {
-    // experiment (CGGP_PIPE_W12=1): 12 compute warps of 32 columns + 2 exchange warps = 14 -> 16 allocated warps,
-    // 128 registers per thread instead of 96 (more independent sqrt / exp chains per warp), 384 columns per CTA
-    static const int w12 = getenv("CGGP_PIPE_W12") ? atoi(getenv("CGGP_PIPE_W12")) : 0;
-    if (nb == 1 && wide && w12) {
-      p = make_plan<KIND, KS, 12, 4, 4, 1, 2, 10, 1, 1>();
-      return true;
-    }
-  }
   if constexpr (KS <= 4) {
     if (nb == 1 && wide) {
       // KS <= 2: 16-row blocks, three buffers (phase 1 is cheap: the exchange gets two periods); KS = 3, 4: 24-row
