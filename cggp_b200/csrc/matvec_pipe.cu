@@ -461,15 +461,6 @@ static bool plan_for_nb(int nb, bool deep, bool wide, Plan& p) {
   // `wide` (D <= 15, one right-hand side): 32 columns per warp = 512 per CTA.  The X fragments and the cross-lane
   // reduction of t are amortised over twice the columns, and the group halves (M = 4096: 8 CTAs, M = 16384: 32): the
   // exchange of a block gathers half as many partials for the same number of Gram entries per block.
-  if constexpr (KS == 1) {
-    // experiment (CGGP_PIPE_XWIDE=1): 64 columns per warp = 1024 per CTA, 8-row blocks, three buffers (M = 16384: 16-CTA
-    // groups, 9 of them = 144 SMs instead of 4 x 32 = 128)
-    static const int xw = getenv("CGGP_PIPE_XWIDE") ? atoi(getenv("CGGP_PIPE_XWIDE")) : 0;
-    if (nb == 1 && wide && xw) {
-      p = make_plan<KIND, KS, 16, 1, 8, 1, 3, 10, 1, 1>();
-      return true;
-    }
-  }
   if constexpr (KS <= 4) {
     if (nb == 1 && wide) {
       // KS <= 2: 16-row blocks, three buffers (phase 1 is cheap: the exchange gets two periods); KS = 3, 4: 24-row
