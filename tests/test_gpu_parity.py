@@ -1024,6 +1024,30 @@ def test_batched_prediction_and_metrics(cb, models_golden):
     np.testing.assert_allclose(met["test/nlpd"], -lpd.sum() / X.shape[0], rtol=1e-9)
 
 
+def test_far_apart_points_take_the_clamped_path(cb):
+    """The pipelined kernel drops the upper clamp of the kernel argument only when every squared norm on both sides is
+    below a per-family limit (pre-pass flag for X, per-CTA vote for Z).  Far-away points - squared distances up to
+    ~1e6 lengthscales^2, kernel values that underflow - must still give finite, correct products (zeros where the
+    reference's exp underflows), whichever side carries the large norms."""
+    rng = np.random.default_rng(77)
+    N, M, D = 3000, 1100, 3
+    for name in ("se", "matern52"):
+        for far in ("x", "z", "none"):
+            X, Z = rng.standard_normal((N, D)), rng.standard_normal((M, D))
+            if far == "x":
+                X[::7] += 600.0
+            if far == "z":
+                Z[5::11] -= 900.0
+            V = rng.standard_normal((1, M))
+            ok = g.KERNELS[name](variance=1.0, lengthscales=np.ones(D))
+            k = cb.kernels.KERNELS[name](variance=1.0, lengthscales=np.ones(D))
+            op = cb.SGPROperator(k, dev(X), dev(Z), 0.1, variant=3)
+            W = cpu(op.kuf_kfu_matmul(dev(V)))
+            ref = om.kuf_kfu_matmul(ok, X, Z, V, chunk=512)
+            assert np.isfinite(W).all()
+            np.testing.assert_allclose(W, ref, rtol=1e-11, atol=1e-12 * np.abs(ref).max())
+
+
 def test_fused_predict_f_and_elbo_entry_points(cb):
     """cggp_predict_f / cggp_elbo_terms (the model chains of cggp/models.py:333-352 and :131-133 as single C calls,
     used when no gradient is wanted) against the step-by-step differentiable path and the oracle."""
