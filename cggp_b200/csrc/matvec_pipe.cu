@@ -665,6 +665,8 @@ static int pipe_launch(cggp_ctx* ctx, int kind, double variance, const double* P
     if (p.dup) {
       rc = dup_scaled_norms(ctx, kind, nX, n, active, &a.xa2, &a.xbig);
       if (rc) return rc;
+      static const int clamp_env = getenv("CGGP_PIPE_CLAMP") ? atoi(getenv("CGGP_PIPE_CLAMP")) : 0;  // tuning knob
+      if (clamp_env) a.xbig = nullptr;  // always take the clamped tile loop
     }
     a.etab = nullptr;
     if (et == 10) {
