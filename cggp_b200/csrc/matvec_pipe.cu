@@ -26,7 +26,6 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
-#include <type_traits>
 
 #include "pipe_common.cuh"
 
@@ -69,7 +68,6 @@ struct Args {
   const int* active;
   const int2* etab;  // exp table of the shared-memory variant (ET = 10: 1024 entries)
   const double2* xa2;  // DUP: (alpha |x_i|^2, alpha |x_i|^2) per row - the initial DMMA accumulator pair, one LDS.128
-  const int* xbig;     // DUP: non-zero when some |x_i|^2 reaches Fam<KIND>::norm_limit (set by the pre-pass), or nullptr
 };
 
 template <int WARPS, int RB, int CBW, int NB, int KS, int NBUF, int ET, int DUP = 0>
@@ -170,7 +168,7 @@ __global__ void __launch_bounds__(WARPS * 32 + 64, 1) kfu_pipe_kernel(const Args
     static_assert(XS == 2, "exchange warp w refills X stage w");
     stage_tile(ew);
     __threadfence_block();
-    __syncthreads_or(0);  // (S) first tiles staged (manual ones visible); the compute warps vote on their Z norms
+    __syncthreads();  // (S) first tiles staged (manual ones visible)
     double* slots_g = a.part + (int64_t)g * SLOTS * a.C * (BM * NB);
     for (int64_t it = ew; it < nit; it += 2) {
       const int par = (int)(it % NBUF);
@@ -254,7 +252,6 @@ __global__ void __launch_bounds__(WARPS * 32 + 64, 1) kfu_pipe_kernel(const Args
   // =============================== compute warps ===============================
   const int lr = lane >> 2, lk = lane & 3;
   const int64_t col0 = (int64_t)rank * BN + warp * WN;  // first column of this warp
-  int zbig = 0;  // some |z_j|^2 of this CTA's columns reaches the limit below which the upper clamp may be dropped
   // per-warp constants held in registers for the whole kernel: Z fragments, v entries, w accumulators
   double bf[CBW][KS];
   double2 vv[CBW][NB];
@@ -267,10 +264,7 @@ __global__ void __launch_bounds__(WARPS * 32 + 64, 1) kfu_pipe_kernel(const Args
       double val = 0.0;
       if (zc < a.m) {
         if (k < a.D) val = Fam<KIND>::beta * a.PZ[zc * a.ldp + k];
-        else if (k == a.D) {
-          val = Fam<KIND>::alpha * a.nZ[zc];
-          zbig |= !(a.nZ[zc] < Fam<KIND>::norm_limit);
-        }
+        else if (k == a.D) val = Fam<KIND>::alpha * a.nZ[zc];
       }
       bf[cb][ks] = val;
     }
@@ -312,14 +306,11 @@ __global__ void __launch_bounds__(WARPS * 32 + 64, 1) kfu_pipe_kernel(const Args
     }
   };
 
-  const int cta_zbig = __syncthreads_or(zbig);  // (S)
-  // CTA-uniform: every squared norm on both sides is small enough for kval<..., NC = 1> (identical results; the
-  // choice may differ between the CTAs of a group)
-  const bool noclamp = DUP && a.xbig != nullptr && !cta_zbig && *a.xbig == 0;
-  // phase 1 of block `it`, instantiated with and without the upper clamp of the kernel argument
-  auto phase1 = [&](auto nc_tag, int64_t it) {
-    constexpr int NC = decltype(nc_tag)::value;
+  __syncthreads();  // (S)
+  for (int64_t it = 0; it < nit; ++it) {
+    // ------------------------------- phase 1 of block `it` -------------------------------
     const int s = (int)(it % XS), par = (int)(it % NBUF);
+    mbar_wait(&mbar[s], (unsigned)((it / XS) & 1));  // X tile (TMA or guarded loads) has landed
     const double* xs = xt + s * BM * LDX + lr * LDX + lk;
     const double* xns = xn + (s * BM + lr) * XNW;
     double2* kb = kbuf + (size_t)par * RB * CBW * THREADS + tid;
@@ -349,8 +340,8 @@ __global__ void __launch_bounds__(WARPS * 32 + 64, 1) kfu_pipe_kernel(const Args
       for (int b = 0; b < NB; ++b) tp[b] = 0.0;
 #pragma unroll
       for (int cb = 0; cb < CBW; ++cb) {
-        const double k0 = kval<KIND, ET, SQ, NC>(c[cb][0], tab, etab);
-        const double k1 = kval<KIND, ET, SQ, NC>(c[cb][1], tab, etab);
+        const double k0 = kval<KIND, ET, SQ>(c[cb][0], tab, etab);
+        const double k1 = kval<KIND, ET, SQ>(c[cb][1], tab, etab);
         kb[(rb * CBW + cb) * THREADS] = make_double2(k0, k1);
 #pragma unroll
         for (int b = 0; b < NB; ++b) tp[b] = fma(k0, vv[cb][b].x, fma(k1, vv[cb][b].y, tp[b]));
@@ -363,17 +354,6 @@ __global__ void __launch_bounds__(WARPS * 32 + 64, 1) kfu_pipe_kernel(const Args
         v += __shfl_xor_sync(0xffffffffu, v, 2);
         if (lk == 0) tr[(rb * 8 + lr) * NB + b] = v;
       }
-    }
-  };
-  for (int64_t it = 0; it < nit; ++it) {
-    // ------------------------------- phase 1 of block `it` -------------------------------
-    const int s = (int)(it % XS), par = (int)(it % NBUF);
-    mbar_wait(&mbar[s], (unsigned)((it / XS) & 1));  // X tile (TMA or guarded loads) has landed
-    if constexpr (DUP) {
-      if (noclamp) phase1(std::integral_constant<int, 1>{}, it);
-      else phase1(std::integral_constant<int, 0>{}, it);
-    } else {
-      phase1(std::integral_constant<int, 0>{}, it);
     }
     __threadfence_block();
     bar_arrive(BAR_T + par, ALL);  // hand the partials (and the X stage) to the exchange warp; do not wait
@@ -413,27 +393,20 @@ __global__ void reduce_groups_kernel(const double* __restrict__ Wp, int G, int N
 }  // namespace kpipe
 
 // (alpha |x_i|^2, alpha |x_i|^2): the initial DMMA accumulator pair of row i, read by the kernels with one LDS.128.
-__global__ void scale_dup_kernel(const double* __restrict__ nX, int64_t n, double alpha, double limit,
-                                 double2* __restrict__ out, int* __restrict__ big) {
+__global__ void scale_dup_kernel(const double* __restrict__ nX, int64_t n, double alpha, double2* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    const double x = nX[i];
-    const double v = alpha * x;
+    const double v = alpha * nX[i];
     out[i] = make_double2(v, v);
-    if (!(x < limit)) *big = 1;  // also NaN; every writer stores the same value
   }
 }
 // Built per launch, or once per cggp_cg_solve (the operator's points cannot change inside a solve: the buffer is
 // keyed on pointer, row count, family and the solve epoch).
 int kpipe::dup_scaled_norms(cggp_ctx* ctx, int kind, const double* nX, int64_t n, const int* active,
-                            const double2** out, const int** big_flag) {
+                            const double2** out) {
   const double alpha = kind == CGGP_SE ? Fam<CGGP_SE>::alpha : kind == CGGP_MATERN12 ? Fam<CGGP_MATERN12>::alpha
                        : kind == CGGP_MATERN32 ? Fam<CGGP_MATERN32>::alpha : Fam<CGGP_MATERN52>::alpha;
-  const double limit = kind == CGGP_SE ? Fam<CGGP_SE>::norm_limit : kind == CGGP_MATERN12 ? Fam<CGGP_MATERN12>::norm_limit
-                       : kind == CGGP_MATERN32 ? Fam<CGGP_MATERN32>::norm_limit : Fam<CGGP_MATERN52>::norm_limit;
-  // the buffer ends with one int: "some squared norm reaches the limit" (written by the pre-pass)
-  const size_t flag_off = (sizeof(double2) * (size_t)(n > 0 ? n : 1) + 15) / 16 * 16;
-  const size_t need = flag_off + 16;
+  const size_t need = sizeof(double2) * (size_t)(n > 0 ? n : 1);
   const bool hit = ctx->solve_epoch > 0 && ctx->xa2_epoch == ctx->solve_epoch && ctx->xa2_key == (const void*)nX &&
                    ctx->xa2_n == n && ctx->xa2_alpha == alpha && ctx->xa2;
   if (!hit) {
@@ -446,11 +419,8 @@ int kpipe::dup_scaled_norms(cggp_ctx* ctx, int kind, const double* nX, int64_t n
       ctx->xa2_bytes = need + need / 8;
     }
     (void)active;  // built unconditionally: a later launch of the same solve may reuse it
-    int* big = (int*)((char*)ctx->xa2 + flag_off);
-    CGGP_CUDA(ctx, cudaMemsetAsync(big, 0, sizeof(int), ctx->stream));
     if (n > 0) {
-      scale_dup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(nX, n, alpha, limit, (double2*)ctx->xa2,
-                                                                             big);
+      scale_dup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(nX, n, alpha, (double2*)ctx->xa2);
       CGGP_LAUNCH_CHECK(ctx);
     }
     ctx->xa2_key = nX;
@@ -459,7 +429,6 @@ int kpipe::dup_scaled_norms(cggp_ctx* ctx, int kind, const double* nX, int64_t n
     ctx->xa2_epoch = ctx->solve_epoch;
   }
   *out = (const double2*)ctx->xa2;
-  if (big_flag) *big_flag = (const int*)((const char*)ctx->xa2 + flag_off);
   return CGGP_OK;
 }
 
@@ -661,12 +630,9 @@ static int pipe_launch(cggp_ctx* ctx, int kind, double variance, const double* P
     a.dbg = 0;
 #endif
     a.xa2 = nullptr;
-    a.xbig = nullptr;
     if (p.dup) {
-      rc = dup_scaled_norms(ctx, kind, nX, n, active, &a.xa2, &a.xbig);
+      rc = dup_scaled_norms(ctx, kind, nX, n, active, &a.xa2);
       if (rc) return rc;
-      static const int clamp_env = getenv("CGGP_PIPE_CLAMP") ? atoi(getenv("CGGP_PIPE_CLAMP")) : 0;  // tuning knob
-      if (clamp_env) a.xbig = nullptr;  // always take the clamped tile loop
     }
     a.etab = nullptr;
     if (et == 10) {

@@ -53,28 +53,24 @@ struct Fam;
 template <>
 struct Fam<CGGP_SE> {  // K = exp(-r2 / 2): the DMMA delivers the exponent itself
   static constexpr double alpha = -0.5, beta = 1.0;
-  static constexpr double norm_limit = 350.0;  // r2 <= 2 (|x|^2 + |z|^2) < 1400 < 2 * 708
 };
 template <>
 struct Fam<CGGP_MATERN12> {  // a = r
   static constexpr double alpha = 1.0, beta = -2.0;
   static constexpr double clampv = 1e-36;
   static constexpr int clamp_hi = 0x38754484;
-  static constexpr double norm_limit = 1.2e5;  // alpha r2 <= 2 alpha (|x|^2 + |z|^2) < 4.8e5 < 708^2 = 5.01e5
 };
 template <>
 struct Fam<CGGP_MATERN32> {  // a = sqrt(3) r
   static constexpr double alpha = 3.0, beta = -6.0;
   static constexpr double clampv = 3e-36;
   static constexpr int clamp_hi = 0x388fe6c6;
-  static constexpr double norm_limit = 4.0e4;
 };
 template <>
 struct Fam<CGGP_MATERN52> {  // a = sqrt(5) r
   static constexpr double alpha = 5.0, beta = -10.0;
   static constexpr double clampv = 5e-36;
   static constexpr int clamp_hi = 0x389a95a5;
-  static constexpr double norm_limit = 2.4e4;
 };
 
 // Unit-variance kernel value from the scaled argument q.  FP64-pipe instructions: SE 9, Matern-1/2 14, 3/2 16,
@@ -83,41 +79,25 @@ struct Fam<CGGP_MATERN52> {  // a = sqrt(5) r
 //           q below GPflow's max(r2, 1e-36) land on the lower clamp, q beyond (708 lengthscales)^2 on the upper one
 //           (exp(-708) = 3e-308 instead of an underflowed 0: absolute error 3e-308);
 //   SE:     hi(q) -> min with hi(-708) as UNSIGNED ints (more negative = larger).
-// NC = 1: the caller has established that no pair of this launch reaches the upper end of the range (every squared
-// norm of both point sets is below Fam<KIND>::norm_limit, so q = alpha |x - z|^2 <= 2 alpha (|x|^2 + |z|^2) stays
-// below 708^2, resp. the SE exponent above -708): the upper clamp is dropped, one integer instruction less per entry.
-template <int KIND, int ET, int SQ = 0, int NC = 0>
+template <int KIND, int ET, int SQ = 0>
 __device__ __forceinline__ double kval(double q, const FastExpTable& tab, const int2* etab) {
   if constexpr (KIND == CGGP_SE) {
-    double x = q;
-    if constexpr (NC == 0) {
-      const unsigned h = min((unsigned)__double2hiint(q), 0xC0862000u);
-      x = __hiloint2double((int)h, __double2loint(q));
-    }
+    const unsigned h = min((unsigned)__double2hiint(q), 0xC0862000u);
+    const double x = __hiloint2double((int)h, __double2loint(q));
     if constexpr (ET == 0) return fast_exp_core(x, tab);
     else return fast_exp_core_smem<ET>(x, etab);
   } else {
     // in place on the register pair (the compiler otherwise copies the low word to a fresh pair)
     double qc = q;
-    if constexpr (NC == 1)  // lower clamp only
-      asm("{\n"
-          ".reg .b32 lo, hi;\n"
-          "mov.b64 {lo, hi}, %0;\n"
-          "max.s32 hi, hi, %1;\n"
-          "mov.b64 %0, {lo, hi};\n"
-          "}\n"
-          : "+d"(qc)
-          : "n"(Fam<KIND>::clamp_hi));
-    else
-      asm("{\n"
-          ".reg .b32 lo, hi;\n"
-          "mov.b64 {lo, hi}, %0;\n"
-          "max.s32 hi, hi, %1;\n"
-          "min.s32 hi, hi, 0x411e9840;\n"
-          "mov.b64 %0, {lo, hi};\n"
-          "}\n"
-          : "+d"(qc)
-          : "n"(Fam<KIND>::clamp_hi));
+    asm("{\n"
+        ".reg .b32 lo, hi;\n"
+        "mov.b64 {lo, hi}, %0;\n"
+        "max.s32 hi, hi, %1;\n"
+        "min.s32 hi, hi, 0x411e9840;\n"
+        "mov.b64 %0, {lo, hi};\n"
+        "}\n"
+        : "+d"(qc)
+        : "n"(Fam<KIND>::clamp_hi));
     const double a = SQ == 1 ? fast_sqrt_pos_cubic(qc) : fast_sqrt_pos_lean(qc);
     double e;
     if constexpr (ET == 0) e = fast_exp_neg_core(a, tab);
@@ -149,8 +129,6 @@ __device__ __forceinline__ void mbar_arrive(void* bar) {
 // 2^(j / 1024), j < 1024 (biased high words, kmath.cuh), built once per ctx on the host (matvec_pipe.cu)
 int exp_table_device(cggp_ctx* ctx, const int2** out);
 // (alpha |x_i|^2, alpha |x_i|^2) per row in a ctx-owned buffer (matvec_pipe.cu)
-// `big_flag` (may be nullptr): receives a device int that is non-zero when some |x_i|^2 reaches Fam<kind>::norm_limit
-int dup_scaled_norms(cggp_ctx* ctx, int kind, const double* nX, int64_t n, const int* active, const double2** out,
-                     const int** big_flag = nullptr);
+int dup_scaled_norms(cggp_ctx* ctx, int kind, const double* nX, int64_t n, const int* active, const double2** out);
 
 }  // namespace kpipe

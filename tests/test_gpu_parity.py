@@ -1024,10 +1024,9 @@ def test_batched_prediction_and_metrics(cb, models_golden):
     np.testing.assert_allclose(met["test/nlpd"], -lpd.sum() / X.shape[0], rtol=1e-9)
 
 
-def test_far_apart_points_take_the_clamped_path(cb):
-    """The pipelined kernel drops the upper clamp of the kernel argument only when every squared norm on both sides is
-    below a per-family limit (pre-pass flag for X, per-CTA vote for Z).  Far-away points - squared distances up to
-    ~1e6 lengthscales^2, kernel values that underflow - must still give finite, correct products (zeros where the
+def test_far_apart_points_stay_finite(cb):
+    """The range clamps of the kernel argument in the pipelined kernels: far-away points - squared distances up to
+    ~1e6 lengthscales^2, kernel values that underflow - must give finite, correct products (zeros where the
     reference's exp underflows), whichever side carries the large norms."""
     rng = np.random.default_rng(77)
     N, M, D = 3000, 1100, 3
