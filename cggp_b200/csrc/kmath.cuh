@@ -284,6 +284,73 @@ __device__ __forceinline__ double fast_exp_neg_core_smem(double a, const int2* t
   return __hiloint2double(e.y + (n << (20 - TBITS)), e.x) * q;
 }
 
+// sqrt + exp(-sqrt) of the Matern family in one routine with the range reduction started EARLY: the table index n and
+// nf = round(a 2^TBITS / ln 2) are taken from the seed-accurate g = u y (relative error 2^-22.9, i.e. < 0.01 table
+// steps for a < 50) while the third-order sqrt step still runs, so the table load and two FP64 instructions leave the
+// dependent chain sqrt -> reduction -> polynomial.  d = -a - nf STEP is formed from the FINAL a: the only effect of
+// the approximate n is |d| <= 0.51 STEP instead of 0.5 (polynomial error x 1.1).  Same instruction count.
+// MPOLY: 0 = exp(-a) alone (Matern-1/2), 1 = (1 + a) exp(-a) (3/2), 2 = (1 + a + u / 3) exp(-a) (5/2, u = a^2).  The
+// Matern polynomial is multiplied into the TABLE value while the exp polynomial is still being evaluated, so the
+// result is one multiply after the last Horner step.
+template <int TBITS, int MPOLY>
+__device__ __forceinline__ double fast_matern_early(double u, const int2* tab) {
+  double y;
+  asm("{\n"
+      ".reg .b32 ulo, uhi, yhi;\n"
+      ".reg .f64 yy;\n"
+      "rsqrt.approx.ftz.f64 yy, %1;\n"
+      "mov.b64 {ulo, yhi}, yy;\n"
+      "mov.b64 {ulo, uhi}, %1;\n"
+      "mov.b64 %0, {ulo, yhi};\n"
+      "}\n"
+      : "=d"(y)
+      : "d"(u));
+  const double MAGIC = 6755399441055744.0;
+  const double g = u * y;
+  const double t = fma(g, -ExpSmemConst<TBITS>::SCALE, MAGIC);
+  const int n = __double2loint(t);
+  const double nf = t - MAGIC;
+  const int2 e = tab[n & ((1 << TBITS) - 1)];
+  const double r = fma(-g, y, 1.0);
+  const double p = fma(r, 0.375, 0.5);
+  const double gr = g * r;
+  const double a = fma(gr, p, g);
+  const double d = fma(nf, -ExpSmemConst<TBITS>::STEP, -a);
+  double tv = __hiloint2double(e.y + (n << (20 - TBITS)), e.x);
+  if constexpr (MPOLY == 1) tv *= 1.0 + a;
+  if constexpr (MPOLY == 2) tv *= fma(u, 1.0 / 3.0, 1.0 + a);
+  return tv * ExpSmemConst<TBITS>::poly(d);
+}
+
+template <int TBITS>
+__device__ __forceinline__ double fast_sqrt_exp_neg_early(double u, const int2* tab, double& a_out) {
+  double y;
+  asm("{\n"
+      ".reg .b32 ulo, uhi, yhi;\n"
+      ".reg .f64 yy;\n"
+      "rsqrt.approx.ftz.f64 yy, %1;\n"
+      "mov.b64 {ulo, yhi}, yy;\n"
+      "mov.b64 {ulo, uhi}, %1;\n"
+      "mov.b64 %0, {ulo, yhi};\n"
+      "}\n"
+      : "=d"(y)
+      : "d"(u));
+  const double MAGIC = 6755399441055744.0;
+  const double g = u * y;
+  const double t = fma(g, -ExpSmemConst<TBITS>::SCALE, MAGIC);
+  const int n = __double2loint(t);
+  const double nf = t - MAGIC;
+  const int2 e = tab[n & ((1 << TBITS) - 1)];
+  const double r = fma(-g, y, 1.0);
+  const double p = fma(r, 0.375, 0.5);
+  const double gr = g * r;
+  const double a = fma(gr, p, g);
+  a_out = a;
+  const double d = fma(nf, -ExpSmemConst<TBITS>::STEP, -a);
+  const double q = ExpSmemConst<TBITS>::poly(d);
+  return __hiloint2double(e.y + (n << (20 - TBITS)), e.x) * q;
+}
+
 // Fast kernel value on r2 (variance is applied by the caller once per row, not per entry).
 template <int KIND>
 __device__ __forceinline__ double kernel_value_fast_unit(double r2, const FastExpTable& tab) {

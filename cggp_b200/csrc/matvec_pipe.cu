@@ -465,18 +465,18 @@ static bool plan_for_nb(int nb, bool deep, bool wide, Plan& p) {
     if (nb == 1 && wide) {
       // KS <= 2: 16-row blocks, three buffers (phase 1 is cheap: the exchange gets two periods); KS = 3, 4: 24-row
       // blocks, two buffers by default (c3: 19.24 ms against 20.79 ms with 16 columns per warp)
-      if (KS <= 2 || deep) p = make_plan<KIND, KS, 16, 2, 4, 1, 3, 10, 1, 1>();
-      else p = make_plan<KIND, KS, 16, 3, 4, 1, 2, 10, 1, 1>();
+      if (KS <= 2 || deep) p = make_plan<KIND, KS, 16, 2, 4, 1, 3, 10, 3, 1>();
+      else p = make_plan<KIND, KS, 16, 3, 4, 1, 2, 10, 3, 1>();
       return true;
     }
   }
   // one right-hand side: 1024-entry shared-memory exp table (degree-3 polynomial) + third-order sqrt step + the
-  // pre-scaled accumulator pair per row; two: 32-entry shuffle table (degree 5) + two Newton steps (no room for the table)
+  // pre-scaled accumulator pair per row + early range reduction (kmath.cuh fast_matern_early); two: 32-entry shuffle table (degree 5) + two Newton steps (no room for the table)
   if (nb == 1) {
     if constexpr (KS <= 4)
-      p = deep ? make_plan<KIND, KS, 16, 4, 2, 1, 3, 10, 1, 1>() : make_plan<KIND, KS, 16, 6, 2, 1, 2, 10, 1, 1>();
+      p = deep ? make_plan<KIND, KS, 16, 4, 2, 1, 3, 10, 3, 1>() : make_plan<KIND, KS, 16, 6, 2, 1, 2, 10, 3, 1>();
     else  // wider X tiles: smaller row blocks keep the kernel inside the 227 KB of shared memory
-      p = deep ? make_plan<KIND, KS, 16, 3, 2, 1, 3, 10, 1, 1>() : make_plan<KIND, KS, 16, 5, 2, 1, 2, 10, 1, 1>();
+      p = deep ? make_plan<KIND, KS, 16, 3, 2, 1, 3, 10, 3, 1>() : make_plan<KIND, KS, 16, 5, 2, 1, 2, 10, 3, 1>();
     return true;
   }
   if constexpr (KS <= 4) {  // 16 <= D <= 31: two and more right-hand sides go through the 8-wide kernel (matvec_pipe8.cu)

@@ -316,8 +316,8 @@ __global__ void __launch_bounds__((WARPS + EWARPS) * 32, 1) kfu_pipe8_kernel(con
       double t0 = 0.0, t1 = 0.0;  // t[row lr][b = 2 lk, 2 lk + 1] over this warp's 16 columns
 #pragma unroll
       for (int cb = 0; cb < CBW; ++cb) {
-        const double k0 = kval<KIND, 10, 1>(c[cb][0], tab, etab);
-        const double k1 = kval<KIND, 10, 1>(c[cb][1], tab, etab);
+        const double k0 = kval<KIND, 10, 3>(c[cb][0], tab, etab);
+        const double k1 = kval<KIND, 10, 3>(c[cb][1], tab, etab);
         *reinterpret_cast<double2*>(kb + (rb * CBW + cb) * 64 + lr * 8 + 2 * lk) = make_double2(k0, k1);
         dmma884(t0, t1, k0, ve[cb]);  // k index lk <-> column 2 lk
         dmma884(t0, t1, k1, vo[cb]);  //                   column 2 lk + 1
