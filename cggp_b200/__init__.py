@@ -1,8 +1,9 @@
 """cggp_b200: B200-native (sm_100a) implementation of the conjugate-gradient hot path of
 awav/conjugate-gradient-sparse-gp (CDGP / SGPR models).  Module names mirror the reference's
-(``conjugate_gradient``, ``models``, ``distance``, ``utils``, ``selection``); compute goes through the C ABI
+(``conjugate_gradient``, ``models``, ``distance``, ``utils``, ``selection``, ``covertree``); compute goes through the C ABI
 ``libcggp_b200.so`` (include/cggp_b200.h).  Importing the package does not need a GPU; using it does."""
 from . import _lib, selection, sharding  # noqa: F401
+from .covertree import CoverTree, covertree_update_inducing_parameters  # noqa: F401
 from .conjugate_gradient import (BlockPreconditioner, CGPreconditioner, ConjugateGradient,  # noqa: F401
                                  DensePreconditioner, EyePreconditioner, conjugate_gradient)
 from .distance import create_distance_fn, euclid_distance  # noqa: F401

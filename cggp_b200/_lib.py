@@ -109,6 +109,14 @@ SIGNATURES = {
                             _vp, _vp, _vp, _vp, C.POINTER(C.c_int32)]),
     "cggp_elbo_terms": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _d, _vp]),
     "cggp_microbench": (_i, [_vp, _i, _i, C.POINTER(_d)]),
+    "cggp_covertree_build": (_i, [_vp, _i, _vp, _i64, _i, _i64, _d, _i, _i, _i, C.POINTER(_vp)]),
+    "cggp_covertree_destroy": (_i, [_vp]),
+    "cggp_covertree_num_levels": (_i, [_vp]),
+    "cggp_covertree_level_size": (_i64, [_vp, _i]),
+    "cggp_covertree_level_radius": (_i, [_vp, _i, C.POINTER(_d)]),
+    "cggp_covertree_level_points": (_i, [_vp, _vp, _i, _vp, _i64, C.POINTER(C.c_int32)]),
+    "cggp_covertree_leaf_members": (_i, [_vp, _vp, _vp, _vp]),
+    "cggp_covertree_cluster_stats": (_i, [_vp, _vp, _i, _vp, _i64, _vp, _vp]),
 }
 
 _lib = None

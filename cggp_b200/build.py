@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcggp_b200.so")
-SOURCES = ["api.cu", "points.cu", "dense.cu", "matvec_simple.cu", "matvec_pipe.cu", "matvec_pipe8.cu", "matvec_tf32.cu", "cg.cu", "model.cu"]
+SOURCES = ["api.cu", "points.cu", "dense.cu", "matvec_simple.cu", "matvec_pipe.cu", "matvec_pipe8.cu", "matvec_tf32.cu", "cg.cu", "model.cu", "covertree.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -317,6 +317,34 @@ int cggp_elbo_terms(cggp_ctx* ctx, int dtype, const void* dev_y, const void* dev
                     double noise_variance, void* dev_out);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Cover-tree inducing-point selection - cggp/covertree.py:25-176 (class CoverTree), called by
+ * cggp/optimize.py:19-39 (covertree_update_inducing_parameters).  Same results as the reference on the same rows:
+ * its greedy order of operations and NumPy's orders of summation are reproduced (csrc/covertree.cu).
+ *
+ * build: dev_X [n, D] float64 rows (ldx elements apart).  spatial_resolution > 0 selects the number of levels as the
+ * reference does (covertree.py:53-55), otherwise num_levels is used; lloyds / voronoi are the reference's switches
+ * (its `distance` argument is ignored there, covertree.py:36-45, and has no counterpart here; `plotting` neither).
+ * The call synchronises the ctx stream (the tree structure lives on the host); the handle owns device copies of the
+ * leaf memberships and must be released with cggp_covertree_destroy.
+ *   level_points  <-> [node.point for node in tree.levels[level]]  (-> `centroids` for the last level); host_parent
+ *                     (may be NULL) receives each node's parent index in the previous level
+ *   leaf_members  <-> node.data of the last level as row numbers: dev_offsets [m + 1], dev_rows [n]
+ *   cluster_stats <-> cluster_mean_and_counts (covertree.py:168-176): np.mean(node.data[1]) (nan for an empty leaf)
+ *                     and the count per leaf, both as floating point [m]; dev_y [n] targets, ldy elements apart */
+typedef struct cggp_covertree cggp_covertree;
+int cggp_covertree_build(cggp_ctx* ctx, int dtype, const void* dev_X, int64_t n, int D, int64_t ldx,
+                         double spatial_resolution, int num_levels, int lloyds, int voronoi, cggp_covertree** out);
+int cggp_covertree_destroy(cggp_covertree* tree);
+int cggp_covertree_num_levels(const cggp_covertree* tree);
+int64_t cggp_covertree_level_size(const cggp_covertree* tree, int level);
+int cggp_covertree_level_radius(const cggp_covertree* tree, int level, double* host_radius);
+int cggp_covertree_level_points(cggp_ctx* ctx, const cggp_covertree* tree, int level, void* dev_out, int64_t ldo,
+                                int32_t* host_parent);
+int cggp_covertree_leaf_members(cggp_ctx* ctx, const cggp_covertree* tree, int64_t* dev_offsets, int64_t* dev_rows);
+int cggp_covertree_cluster_stats(cggp_ctx* ctx, const cggp_covertree* tree, int dtype, const void* dev_y, int64_t ldy,
+                                 void* dev_means, void* dev_counts);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Micro-benchmarks for the roofline denominators that MEASURED_PEAKS.json lacks:
  * which: 0 = FP64 DFMA, 1 = FP64 DMMA m8n8k4, 2 = FP64 exp with the 32-entry shuffle table (two-RHS kernels),
  *        3 = FP64 sqrt (rsqrt seed + two Newton steps), 4 = DMMA m16n8k4, 5 = the exp of the pipelined kernels
