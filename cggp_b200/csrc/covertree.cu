@@ -23,10 +23,13 @@
 //
 // Entry points: cggp_covertree_build / _num_levels / _level_size / _level_radius / _level_points / _leaf_members /
 // _cluster_stats / _destroy (include/cggp_b200.h).
+#include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -149,18 +152,37 @@ struct PassSmem {
   int total;
 };
 
-__device__ int64_t list_pass(const double* __restrict__ X, int64_t ldx, int D, int* list, int64_t n, const double* point,
-                             double radius, int* sel_out, bool compact, PassSmem& s) {
+// Entries [lo, hi) of `src`: the kept (un-flagged) ones go to dst[kept_base ...], the flagged ones to
+// sel_out[sel_base ...], both in list order.  dst == src with kept_base <= lo is a stable in-place compaction (every
+// chunk is read completely before it is written, and writes never pass the read position).  COH: the lists are written
+// by other CTAs of the cluster - read them through L2.  Returns the number of KEPT entries (same in every thread).
+template <bool COH>
+__device__ int64_t slice_pass(const double* __restrict__ X, int64_t ldx, int D, const int* src, int* dst, int64_t lo,
+                              int64_t hi, int64_t kept_base, int64_t sel_base, const double* point, double radius,
+                              int* sel_out, bool count_only, PassSmem& s) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   int64_t kept_total = 0;
-  for (int64_t base = 0; base < n; base += CHUNK) {
+  int wcount = 0;
+  // the entries of the NEXT chunk are fetched before the rows of this one are gathered: one memory latency per chunk
+  // instead of two (in place this is safe: a chunk's writes never reach the positions of the next chunk)
+  int nxt[ITEMS];
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int64_t i = lo + j * T + tid;
+    nxt[j] = i < hi ? (COH ? __ldcg(src + i) : src[i]) : 0;
+  }
+  for (int64_t base = lo; base < hi; base += CHUNK) {
     int idx[ITEMS];
     bool keep[ITEMS], valid[ITEMS];
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
-      const int64_t i = base + j * T + tid;
-      valid[j] = i < n;
-      idx[j] = valid[j] ? list[i] : 0;
+      valid[j] = base + j * T + tid < hi;
+      idx[j] = nxt[j];
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const int64_t i = base + CHUNK + j * T + tid;
+      nxt[j] = i < hi ? (COH ? __ldcg(src + i) : src[i]) : 0;
     }
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
@@ -168,8 +190,10 @@ __device__ int64_t list_pass(const double* __restrict__ X, int64_t ldx, int D, i
       if (valid[j]) inside = row_dist(X + (int64_t)idx[j] * ldx, point, D) <= radius;
       keep[j] = valid[j] && !inside;
       const unsigned m = __ballot_sync(0xffffffffu, keep[j]);
-      if (lane == 0) s.cnt[j * NW + w] = __popc(m);
+      if (count_only) wcount += __popc(m);
+      else if (lane == 0) s.cnt[j * NW + w] = __popc(m);
     }
+    if (count_only) continue;
     __syncthreads();
     if (w == 0) {
       const int v0 = s.cnt[2 * lane], v1 = s.cnt[2 * lane + 1];
@@ -191,25 +215,42 @@ __device__ int64_t list_pass(const double* __restrict__ X, int64_t ldx, int D, i
       const unsigned m = __ballot_sync(0xffffffffu, keep[j]);
       const int kr = s.off[j * NW + w] + __popc(m & ((1u << lane) - 1u));  // rank among the kept entries of the chunk
       if (keep[j]) {
-        if (compact) list[kept_total + kr] = idx[j];
+        if (dst) dst[kept_base + kept_total + kr] = idx[j];
       } else if (valid[j] && sel_out) {
-        const int pos = j * T + tid;                                        // position in the chunk, list order
-        sel_out[(base - kept_total) + (pos - kr)] = idx[j];                 // flagged before this chunk + rank among flagged
+        const int pos = j * T + tid;  // position in the chunk, list order
+        // flagged entries of the slice before this chunk + rank among the flagged entries of the chunk
+        sel_out[sel_base + ((base - lo) - kept_total) + (pos - kr)] = idx[j];
       }
     }
     kept_total += kept_chunk;
   }
+  if (count_only) {
+    __syncthreads();  // protect s.cnt from a previous use
+    if (lane == 0) s.cnt[w] = wcount;
+    __syncthreads();
+    for (int k = 0; k < NW; ++k) kept_total += s.cnt[k];
+  }
   __syncthreads();
-  return n - kept_total;
+  return kept_total;
+}
+
+// One CTA over a whole list: flagged entries appended to sel_out, optional in-place compaction of the others.
+// Returns the number of flagged entries.
+__device__ int64_t list_pass(const double* __restrict__ X, int64_t ldx, int D, int* list, int64_t n, const double* point,
+                             double radius, int* sel_out, bool compact, PassSmem& s) {
+  return n - slice_pass<false>(X, ldx, D, list, compact ? list : nullptr, 0, n, 0, 0, point, radius, sel_out,
+                               !compact && !sel_out, s);
 }
 
 // Ordered mean of the rows list[0..n) into point[0..D) (shared memory): x[list].mean(axis=-2).
+template <bool COH = false>
 __device__ void ordered_mean(const double* __restrict__ X, int64_t ldx, int D, const int* list, int64_t n, double* point,
                              double* stage, int stage_rows) {
+  auto at = [&](int64_t i) { return COH ? __ldcg(list + i) : list[i]; };
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (D == 1) {
     if (w == 0) {
-      const double s = warp_pw([&](int64_t i) { return X[(int64_t)list[i] * ldx]; }, n, lane);
+      const double s = warp_pw([&](int64_t i) { return X[(int64_t)at(i) * ldx]; }, n, lane);
       if (lane == 0) point[0] = __ddiv_rn(s, (double)n);
     }
     __syncthreads();
@@ -225,7 +266,7 @@ __device__ void ordered_mean(const double* __restrict__ X, int64_t ldx, int D, c
     if (w > 0) {
       for (int e = tid - 32; e < rows * D; e += T - 32) {
         const int row = e / D, d = e - row * D;
-        buf[e] = X[(int64_t)list[r0 + row] * ldx + d];
+        buf[e] = X[(int64_t)at(r0 + row) * ldx + d];
       }
     }
     __syncthreads();
@@ -265,7 +306,9 @@ struct GreedyArgs {
   const int* rn_idx;
   const int64_t* seg_off;
   int64_t* seg_cnt;
-  int* data_idx;
+  int* data_idx;   // the lists, buffer 0
+  int* data_alt;   // buffer 1 (cluster passes compact out of place and flip `which`)
+  int* which;      // per parent: the buffer its list is in
   int* scratch;
   double* ch_pt;
   int* ch_next;
@@ -297,12 +340,14 @@ __global__ void __launch_bounds__(T) greedy_kernel(GreedyArgs a) {
   volatile int64_t* seg_cnt = a.seg_cnt;
   volatile int* err = a.err;
   __shared__ int64_t s_cnt;
+  auto list_of = [&](int r) { return (a.which[r] ? a.data_alt : a.data_idx) + a.seg_off[r]; };  // (no flips in this kernel)
+  int* const list_p = list_of(p);
   while (true) {
     if (tid == 0) s_cnt = *err != 0 ? 0 : seg_cnt[p];  // another CTA's failure stops everybody
     __syncthreads();
     const int64_t cnt = s_cnt;
     if (cnt == 0) break;
-    const int first = a.data_idx[off_p];
+    const int first = list_p[0];
     if (tid < D) {
       const double v = a.X[(int64_t)first * a.ldx + tid];
       init[tid] = v;
@@ -311,7 +356,7 @@ __global__ void __launch_bounds__(T) greedy_kernel(GreedyArgs a) {
     __syncthreads();
     if (a.lloyds) {
       int* sel = a.scratch + off_p;
-      const int64_t nsel = list_pass(a.X, a.ldx, D, a.data_idx + off_p, cnt, init, a.radius, sel, false, ps);
+      const int64_t nsel = list_pass(a.X, a.ldx, D, list_p, cnt, init, a.radius, sel, false, ps);
       // nsel >= 1: the first row is at distance 0 from itself
       ordered_mean(a.X, a.ldx, D, sel, nsel, point, stage, a.stage_rows);
       // rejected when it comes within `radius` of an existing child of a neighbouring parent (covertree.py:76-83)
@@ -356,7 +401,7 @@ __global__ void __launch_bounds__(T) greedy_kernel(GreedyArgs a) {
       for (int64_t ri = rb; ri < re; ++ri) {
         const int r = a.rn_idx[ri];
         const int64_t n = seg_cnt[r];
-        if (n > 0) total += list_pass(a.X, a.ldx, D, a.data_idx + a.seg_off[r], n, point, a.radius, nullptr, false, ps);
+        if (n > 0) total += list_pass(a.X, a.ldx, D, list_of(r), n, point, a.radius, nullptr, false, ps);
       }
       if (tid == 0) {
         s_pool = atomicAdd(a.pool_ptr, (unsigned long long)total);
@@ -372,7 +417,7 @@ __global__ void __launch_bounds__(T) greedy_kernel(GreedyArgs a) {
       const int r = a.rn_idx[ri];
       const int64_t n = seg_cnt[r];
       if (n == 0) continue;
-      const int64_t taken = list_pass(a.X, a.ldx, D, a.data_idx + a.seg_off[r], n, point, a.radius, pool, true, ps);
+      const int64_t taken = list_pass(a.X, a.ldx, D, list_of(r), n, point, a.radius, pool, true, ps);
       if (pool) pool += taken;
       if (r == p) taken_here = taken;
       if (tid == 0 && taken) seg_cnt[r] = n - taken;
@@ -383,6 +428,186 @@ __global__ void __launch_bounds__(T) greedy_kernel(GreedyArgs a) {
       break;
     }
   }
+}
+
+// The same loop for ONE parent per thread-block CLUSTER (2, 4, 8 or 16 CTAs), used for the waves with few parents, where one
+// CTA per parent would leave most SMs idle.  Two ways of sharing a step:
+//   * by slices (few, long lists - the coarse levels, where a step walks up to N rows): every CTA counts the kept
+//     entries of its contiguous slice -> the counts are exchanged through distributed shared memory (one cluster
+//     barrier) -> every CTA writes its slice at its prefix, kept entries into the OTHER buffer of the list (`which`
+//     flips), flagged entries to the selection / the new node's rows;
+//   * by lists (>= 2 lists per CTA - the fine levels): the CTAs take the neighbouring lists in turn and compact them in
+//     place, one cluster barrier per step.
+// The ordered Lloyd mean, the rejection test and the node table stay with CTA 0, which broadcasts the outcome into the
+// other CTAs' shared memory.
+struct ClusterShared {
+  int64_t kept[2][16];  // per pass parity: kept entries of every CTA's slice
+  int64_t cnt;         // rows left in the parent (0 = stop), broadcast by CTA 0
+  int child;
+  unsigned long long pool;
+};
+
+__global__ void __launch_bounds__(T) greedy_cluster_kernel(GreedyArgs a) {
+  namespace cgx = cooperative_groups;
+  cgx::cluster_group cluster = cgx::this_cluster();
+  const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
+  extern __shared__ double sm[];
+  double* point = sm;
+  double* init = sm + a.D;
+  double* stage = sm + 2 * a.D;
+  __shared__ PassSmem ps;
+  __shared__ ClusterShared cs;
+  const int tid = threadIdx.x, D = a.D;
+  const int p = a.wave_parents[blockIdx.x / CS];
+  const int64_t off_p = a.seg_off[p];
+  const int64_t rb = a.rn_off[p], re = a.rn_off[p + 1];
+  volatile int64_t* seg_cnt = a.seg_cnt;
+  volatile int* which = a.which;
+  volatile int* err = a.err;
+  int pass_no = 0;
+
+  // cooperative pass over the list of node r (n rows): returns the number of flagged rows
+  auto coop_pass = [&](int r, int64_t n, const double* pt, int* sel_out, bool compact) -> int64_t {
+    const int wh = which[r];
+    const int* src = (wh ? a.data_alt : a.data_idx) + a.seg_off[r];
+    int* dst = (wh ? a.data_idx : a.data_alt) + a.seg_off[r];
+    const int64_t nch = (n + CHUNK - 1) / CHUNK, per = (nch + CS - 1) / CS;
+    const int64_t lo = min(n, (int64_t)rank * per * CHUNK), hi = min(n, (int64_t)(rank + 1) * per * CHUNK);
+    const int64_t kept_local = slice_pass<true>(a.X, a.ldx, D, src, nullptr, lo, hi, 0, 0, pt, a.radius, nullptr, true, ps);
+    const int par = pass_no & 1;
+    ++pass_no;
+    if (tid < CS) *cluster.map_shared_rank(&cs.kept[par][rank], tid) = kept_local;
+    cluster.sync();
+    int64_t prefix = 0, total = 0;
+    for (int c = 0; c < CS; ++c) {
+      const int64_t v = cs.kept[par][c];
+      if (c < rank) prefix += v;
+      total += v;
+    }
+    const int64_t flagged = n - total;
+    if (flagged > 0 && (sel_out || compact)) {
+      slice_pass<true>(a.X, a.ldx, D, src, compact ? dst : nullptr, lo, hi, prefix, lo - prefix, pt, a.radius, sel_out,
+                       false, ps);
+      if (compact && rank == 0 && tid == 0) {
+        which[r] = wh ^ 1;
+        seg_cnt[r] = total;
+      }
+    }
+    return flagged;
+  };
+
+  while (true) {
+    if (rank == 0 && tid == 0) {
+      const int64_t v = *err != 0 ? 0 : seg_cnt[p];
+      for (int c = 0; c < CS; ++c) *cluster.map_shared_rank(&cs.cnt, c) = v;
+    }
+    cluster.sync();
+    const int64_t cnt = cs.cnt;
+    if (cnt == 0) break;
+    const int first = __ldcg((which[p] ? a.data_alt : a.data_idx) + off_p);
+    if (tid < D) {
+      const double v = a.X[(int64_t)first * a.ldx + tid];
+      init[tid] = v;
+      point[tid] = v;
+    }
+    __syncthreads();
+    if (a.lloyds) {
+      int* sel = a.scratch + off_p;
+      const int64_t nsel = coop_pass(p, cnt, init, sel, false);
+      cluster.sync();  // the selection is complete
+      if (rank == 0) {
+        ordered_mean<true>(a.X, a.ldx, D, sel, nsel, point, stage, a.stage_rows);
+        int hit = 0;
+        for (int64_t ri = rb + tid; ri < re; ri += T) {
+          const int r = a.rn_idx[ri];
+          for (int c = __ldcg(a.p_first + r); c >= 0 && !hit; c = __ldcg(a.ch_next + c)) {
+            double s = 0.0;
+            for (int d = 0; d < D; ++d) {
+              const double t = __dsub_rn(point[d], __ldcg(a.ch_pt + (int64_t)c * D + d));
+              s = __fma_rn(t, t, s);
+            }
+            if (__dsqrt_rn(s) < a.radius) hit = 1;
+          }
+        }
+        if (__syncthreads_or(hit)) {
+          if (tid < D) point[tid] = init[tid];
+          __syncthreads();
+        }
+      }
+    }
+    // the new child: CTA 0 enters it into the node table and tells the others
+    if (rank == 0) {
+      if (tid == 0) {
+        const int id = atomicAdd(a.n_children, 1);
+        int child = -1;
+        if (id >= a.ch_cap) {
+          *err = 2;
+        } else {
+          a.ch_next[id] = -1;
+          const int last = a.p_last[p];
+          if (last < 0) a.p_first[p] = id; else a.ch_next[last] = id;
+          a.p_last[p] = id;
+          child = id;
+        }
+        for (int c = 0; c < CS; ++c) *cluster.map_shared_rank(&cs.child, c) = child;
+      }
+      if (tid < D) {
+        const double v = point[tid];
+        for (int c = 1; c < CS; ++c) cluster.map_shared_rank(point, c)[tid] = v;
+      }
+    }
+    cluster.sync();
+    const int child = cs.child;
+    if (child < 0) break;
+    if (rank == 0 && tid < D) a.ch_pt[(int64_t)child * D + tid] = point[tid];
+    int* pool = nullptr;
+    if (a.store_children) {
+      int64_t total = 0;
+      for (int64_t ri = rb; ri < re; ++ri) {
+        const int r = a.rn_idx[ri];
+        const int64_t n = seg_cnt[r];
+        if (n > 0) total += coop_pass(r, n, point, nullptr, false);
+      }
+      if (rank == 0 && tid == 0) {
+        const unsigned long long base = atomicAdd(a.pool_ptr, (unsigned long long)total);
+        a.ch_off[child] = (int64_t)base;
+        a.ch_cnt[child] = total;
+        for (int c = 0; c < CS; ++c) *cluster.map_shared_rank(&cs.pool, c) = base;
+      }
+      cluster.sync();
+      pool = a.ch_pool + cs.pool;
+    }
+    if (!a.store_children && re - rb >= 2 * CS) {
+      // many neighbouring lists: the CTAs of the cluster take them in turn, each compacting its lists in place
+      for (int64_t ri = rb + rank; ri < re; ri += CS) {
+        const int r = a.rn_idx[ri];
+        const int64_t n = seg_cnt[r];
+        if (n == 0) continue;
+        int* list = (which[r] ? a.data_alt : a.data_idx) + a.seg_off[r];
+        const int64_t kept = slice_pass<true>(a.X, a.ldx, D, list, list, 0, n, 0, 0, point, a.radius, nullptr, false, ps);
+        if (tid == 0) {
+          if (kept != n) seg_cnt[r] = kept;
+          if (r == p && kept == n) *err = 1;  // the reference would loop forever here
+        }
+      }
+      cluster.sync();  // all lists and counts are in place before CTA 0 looks at the parent again
+      continue;
+    }
+    int64_t taken_here = 0;
+    for (int64_t ri = rb; ri < re; ++ri) {
+      const int r = a.rn_idx[ri];
+      const int64_t n = seg_cnt[r];
+      if (n == 0) continue;
+      const int64_t taken = coop_pass(r, n, point, pool, true);
+      if (pool) pool += taken;
+      if (r == p) taken_here = taken;
+    }
+    if (taken_here == 0) {  // the reference would loop forever here
+      if (rank == 0 && tid == 0) *err = 1;
+      break;
+    }
+  }
+  cluster.sync();  // nobody leaves while its shared memory may still be written
 }
 
 // root: mean of all rows (covertree.py:49)
@@ -501,15 +726,35 @@ __global__ void exclusive_offsets_kernel(const int64_t* __restrict__ cnt, int64_
   }
 }
 
+// Bump allocator over the ctx workspace (kept between calls: cudaMalloc / cudaFree of hundreds of MB per build cost
+// up to 270 ms) - `base == nullptr` only measures.
+struct Arena {
+  char* base = nullptr;
+  size_t used = 0;
+  void* take(size_t bytes) {
+    used = (used + 255) & ~(size_t)255;
+    void* p = base ? base + used : nullptr;
+    used += bytes;
+    return p;
+  }
+};
 template <typename U>
 struct DevBuf {
   U* p = nullptr;
   size_t n = 0;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t count) {
-    if (p) { cudaFree(p); p = nullptr; }
+  bool owned = false;
+  ~DevBuf() { if (p && owned) cudaFree(p); }
+  cudaError_t alloc(size_t count) {  // own allocation (small per-level tables)
+    if (p && owned) cudaFree(p);
+    p = nullptr;
     n = count;
+    owned = true;
     return cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(U));
+  }
+  void carve(Arena& a, size_t count) {  // a piece of the workspace
+    n = count;
+    owned = false;
+    p = (U*)a.take(std::max<size_t>(count, 1) * sizeof(U));
   }
 };
 
@@ -556,39 +801,86 @@ extern "C" int cggp_covertree_build(cggp_ctx* ctx, int dtype, const void* dev_X,
   cudaStream_t st = ctx->stream;
 
   // shared memory of the greedy kernel: point, first row, two stages of rows for the ordered mean
-  int stage_rows = std::max(8, std::min(256, (int)((96 * 1024) / (sizeof(double) * 2 * D))));
+  int stage_rows = std::max(8, std::min(2048, (int)((96 * 1024) / (sizeof(double) * 2 * D))));
   const size_t greedy_smem = sizeof(double) * (2 * (size_t)D + 2 * (size_t)stage_rows * D);
   CGGP_CUDA(ctx, cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)greedy_smem));
+  CGGP_CUDA(ctx, cudaFuncSetAttribute(greedy_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)greedy_smem));
   CGGP_CUDA(ctx, cudaFuncSetAttribute(root_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)greedy_smem));
+  // waves with few parents run one parent per cluster of CTAs (CGGP_CT_CLUSTER = 0: never, 1: always, default: where a
+  // parent holds >= 32 rows on average; results do not depend on it)
+  const char* cl_env = getenv("CGGP_CT_CLUSTER");
+  const int cl_mode = cl_env ? atoi(cl_env) : -1;
+  const bool trace = getenv("CGGP_CT_TRACE") != nullptr;
+  // clusters of 16 CTAs (non-portable size) where the device schedules them, 8 otherwise
+  int max_cluster = 8;
+  if (cudaFuncSetAttribute(greedy_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(16);
+    cfg.blockDim = dim3(T);
+    cfg.dynamicSmemBytes = greedy_smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 16;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, greedy_cluster_kernel, &cfg) == cudaSuccess && nclusters >= 1)
+      max_cluster = 16;
+  }
+  (void)cudaGetLastError();
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto ms_since = [](std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  };
   const int vor_smem_doubles = (96 * 1024) / sizeof(double);
   CGGP_CUDA(ctx, cudaFuncSetAttribute(voronoi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(vor_smem_doubles * sizeof(double))));
 
-  DevBuf<int> data_idx, scratch, vorA, vorB, keysA, keysB, ch_next, p_first, p_last, pool, counters;
+  DevBuf<int> data_idx, data_alt, which, scratch, vorA, vorB, keysA, keysB, ch_next, p_first, p_last, pool, counters;
   DevBuf<double> ch_pt, small;
   DevBuf<int64_t> seg_off, seg_cnt, ch_off, ch_cnt;
   DevBuf<unsigned long long> ull;
   DevBuf<unsigned char> cub_tmp;
-  CGGP_CUDA(ctx, data_idx.alloc(n));
-  CGGP_CUDA(ctx, scratch.alloc(n));
-  CGGP_CUDA(ctx, ch_next.alloc(n));
-  CGGP_CUDA(ctx, p_first.alloc(n));
-  CGGP_CUDA(ctx, p_last.alloc(n));
-  CGGP_CUDA(ctx, ch_pt.alloc((size_t)n * D));
-  CGGP_CUDA(ctx, seg_off.alloc(n + 1));
-  CGGP_CUDA(ctx, seg_cnt.alloc(n + 1));
-  CGGP_CUDA(ctx, counters.alloc(4));   // [0] number of children, [1] error flag
-  CGGP_CUDA(ctx, ull.alloc(2));        // [0] pool pointer, [1] largest root distance
-  CGGP_CUDA(ctx, small.alloc(MAX_D));
-  if (voronoi) {
-    CGGP_CUDA(ctx, vorA.alloc(n));
-    CGGP_CUDA(ctx, vorB.alloc(n));
-    CGGP_CUDA(ctx, keysA.alloc(n));
-    CGGP_CUDA(ctx, keysB.alloc(n));
-  } else {
-    CGGP_CUDA(ctx, pool.alloc(n));
-    CGGP_CUDA(ctx, ch_off.alloc(n));
-    CGGP_CUDA(ctx, ch_cnt.alloc(n));
+  size_t cub_bytes = 0;
+  if (voronoi)
+    CGGP_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const int*)nullptr, (int*)nullptr,
+                                                   (const int*)nullptr, (int*)nullptr, n, 0, 31, st));
+  auto layout = [&](Arena& ar) {
+    data_idx.carve(ar, n);
+    data_alt.carve(ar, n);
+    which.carve(ar, n);
+    scratch.carve(ar, n);
+    ch_next.carve(ar, n);
+    p_first.carve(ar, n);
+    p_last.carve(ar, n);
+    ch_pt.carve(ar, (size_t)n * D);
+    seg_off.carve(ar, n + 1);
+    seg_cnt.carve(ar, n + 1);
+    counters.carve(ar, 4);  // [0] number of children, [1] error flag
+    ull.carve(ar, 2);       // [0] pool pointer, [1] largest root distance
+    small.carve(ar, MAX_D);
+    if (voronoi) {
+      vorA.carve(ar, n);
+      vorB.carve(ar, n);
+      keysA.carve(ar, n);
+      keysB.carve(ar, n);
+      cub_tmp.carve(ar, cub_bytes);
+    } else {
+      pool.carve(ar, n);
+      ch_off.carve(ar, n);
+      ch_cnt.carve(ar, n);
+    }
+  };
+  {
+    Arena measure;
+    layout(measure);
+    const int rc = cggp_ws_reserve(ctx, measure.used + 256);
+    if (rc) return rc;
+    Arena real;
+    real.base = (char*)ctx->ws;
+    layout(real);
   }
   const int iota_grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
 
@@ -625,6 +917,7 @@ extern "C" int cggp_covertree_build(cggp_ctx* ctx, int dtype, const void* dev_X,
   tree->n = n;
   tree->device = ctx->device;
   tree->levels.resize(num_levels);
+  if (trace) fprintf(stderr, "covertree: buffers + root (mean, largest distance) %.3f ms\n", ms_since(t_begin));
   {
     Level& root = tree->levels[0];
     root.size = 1;
@@ -686,24 +979,55 @@ extern "C" int cggp_covertree_build(cggp_ctx* ctx, int dtype, const void* dev_X,
     CGGP_CUDA(ctx, cudaMemsetAsync(ull.p, 0, sizeof(unsigned long long), st));
     CGGP_CUDA(ctx, cudaMemsetAsync(p_first.p, 0xff, sizeof(int) * P, st));
     CGGP_CUDA(ctx, cudaMemsetAsync(p_last.p, 0xff, sizeof(int) * P, st));
+    CGGP_CUDA(ctx, cudaMemsetAsync(which.p, 0, sizeof(int) * P, st));
+    const auto t_level = std::chrono::steady_clock::now();
 
     GreedyArgs ga;
     ga.X = X; ga.ldx = ldx; ga.D = D; ga.radius = radius; ga.lloyds = lloyds; ga.store_children = voronoi ? 0 : 1;
     ga.rn_off = d_rn_off.p; ga.rn_idx = d_rn_idx.p; ga.seg_off = seg_off.p; ga.seg_cnt = seg_cnt.p;
-    ga.data_idx = data_cur; ga.scratch = scratch.p; ga.ch_pt = ch_pt.p; ga.ch_next = ch_next.p;
+    ga.data_idx = data_cur; ga.data_alt = data_alt.p; ga.which = which.p; ga.scratch = scratch.p; ga.ch_pt = ch_pt.p; ga.ch_next = ch_next.p;
     ga.p_first = p_first.p; ga.p_last = p_last.p; ga.n_children = counters.p; ga.ch_cap = (int)n;
     ga.ch_off = ch_off.p; ga.ch_cnt = ch_cnt.p; ga.ch_pool = pool_cur; ga.pool_ptr = ull.p; ga.err = counters.p + 1;
     ga.stage_rows = stage_rows;
+    int n_clustered = 0;
     for (int wv = 1; wv <= n_waves; ++wv) {
       const int64_t cnt = wave_off[wv + 1] - wave_off[wv];
       if (cnt == 0) continue;
       ga.wave_parents = d_wave_parents.p + wave_off[wv];
-      greedy_kernel<<<(unsigned)cnt, T, greedy_smem, st>>>(ga);
+      // one cluster of CTAs per parent where the wave leaves SMs idle (the largest size that still fits)
+      int CS = 1;
+      if (cl_mode > 0 || (cl_mode < 0 && n / P >= 32))  // (very short lists: the cluster barriers cost more than they save)
+        // (16 CTAs only for long lists: at the fine levels their barriers cost more than the extra CTAs save -
+        // N = 8M, D = 2: level 8 of 9 took 423 ms with 16 against 160 ms with 8)
+        for (int c = (n / P >= 65536 ? max_cluster : 8); c > 1; c >>= 1)
+          if (cnt * c <= ctx->sm_count) { CS = c; break; }
+      if (CS > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(cnt * CS));
+        cfg.blockDim = dim3(T);
+        cfg.dynamicSmemBytes = greedy_smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CS;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CGGP_CUDA(ctx, cudaLaunchKernelEx(&cfg, greedy_cluster_kernel, ga));
+        ++n_clustered;
+      } else {
+        greedy_kernel<<<(unsigned)cnt, T, greedy_smem, st>>>(ga);
+      }
       CGGP_LAUNCH_CHECK(ctx);
     }
     int host_counters[4] = {0, 0, 0, 0};
     CGGP_CUDA(ctx, cudaMemcpyAsync(host_counters, counters.p, sizeof(host_counters), cudaMemcpyDeviceToHost, st));
     CGGP_CUDA(ctx, cudaStreamSynchronize(st));
+    if (trace)
+      fprintf(stderr, "covertree level %d: %lld parents, %d waves (%d clustered), %d new nodes, greedy pass %.3f ms\n", level,
+              (long long)P, n_waves, n_clustered, host_counters[0], ms_since(t_level));
+    const auto t_host = std::chrono::steady_clock::now();
     if (host_counters[1] == 1)
       CGGP_FAIL(ctx, CGGP_ERR_INVALID, "covertree: level %d: a new node took no row of its parent (the reference loops "
                 "forever on such input)", level);
@@ -764,6 +1088,8 @@ extern "C" int cggp_covertree_build(cggp_ctx* ctx, int dtype, const void* dev_X,
       }
     }
 
+    if (trace) fprintf(stderr, "covertree level %d: node order + neighbour lists on the host %.3f ms\n", level, ms_since(t_host));
+    const auto t_vor = std::chrono::steady_clock::now();
     if (voronoi) {
       // host copy of the parents' Voronoi extents (their lists lie back to back in vor_cur, in level order)
       std::vector<int64_t> vor_off(P + 1);
@@ -808,7 +1134,7 @@ extern "C" int cggp_covertree_build(cggp_ctx* ctx, int dtype, const void* dev_X,
       while ((1ll << bits) < nc) ++bits;
       size_t tmp_bytes = 0;
       CGGP_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keysA.p, keysB.p, vor_cur, vor_alt, n, 0, bits, st));
-      if (tmp_bytes > cub_tmp.n) CGGP_CUDA(ctx, cub_tmp.alloc(tmp_bytes));
+      if (tmp_bytes > cub_tmp.n) CGGP_CUDA(ctx, cub_tmp.alloc(tmp_bytes));  // (not expected: sized for 31 key bits)
       CGGP_CUDA(ctx, cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, keysA.p, keysB.p, vor_cur, vor_alt, n, 0, bits, st));
       ctx->launches += 1;
       std::swap(vor_cur, vor_alt);
@@ -837,6 +1163,10 @@ extern "C" int cggp_covertree_build(cggp_ctx* ctx, int dtype, const void* dev_X,
       }
       std::swap(data_cur, pool_cur);
     }
+    if (trace) {
+      cudaStreamSynchronize(st);
+      fprintf(stderr, "covertree level %d: Voronoi pass / list hand-over %.3f ms\n", level, ms_since(t_vor));
+    }
   }
 
   // rows of the last level
@@ -852,6 +1182,7 @@ extern "C" int cggp_covertree_build(cggp_ctx* ctx, int dtype, const void* dev_X,
   CGGP_CUDA(ctx, cudaStreamSynchronize(st));
   guard.keep = true;
   *out = tree;
+  if (trace) fprintf(stderr, "covertree: built in %.3f ms\n", ms_since(t_begin));
   return CGGP_OK;
 }
 

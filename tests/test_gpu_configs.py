@@ -112,6 +112,42 @@ def test_config2_cdgp_elbo_replica(cb):
     np.testing.assert_allclose(float(m.prior_kl()) + 0.5 * logdet, float(cl.prior_kl()), rtol=2e-4)
 
 
+def test_config2_cover_tree_selected_inducing_points(cb):
+    """configs[1] as worded: "M cover-tree-selected" - the inducing points, pseudo targets and counts come from the
+    device cover tree (optimize.py:19-39), bit-identical to the oracle's tree, and feed the CDGP ELBO."""
+    import warnings
+
+    from oracle import covertree as oct_
+
+    rng = np.random.default_rng(11)
+    N, D = 30_000, 3
+    X = rng.standard_normal((N, D))
+    y = np.sin(X.sum(-1, keepdims=True)) + np.sqrt(0.1) * rng.standard_normal((N, 1))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tree = oct_.CoverTree(None, (X, y), spatial_resolution=0.8)
+    omeans, ocounts = tree.cluster_mean_and_counts
+    keep = ocounts.reshape(-1) != 0
+    Z, u, cnt = tree.centroids[keep], omeans[keep], ocounts[keep]
+    iv, means, counts = cb.covertree_update_inducing_parameters(None, (dev(X), dev(y)), None, 0.8)
+    np.testing.assert_array_equal(cpu(iv), Z)
+    np.testing.assert_array_equal(cpu(means), u)
+    np.testing.assert_array_equal(cpu(counts), cnt)
+    ok, k = g.SquaredExponential(1.0, np.ones(D)), cb.SquaredExponential(1.0, np.ones(D))
+    thr = 1e-10
+    m = cb.CGGP(k, cb.Gaussian(0.1), iv, cb.ConjugateGradient(thr), num_probes=None, cluster_counts=counts,
+                pseudo_u=means, num_data=N)
+    batch = (X[:2000], y[:2000])
+    elbo = float(m.elbo((dev(batch[0]), dev(batch[1]))))
+
+    def oracle(cgobj):
+        mo = om.CGGP(ok, g.Gaussian(0.1), Z, cgobj, num_probes=None, cluster_counts=cnt, pseudo_u=u, num_data=N)
+        return mo.elbo(batch)
+
+    ref = oracle(ocg.ConjugateGradient(thr))
+    nz.assert_close_with_noise(elbo, ref, [oracle(nz.PermutedCG(s, thr)) for s in (0, 1)], 1e-8, "elbo")
+
+
 def test_config3_headline_solve_replica(cb):
     """Matrix-free CG on Sigma = Kuu + Kuf Kfu / s2, D=11, Matern-5/2, through the pipelined kernel (variant 3, both
     the B=1 and B=2 plans), vs the oracle: trajectory, iteration count, Nystrom-preconditioned full solve."""

@@ -41,8 +41,10 @@ def check_against(tree, level_sizes, level_points, centroids, means, counts, mem
     assert np.array_equal(m.cpu().numpy(), means, equal_nan=True)
 
 
+@pytest.mark.parametrize("cluster", ["0", "1"])   # one CTA per parent / one cluster of 8 CTAs per parent (few parents)
 @pytest.mark.parametrize("name", CASES)
-def test_covertree_vs_reference_golden(name):
+def test_covertree_vs_reference_golden(name, cluster, monkeypatch):
+    monkeypatch.setenv("CGGP_CT_CLUSTER", cluster)
     x, y = GOLD[f"{name}/x"], GOLD[f"{name}/y"]
     tree = build(x, y, **case_kwargs(name))
     check_against(tree, GOLD[f"{name}/level_sizes"], GOLD[f"{name}/level_points"], GOLD[f"{name}/centroids"],
@@ -59,7 +61,7 @@ def test_covertree_vs_reference_golden(name):
     (30000, 2, 0.15, {"lloyds": False}),
     (50000, 1, 0.002, {}),                     # D = 1: NumPy's mean over rows is pairwise
 ])
-def test_covertree_vs_oracle_many_parents(n, d, res, kw):
+def test_covertree_vs_oracle_many_parents(n, d, res, kw, monkeypatch):
     from oracle import covertree as oct_
 
     rng = np.random.default_rng(n + d)
@@ -68,12 +70,17 @@ def test_covertree_vs_oracle_many_parents(n, d, res, kw):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         want = oct_.CoverTree(None, (x, y), spatial_resolution=res, **kw)
-    tree = build(x, y, spatial_resolution=res, **kw)
     wm, wc = want.cluster_mean_and_counts
     members = want.cluster_indices
-    check_against(tree, [len(lv) for lv in want.levels],
-                  np.concatenate([np.stack([nd.point for nd in lv]) for lv in want.levels if lv]),
-                  want.centroids, wm, wc, [len(m) for m in members], np.concatenate(members))
+    for cluster in ("0", "1", None):   # None = the default choice per wave
+        if cluster is None:
+            monkeypatch.delenv("CGGP_CT_CLUSTER", raising=False)
+        else:
+            monkeypatch.setenv("CGGP_CT_CLUSTER", cluster)
+        tree = build(x, y, spatial_resolution=res, **kw)
+        check_against(tree, [len(lv) for lv in want.levels],
+                      np.concatenate([np.stack([nd.point for nd in lv]) for lv in want.levels if lv]),
+                      want.centroids, wm, wc, [len(m) for m in members], np.concatenate(members))
 
 
 def test_covertree_update_inducing_parameters_and_views():
