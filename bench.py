@@ -565,6 +565,18 @@ def run_native(args):
                 secondary[wl] = quick_its(cb, device, wl)
             except Exception as exc:  # pragma: no cover
                 secondary[wl] = {"error": str(exc)}
+        # BASELINE configs[1] as worded (cover-tree-selected inducing points -> CDGP ELBO -> predict_f), stage by stage
+        try:
+            import importlib.util
+
+            spec = importlib.util.spec_from_file_location("config2_pipeline",
+                                                          os.path.join(ROOT, "tools", "config2_pipeline.py"))
+            config2_pipeline = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(config2_pipeline)
+            secondary["c2_cdgp_pipeline"] = config2_pipeline.run(cb, device)
+            torch.cuda.empty_cache()
+        except Exception as exc:  # pragma: no cover
+            secondary["c2_cdgp_pipeline"] = {"error": str(exc)}
         # the multi-RHS form of the headline product: 8 right-hand sides per sweep, both contractions on DMMA
         try:
             g8 = torch.Generator(device=device).manual_seed(3)
