@@ -1,5 +1,5 @@
 """Short single-GPU cases for ncu (one kernel family per run, few launches; the same command line must first exit 0
-without ncu - B200_PROFILING.md):  python tools/prof_case.py pipe1 | pipe8 | cg | gram [rows]"""
+without ncu - B200_PROFILING.md):  python tools/prof_case.py pipe1 | pipe8 | cg | gram [rows] [c3 | c2 | c4]"""
 import os
 import sys
 
@@ -13,9 +13,14 @@ def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "pipe1"
     g = torch.Generator(device="cuda").manual_seed(0)
     N, M, D = (int(sys.argv[2]) if len(sys.argv) > 2 else 500_000), 4096, 11
+    shape = sys.argv[3] if len(sys.argv) > 3 else "c3"
+    if shape == "c2":
+        M, D = 2048, 3
+    elif shape == "c4":
+        M, D = 16384, 2
     X = torch.randn(N, D, dtype=torch.float64, device="cuda", generator=g)
     Z = torch.randn(M, D, dtype=torch.float64, device="cuda", generator=g)
-    k = cb.Matern52(variance=1.0, lengthscales=[1.0] * D)
+    k = (cb.SquaredExponential if shape == "c2" else cb.Matern52)(variance=1.0, lengthscales=[1.0] * D)
     op = cb.SGPROperator(k, X, Z, 0.1)
     if which in ("pipe1", "pipe8"):
         V = torch.randn(1 if which == "pipe1" else 8, M, dtype=torch.float64, device="cuda", generator=g)
