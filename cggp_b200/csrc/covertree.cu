@@ -1014,8 +1014,12 @@ extern "C" int cggp_covertree_build(cggp_ctx* ctx, int dtype, const void* dev_X,
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        CGGP_CUDA(ctx, cudaLaunchKernelEx(&cfg, greedy_cluster_kernel, ga));
-        ++n_clustered;
+        if (cudaLaunchKernelEx(&cfg, greedy_cluster_kernel, ga) == cudaSuccess) {
+          ++n_clustered;
+        } else {  // e.g. a partitioned device that cannot co-schedule the cluster: one CTA per parent instead
+          (void)cudaGetLastError();
+          greedy_kernel<<<(unsigned)cnt, T, greedy_smem, st>>>(ga);
+        }
       } else {
         greedy_kernel<<<(unsigned)cnt, T, greedy_smem, st>>>(ga);
       }
