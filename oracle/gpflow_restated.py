@@ -9,10 +9,15 @@ vendored under /root/reference and not installable here), so this file restates 
 expectations), ``cggp/optimize.py:50`` (square_distance), ``cggp/cli_utils.py:444-446`` (SGPR),
 ``cggp/distance.py:17-20,26-29`` (kernel __call__).
 
-PARITY UNPINNED: the reference holds no golden vectors for these values.  What pins them
-instead: closed forms and the CGGP / ClusterGP / dense cross-checks (tests/test_oracle_gpflow.py), and an independent
-third-party implementation of the same published formulas - scikit-learn's RBF / Matern kernels and exact GP
-regression (tests/test_oracle_vs_sklearn.py).
+PARITY UNPINNED at the last digits: the reference holds no golden vectors for these values.
+What pins them: (1) the reference's ONE known-answer test of the kernel values, ``cggp/rff_test.py:9-29`` - the
+random-Fourier-feature estimate built by the reference's unmodified ``cggp/rff.py`` (spectral sampling, independent of
+these closed forms) must reproduce K(X, X) to rtol 1e-3 / atol 1e-2: fixtures from that file run here
+(tests/golden/make_golden_rff.py, 4e6 bases) agree with these kernels to 1e-3 (tests/test_oracle_rff.py), which fixes
+the kernel family, the sqrt(3) / sqrt(5) scalings, the variance and the ARD lengthscale convention; (2) closed forms and
+the CGGP / ClusterGP / dense cross-checks (tests/test_oracle_gpflow.py); (3) an independent third-party implementation
+of the same published formulas - scikit-learn's RBF / Matern kernels and exact GP regression, to 5e-13
+(tests/test_oracle_vs_sklearn.py).
 """
 from __future__ import annotations
 

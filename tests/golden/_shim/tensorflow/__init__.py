@@ -140,6 +140,7 @@ linalg = types.SimpleNamespace(
     logdet=lambda a: np.linalg.slogdet(a)[1],
     adjoint=lambda a: np.swapaxes(a, -1, -2),
 )
-math = types.SimpleNamespace(log=np.log, reciprocal=np.reciprocal, argmin=np.argmin, argmax=np.argmax)
+math = types.SimpleNamespace(log=np.log, reciprocal=np.reciprocal, argmin=np.argmin, argmax=np.argmax, cos=np.cos,
+                             sin=np.sin, truediv=np.true_divide)  # cos / sin / truediv: cggp/rff.py
 data = types.SimpleNamespace(Dataset=object, experimental=types.SimpleNamespace(AUTOTUNE=-1))
 concat = lambda xs, axis=0: np.concatenate(xs, axis=axis)  # noqa: E731

@@ -74,6 +74,21 @@ def test_kernel_matrix_vs_oracle(cb, name, D):
     np.testing.assert_allclose(cpu(cb.Kuu(dev(Z), k, jitter=1e-6)), g.Kuu(Z, ok, 1e-6), rtol=1e-6 if rough else 1e-12)
 
 
+def test_kernel_matrix_vs_reference_rff_estimates(cb):
+    """The reference's own known-answer test of the kernel values (cggp/rff_test.py:9-29): the random-Fourier-feature
+    estimates produced by the unmodified cggp/rff.py (tests/golden/rff_golden.npz) against the CUDA kernel matrices, at
+    that test's tolerance and at the Monte-Carlo level of the fixture."""
+    import os
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "rff_golden.npz"))
+    for key in sorted({"/".join(k.split("/")[:2]) for k in gold.files}):
+        name = key.split("/")[0]
+        X, ls, var = gold[f"{key}/inputs"], gold[f"{key}/lengthscales"], float(gold[f"{key}/variance"])
+        kxx = cpu(cb.kernels.KERNELS[name](variance=var, lengthscales=ls)(dev(X)))
+        np.testing.assert_allclose(gold[f"{key}/rff_approx"], kxx, rtol=1e-3, atol=1e-2)
+        assert np.abs(gold[f"{key}/rff_approx"] - kxx).max() < 4e-3, key
+
+
 def test_kernel_matrix_float32_and_isotropic(cb):
     rng = np.random.default_rng(0)
     X = rng.standard_normal((200, 5)).astype(np.float32)
