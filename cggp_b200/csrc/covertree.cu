@@ -900,6 +900,8 @@ extern "C" int cggp_covertree_build(cggp_ctx* ctx, int dtype, const void* dev_X,
   double max_radius;
   memcpy(&max_radius, &maxbits, sizeof(double));
   if (spatial_resolution > 0.0) {
+    // (all rows equal: the reference's math.log2(0) raises as well)
+    if (!(max_radius > 0.0)) CGGP_FAIL(ctx, CGGP_ERR_INVALID, "covertree: all rows coincide, no level count for a resolution");
     num_levels = (int)std::ceil(std::log2(max_radius / spatial_resolution)) + 1;
     if (num_levels >= 1) max_radius = spatial_resolution * (double)(1ll << (num_levels - 1));
   }
