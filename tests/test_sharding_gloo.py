@@ -91,3 +91,26 @@ def test_sharded_operator_allreduce_matches_unsharded(tmp_path):
     # sharding only changes the summation order: 1e-9 while CG has not amplified the rounding (the system has
     # cond ~ 1e9), loose afterwards
     assert dev_early < 1e-9 and dev_all < 1e-5 and dev_sol < 1e-5
+
+
+def test_shard_rows_weighted_partitions_and_follows_the_speeds():
+    from cggp_b200.sharding import shard_rows, shard_rows_weighted
+
+    for n in (0, 5, 1000, 250_007, 2_000_000):
+        for speeds in ([1.0], [1.0, 1.0], [1.0, 0.98, 1.01, 0.99, 1.0, 1.02, 0.97, 1.0], [3.0, 1.0, 1.0]):
+            world = len(speeds)
+            spans = [shard_rows_weighted(n, r, speeds) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[r][1] == spans[r + 1][0] for r in range(world - 1))
+            assert all(a <= b for a, b in spans)
+            if n >= 100_000:
+                total = sum(speeds)
+                for (a, b), s in zip(spans, speeds):
+                    assert abs((b - a) / n - s / total) < 1e-3
+    # equal speeds: the even split up to the block granularity
+    for r in range(4):
+        a, b = shard_rows_weighted(2_000_000, r, [1.0] * 4)
+        e = shard_rows(2_000_000, r, 4)
+        assert abs(a - e[0]) <= 24 and abs(b - e[1]) <= 24
+    with pytest.raises(ValueError):
+        shard_rows_weighted(10, 0, [1.0, 0.0])
