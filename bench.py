@@ -367,26 +367,28 @@ def run_native(args):
     esize = 4 if f32w else 8
 
     # ---- synthetic data: HOST (pinned) copies for the e2e leg, device copies for the resident leg -------------
-    g = torch.Generator().manual_seed(1234 + rank)
-    Xh = torch.randn(n_local, D, dtype=f64, generator=g).pin_memory()
-    yh = (torch.sin(Xh.sum(-1, keepdim=True)) + math.sqrt(NOISE) * torch.randn(n_local, 1, dtype=f64, generator=g))
-    yh = yh.pin_memory()
-    # inducing points: M rows drawn from rank 0's shard (uniform without replacement, cggp/cli_utils.py:157-161)
-    if rank == 0:
-        sel = torch.randperm(n_local, generator=g)[:M]
-        Zh = Xh[sel].clone()
-    else:
-        Zh = torch.empty(M, D, dtype=f64)
-    Zd = Zh.to(device)
-    if world > 1:
-        dist.broadcast(Zd, src=0)
-        Zh = Zd.cpu()
-    Zh = Zh.pin_memory()
     kernel = cb.kernels.KERNELS[kern](variance=1.0, lengthscales=[math.sqrt(D) if f32w else 1.0] * D)
 
-    Xd, yd = Xh.to(device), yh.to(device)
-    op = cb.SGPROperator(kernel, Xd, Zd, NOISE)
-    rhs = (op.kuf_times(yd) / NOISE).t().contiguous()  # [1, M]  s^-2 Kuf y (all-reduced)
+    def make_problem(rows):
+        g = torch.Generator().manual_seed(1234 + rank)
+        Xh_ = torch.randn(rows, D, dtype=f64, generator=g).pin_memory()
+        yh_ = (torch.sin(Xh_.sum(-1, keepdim=True)) + math.sqrt(NOISE) * torch.randn(rows, 1, dtype=f64, generator=g))
+        yh_ = yh_.pin_memory()
+        # inducing points: M rows drawn from rank 0's shard (uniform without replacement, cggp/cli_utils.py:157-161)
+        if rank == 0:
+            sel = torch.randperm(rows, generator=g)[:M]
+            Zh_ = Xh_[sel].clone()
+        else:
+            Zh_ = torch.empty(M, D, dtype=f64)
+        Zd_ = Zh_.to(device)
+        if world > 1:
+            dist.broadcast(Zd_, src=0)
+            Zh_ = Zd_.cpu()
+        Zh_ = Zh_.pin_memory()
+        Xd_, yd_ = Xh_.to(device), yh_.to(device)
+        op_ = cb.SGPROperator(kernel, Xd_, Zd_, NOISE)
+        rhs_ = (op_.kuf_times(yd_) / NOISE).t().contiguous()  # [1, M]  s^-2 Kuf y (all-reduced)
+        return Xh_, yh_, Zh_, Zd_, Xd_, yd_, op_, rhs_
 
     def barrier():
         if world > 1:
@@ -395,6 +397,31 @@ def run_native(args):
 
     def solve(operator, b, iters):
         return cb.conjugate_gradient(operator, b, None, 0.0, None, iters, iters + 1)
+
+    Xh, yh, Zh, Zd, Xd, yd, op, rhs = make_problem(n_local)
+    balance = None
+    if args.balance and world > 1:
+        # speed-weighted row split (opt-in): the devices of a box differ by a constant 1 - 2 %; calibrate the per-rank
+        # product time on the even split, re-shard once in proportion to the measured rates (cggp_b200.sharding)
+        from cggp_b200.sharding import shard_rows_weighted
+
+        solve(op, rhs, 3)
+        barrier()
+        ctx.profile(True)
+        solve(op, rhs, 12)
+        torch.cuda.synchronize()
+        pm = ctx.profile_read()["kuf_kfu_matvec"]
+        ctx.profile(False)
+        mine = torch.tensor([pm[0] / max(pm[1], 1) / max(n_local, 1)], dtype=torch.float64, device=device)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_row = [float(v.item()) for v in allr]
+        r_lo, r_hi = shard_rows_weighted(N, rank, [1.0 / v for v in per_row])
+        del op, Xd, yd, rhs
+        torch.cuda.empty_cache()
+        n_local = r_hi - r_lo
+        Xh, yh, Zh, Zd, Xd, yd, op, rhs = make_problem(n_local)
+        balance = {"ms_per_million_rows_even_split": [v * 1e6 for v in per_row], "rows_this_rank": n_local}
 
     # ---- resident leg: W warm-up iterations, then exactly K timed iterations ---------------------------------
     solve(op, rhs, max(args.warmup, 3))
@@ -622,7 +649,9 @@ def run_native(args):
             "config": {"workload": workload_string(args.workload), "operator": OPERATOR_STRING, "step": STEP_STRING,
                        "l2": l2_string(args.workload, world)},
             "run": {
-                "sharding": f"rows sharded over {world} GPU(s), {n_local} on rank 0; Z, Kuu and the CG vectors replicated",
+                "sharding": f"rows sharded over {world} GPU(s), {n_local} on rank 0; Z, Kuu and the CG vectors replicated"
+                            + ("; speed-weighted split from a calibration solve (--balance)" if balance else ""),
+                "balance": balance,
                 "allreduce": (("fused tail kernel: rank-ordered sum over NVLink peer memory (incl. each rank's 1/W share "
                                "of p Kuu) + CG vector update in one launch" if ctx.peer_allreduce
                                else "ncclAllReduce, then the fused combine + vector-update kernel")
@@ -659,6 +688,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--balance", action="store_true",
+                    help="N > 1: speed-weighted row split from a calibration solve instead of the even one (opt-in)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the c2 / c5 / 8-RHS secondary figures (N = 1, c3)")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the sharded-vs-1-rank parity check (N > 1)")
     ap.add_argument("--mode", default="cg", choices=["cg", "predict"],
