@@ -160,3 +160,17 @@ def test_sass_has_dmma_and_no_cpu_path():
         pytest.skip("cuobjdump unavailable")
     assert "DMMA" in out.stdout
     assert "sm_100a" in out.stdout
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/cggp_b200.h must compile as C99 (no C++-only constructs, no torch types)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    header = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "cggp_b200.h")
+    r = subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-pedantic", "-Werror", header],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
