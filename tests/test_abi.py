@@ -144,6 +144,9 @@ def test_no_cpu_fallback_and_no_oracle_in_product():
         with pytest.raises(cggp_b200._lib.CggpError):
             cggp_b200.conjugate_gradient(torch.eye(3, dtype=torch.float64), torch.ones(1, 3, dtype=torch.float64),
                                          None, 1e-6)
+        with pytest.raises(cggp_b200._lib.CggpError):
+            cggp_b200.CoverTree(None, (torch.zeros(4, 2, dtype=torch.float64), torch.zeros(4, 1, dtype=torch.float64)),
+                                spatial_resolution=0.5)
     # nothing under cggp_b200/ may import the oracle
     pkg = os.path.join(ROOT, "cggp_b200")
     for dirpath, _, files in os.walk(pkg):
